@@ -1,0 +1,114 @@
+"""Pin the CPU oracle (oracle/port.py) to golden vectors minted from the unmodified reference
+(tools/make_golden.py).  CPU only."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import golden, assert_parity
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+from oracle import port  # noqa: E402
+from radtxfr_b200 import synthetic as syn  # noqa: E402
+
+TIGHT = dict(rtol=1e-13, floor=1e-15)
+
+
+def test_weideman_coefficients_and_wofz():
+    g = golden("wofz.npz")
+    a, L = port.weideman_coeffs(24)
+    assert L == float(g["weideman_L"]) == 4.119534287814235
+    assert np.array_equal(a, g["weideman_a"])
+    wr, wi = port.hum1_wei(g["x"], g["y"])
+    assert np.array_equal(wr, g["wr"]) and np.array_equal(wi, g["wi"])
+    # SURVEY.md App. D spot values
+    assert wr[1] == 0.5331567079123801 and wi[1] == 0.2304882313844082
+    assert wr[7] == 0.0004246359021385162
+
+
+def test_profile_voigt():
+    g = golden("profile_voigt.npz")
+    for (sg0, gd, g0), sg, V in zip(g["cases"], g["sg"], g["V"]):
+        assert_parity(port.profile_voigt(sg0, gd, g0, sg), V, what="PROFILE_VOIGT", **TIGHT)
+    v = port.profile_voigt(1000.0, 0.0014544, 0.07, np.array([999, 999.99, 1000, 1000.5]))
+    assert_parity(v, [0.02217314446367562, 4.4550875777944, 4.5458685127508485, 0.0874149938033936], **TIGHT)
+
+
+def test_tips_and_line_kats():
+    g = golden("tips.npz")
+    for (m, i), row in zip(g["mi"], g["Q"]):
+        for T, q in zip(g["T"], row):
+            assert port.tips_q(int(m), int(i), float(T)) == q
+    assert port.tips_q(1, 1, 296.0) == 174.63820437890627
+    with pytest.raises(Exception):
+        port.tips_q(1, 1, 69.9)
+    with pytest.raises(Exception):
+        port.tips_q(1, 1, 3000.1)
+    S = port.line_strength(1e-22, 250.0, port.tips_q(1, 1, 250.0), port.tips_q(1, 1, 296.0), 1500.0, 1000.0)
+    assert S == float(g["S_kat"])
+    assert port.doppler_hwhm(1000.0, 296.0, 18.010565) == float(g["gammaD_kat"])
+    assert port.volume_concentration(1.0, 296.0) == float(g["volconc_kat"]) == 2.479371831717524e19
+
+
+def test_xsect_cases():
+    import make_golden as mg
+    g = golden("xsect.npz")
+    for name, seed, n, (lo, hi, npts), T, p, kw in mg.XS_CASES:
+        cols = syn.synthetic_lines(seed, n, lo - 25.0, hi + 25.0, 1)
+        grid = np.linspace(lo, hi, npts)
+        om, xs = port.absorption_coefficient_voigt(cols, T=T, p=p, OmegaGrid=grid, **kw)
+        assert np.array_equal(om, grid)
+        assert_parity(xs, g["xs_" + name], what="xsect " + name, **TIGHT)
+
+
+def _tud_kw():
+    import make_golden as mg
+    atm, tabs = mg.tud_inputs()
+    return tabs, dict(Zs=atm["Zs"], Ts=atm["Ts"], Ps=atm["Ps"], PLs=atm["PLs"], MFs_VAL=atm["MFs_VAL"],
+                      MFs_ID=atm["MFs_ID"], DVOUT=0.05)
+
+
+def test_tud():
+    g = golden("tud.npz")
+    tabs, kw = _tud_kw()
+    X, tau, Lu, Ld, OD = port.compute_tud(tabs, 700.0, 750.0, return_od_matrix=True, **kw)
+    assert np.array_equal(X, g["X"])
+    for a, b, w in ((tau, g["tau"], "tau"), (Lu, g["Lu"], "Lu"), (Ld, g["Ld"], "Ld")):
+        assert_parity(a, b, what=w, **TIGHT)
+    assert tau.min() < 0.1 and 0.2 < np.median(tau) < 0.8 and tau.max() <= 1.0   # optically interesting column
+    Z, T = kw["Zs"], kw["Ts"]
+    t2, u2, d2 = port.tud_from_od(X, OD, Z, T, N_angle=7, Altitudes=np.array([1.0, 10.0, 500.0, 3.0]))
+    assert t2.shape == (X.size, 4)
+    for a, b, w in ((t2, g["tau_alt"], "tau_alt"), (u2, g["Lu_alt"], "Lu_alt"), (d2, g["Ld_alt"], "Ld_alt")):
+        assert_parity(a, b, what=w, **TIGHT)
+    t3, u3, d3 = port.tud_from_od(X, OD, Z, T, N_angle=4, theta_r=0.6, returnOD=True)
+    for a, b, w in ((t3, g["tau_od"], "tau_od"), (u3, g["Lu_od"], "Lu_od"), (d3, g["Ld_od"], "Ld_od")):
+        assert_parity(a, b, what=w, **TIGHT)
+
+
+def test_sensor_model():
+    g = golden("sensor.npz")
+    X, Y1, Y2 = g["X"], g["Y1"], g["Y2"]
+    Xo, t1 = port.ils_mako_triangle(X, Y1)
+    assert np.array_equal(Xo, g["Xo"]) and Xo.size == 128
+    assert_parity(t1, g["tri1"], what="tri 1-D", **TIGHT)
+    assert_parity(port.ils_mako_triangle(X, Y2, returnX=False), g["tri2"], what="tri 2-D", **TIGHT)
+    Xr, t3 = port.ils_mako_triangle(X, Y2, resFactor=2, fwhm_sf=0.8, shift=0.3, scale=1.001)
+    assert np.array_equal(Xr, g["Xo_res"]) and Xr.size == 256
+    assert_parity(t3, g["tri_res"], what="tri resFactor", **TIGHT)
+    Xc, t4 = port.ils_mako_triangle(g["Xc"], Y2[:4001])
+    assert np.array_equal(Xc, g["Xo_clip"]) and Xc.size < 128
+    assert_parity(t4, g["tri_clip"], what="tri clipped", **TIGHT)
+    Xg, g1 = port.ils_mako_gauss(X, Y1)
+    assert np.array_equal(Xg, g["Xg"])
+    assert_parity(g1, g["gauss1"], what="gauss 1-D", **TIGHT)
+    assert_parity(port.ils_mako_gauss(X, Y2)[1], g["gauss2"], what="gauss 2-D", **TIGHT)
+    args = (g["Xo"], g["emis"], g["Ts"], g["tau"], g["La"], g["Ld"])
+    assert np.array_equal(port.apparent_radiance(*args), g["L0"])
+    L1, Ls1 = port.apparent_radiance(*args, dT=g["dT"], return_Ls=True)
+    assert np.array_equal(L1, g["L1"]) and np.array_equal(Ls1, g["Ls1"])
+    assert abs(port.planckian(500.0, 296.0)[0] - 14.36645756) < 5e-9
+    assert np.array_equal(port.planckian(np.linspace(700, 1500, 8001), np.array([280.0, 300.0])), g["planck_grid"])
+    assert np.array_equal(port.planckian(np.linspace(7.5, 13.5, 61), np.array([[280.0, 300.0], [310., 250.]]),
+                                         wavelength=True), g["planck_um"])

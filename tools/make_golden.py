@@ -1,0 +1,151 @@
+"""Mint golden vectors by executing the UNMODIFIED reference in the build container.
+
+    PYTHONDONTWRITEBYTECODE=1 python tools/make_golden.py
+
+Writes tests/golden/*.npz.  Each file stores the inputs (or the seeds that regenerate them through
+radtxfr_b200.synthetic) and the outputs of the reference function named in the file's `source` entry.
+The reference has no tests/golden vectors of its own; these files are the pins.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import ref_harness as R  # noqa: E402
+from radtxfr_b200 import synthetic as syn  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def save(name, **kw):
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **kw)
+    print("wrote %-28s %8d bytes" % (name, os.path.getsize(path)))
+
+
+def g_wofz():
+    h = R.hapi()
+    rng = np.random.default_rng(100)
+    x = np.concatenate([[0, 0.5, 1, 3, 7.5, 14, -2, 20, 100, 2000], rng.uniform(-30, 30, 400),
+                        rng.uniform(-16, 16, 200)])
+    y = np.concatenate([[1e-3, 0.5, 1, 0.1, 2, 0.5, 1e-5, 0.3, 40, 40], 10 ** rng.uniform(-6, 1.7, 400),
+                        10 ** rng.uniform(-3, 1.2, 200)])
+    wr, wi = h.hum1_wei(x.copy(), y.copy())
+    # Weideman coefficients as the reference derives them (misc/hapi.py:9816-9824)
+    N = 24; M = 2 * N; M2 = 2 * M
+    k = h.arange(-M + 1, M); L = h.sqrt(N / h.sqrt(2)); th = k * h.pi / M; t = L * h.tan(th / 2)
+    f = h.zeros(len(t) + 1); f[1:] = h.exp(-t ** 2) * (L ** 2 + t ** 2)
+    a = h.flipud((h.real(h.fft(h.fftshift(f))) / M2)[1:N + 1])
+    save("wofz.npz", source="misc/hapi.py:9833-9844 hum1_wei", x=x, y=y, wr=wr, wi=wi, weideman_a=a, weideman_L=L)
+
+
+def g_profile():
+    h = R.hapi()
+    cases = [(1000.0, 0.0014544, 0.07), (1000.0, 0.0014544, 0.0007), (800.3, 0.0011, 0.012),
+             (1299.9, 0.002, 1e-5), (950.0, 0.0013, 0.035)]
+    sgs, vals = [], []
+    for sg0, gd, g0 in cases:
+        sg = np.sort(np.concatenate([sg0 + np.linspace(-50 * max(gd, g0), 50 * max(gd, g0), 301),
+                                     [sg0, sg0 + 1e-4, sg0 - 0.01]]))
+        sgs.append(sg)
+        vals.append(h.PROFILE_VOIGT(sg0, gd, g0, sg)[0])
+    save("profile_voigt.npz", source="misc/hapi.py:10131-10140 PROFILE_VOIGT", cases=np.array(cases),
+         sg=np.array(sgs), V=np.array(vals))
+
+
+def g_tips():
+    h = R.hapi()
+    mi = [(1, 1), (1, 2), (1, 3), (1, 4), (2, 1), (2, 2), (2, 3), (2, 4), (3, 1), (3, 2), (3, 3), (4, 1), (5, 1),
+          (6, 1), (7, 1), (22, 1)]
+    Ts = np.array([70.0, 84.9, 85.0, 100.0, 180.3, 216.7, 250.0, 287.87, 296.0, 330.0, 1000.0, 2985.0, 2990.0, 3000.0])
+    Q = np.array([[h.PYTIPS(m, i, float(T)) for T in Ts] for (m, i) in mi])
+    S = h.EnvironmentDependency_Intensity(1e-22, 250., 296., h.PYTIPS(1, 1, 250.), h.PYTIPS(1, 1, 296.), 1500., 1000.)
+    m = h.molecularMass(1, 1) * 1.66053873e-27 * 1000
+    gd = h.sqrt(2 * h.cBolts * 296. * h.log(2) / m / h.cc ** 2) * 1000.
+    save("tips.npz", source="misc/hapi.py:10030 PYTIPS; :10169 EnvironmentDependency_Intensity", mi=np.array(mi),
+         T=Ts, Q=Q, S_kat=S, gammaD_kat=gd, volconc_kat=h.volumeConcentration(1.0, 296.0))
+
+
+XS_CASES = [
+    # name, seed, nlines, grid(lo,hi,n), T, p, kwargs
+    ("base", 10, 300, (800.0, 1300.0, 10001), 296.0, 1.0, {}),
+    ("cold_low", 11, 300, (800.0, 1300.0, 10001), 220.0, 0.01, {}),
+    ("mid", 12, 300, (900.0, 1000.0, 20001), 250.0, 0.3, {}),
+    ("top", 13, 200, (990.0, 1010.0, 20001), 225.53, 7.30 / 101325.0, {}),
+    ("self", 14, 200, (800.0, 1300.0, 5001), 296.0, 0.5, {"GammaL": "gamma_self"}),
+    ("mix", 15, 200, (800.0, 1300.0, 5001), 280.0, 0.8, {"Diluent": {"air": 0.7, "self": 0.3}}),
+    ("nonhitran", 16, 150, (800.0, 1300.0, 5001), 296.0, 1.0, {"HITRAN_units": False}),
+    ("wing_abs", 17, 150, (800.0, 1300.0, 5001), 296.0, 0.2, {"OmegaWing": 10.0}),
+    ("wing_hw", 18, 150, (800.0, 1300.0, 5001), 296.0, 1.0, {"OmegaWingHW": 5.0}),
+    ("thresh", 19, 300, (800.0, 1300.0, 5001), 296.0, 1.0, {"IntensityThreshold": 1e-24}),
+    ("components", 20, 300, (800.0, 1300.0, 5001), 296.0, 1.0, {"Components": [(1, 1), (1, 3, 0.5)]}),
+]
+
+
+def g_xsect():
+    out = {"source": "misc/hapi.py:10906-11141 absorptionCoefficient_Voigt", "names": np.array([c[0] for c in XS_CASES])}
+    for name, seed, n, (lo, hi, npts), T, p, kw in XS_CASES:
+        cols = syn.synthetic_lines(seed, n, lo - 25.0, hi + 25.0, 1)
+        grid = np.linspace(lo, hi, npts)
+        _, xs = R.ref_xsect(cols, T, p, grid, **kw)
+        out["xs_" + name] = xs
+    save("xsect.npz", **out)
+
+
+def tud_inputs():
+    atm = syn.standard_atmosphere()
+    tabs = {1: syn.synthetic_lines(30, 40, 690.0, 760.0, 1),
+            2: syn.synthetic_lines(31, 60, 690.0, 760.0, 2),
+            3: syn.synthetic_lines(32, 60, 690.0, 760.0, 3, (1, 2, 3), (0.8, 0.1, 0.1))}
+    return atm, tabs
+
+
+def g_tud():
+    atm, tabs = tud_inputs()
+    kw = dict(Zs=atm["Zs"], Ts=atm["Ts"], Ps=atm["Ps"], PLs=atm["PLs"], MFs_VAL=atm["MFs_VAL"], MFs_ID=atm["MFs_ID"],
+              DVOUT=0.05)
+    X, tau, Lu, Ld = R.ref_tud(tabs, 700.0, 750.0, **kw)
+    X2, tau2, Lu2, Ld2 = R.ref_tud(tabs, 700.0, 750.0, Altitudes=np.array([1.0, 10.0, 500.0, 3.0]), N_angle=7, **kw)
+    X3, tau3, Lu3, Ld3 = R.ref_tud(tabs, 700.0, 750.0, returnOD=True, theta_r=0.6, N_angle=4, **kw)
+    save("tud.npz", source="radiative_transfer.py:274-392 compute_TUD (+App. B.1 OD wiring via hapi)",
+         X=X, tau=tau, Lu=Lu, Ld=Ld, tau_alt=tau2, Lu_alt=Lu2, Ld_alt=Ld2, tau_od=tau3, Lu_od=Lu3, Ld_od=Ld3)
+
+
+def g_sensor():
+    r = R.rt()
+    rng = np.random.default_rng(40)
+    X = np.linspace(700.0, 1400.0, 7001)
+    Y1 = rng.uniform(0, 1, X.size)
+    Y2 = rng.uniform(0, 50, (X.size, 5))
+    Xo, t1 = r.ILS_MAKO(X, Y1)
+    _, t2 = r.ILS_MAKO(X, Y2)
+    Xo_r, t3 = r.ILS_MAKO(X, Y2, resFactor=2, fwhm_sf=0.8, shift=0.3, scale=1.001)
+    Xc = np.linspace(800.0, 1200.0, 4001)
+    Xo_c, t4 = r.ILS_MAKO(Xc, Y2[:4001])
+    g = R.ils_gauss()
+    Xg, g1 = g.ILS_MAKO(X, Y1)
+    _, g2 = g.ILS_MAKO(X, Y2)
+    nE, nA = 6, 4
+    Xb = Xo
+    emis = syn.synthetic_emissivities(41, nE, Xb)
+    Ts = rng.uniform(270, 320, nA)
+    tau = rng.uniform(0.2, 1.0, (Xb.size, nA)); La = rng.uniform(0, 300, (Xb.size, nA)); Ld = rng.uniform(0, 600, (Xb.size, nA))
+    dT = np.arange(-10, 10.5, 2.5)
+    L0 = r.compute_LWIR_apparent_radiance(Xb, emis, Ts, tau, La, Ld)
+    L1, Ls1 = r.compute_LWIR_apparent_radiance(Xb, emis, Ts, tau, La, Ld, dT=dT, return_Ls=True)
+    Pl = r.planckian(np.linspace(700, 1500, 8001), np.array([280.0, 300.0]))
+    Pw = r.planckian(np.linspace(7.5, 13.5, 61), np.array([[280.0, 300.0], [310., 250.]]), wavelength=True)
+    save("sensor.npz", source="radiative_transfer.py:1072-1263 ILS_MAKO; ILS_MAKO.py:2-35; :1017-1069; :792-848",
+         X=X, Y1=Y1, Y2=Y2, Xo=Xo, tri1=t1, tri2=t2, Xo_res=Xo_r, tri_res=t3, Xc=Xc, Xo_clip=Xo_c, tri_clip=t4,
+         Xg=Xg, gauss1=g1, gauss2=g2, emis=emis, Ts=Ts, tau=tau, La=La, Ld=Ld, dT=dT, L0=L0, L1=L1, Ls1=Ls1,
+         planck_kat=r.planckian(500., 296.), planck_grid=Pl, planck_um=Pw)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor"]
+    for w in which:
+        globals()["g_" + w]()
