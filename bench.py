@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on B200:  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): StandardAtmosphere.csv profile (66 layers), H2O+CO2+O3 absorption and
+layer-integrated TUD over 700-1500 cm^-1 at 0.001 cm^-1 (800 000 grid points), N_angle=30.  One "step" = one TUD
+spectrum of one atmosphere: Voigt line sum for all 66 layers (optical depth) + layer integration.  Each step
+uses a different perturbed atmosphere (config 3's generator), so nothing can be cached between steps.  Lines are
+synthetic (seed 1: 30 000 H2O + 80 000 CO2 + 100 000 O3) because the reference ships no line data.
+
+Metric: Voigt line-gridpoint evals/s, where an eval is one (line, grid point) pair inside the reference's wing
+window (misc/hapi.py:11131-11134), counted exactly on the device outside the timed region.  The whole step
+(including the TUD integration) is inside the timed region; `tud_spectra_per_s` reports the same time as
+spectra/s.  N>1: one process per GPU (torchrun), each rank integrates its own atmospheres (weak scaling) and the
+ranks all-gather the (tau, Lu, Ld) spectra every step -- the path's one exchange.
+
+`--impl reference` times the CPU oracle port (oracle/port.py: the reference's per-line numpy algorithm; the
+reference itself is pure Python and cannot travel to the GPU box) on all host cores over a bounded sample of the
+same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+XMIN, XMAX, DV = 700.0, 1500.0, 0.001
+N_ANGLE = 30
+METRIC = "voigt_line_gridpoint_evals_per_s"
+UNIT = "evals/s"
+WORKLOAD = ("config2: StandardAtmosphere 66 layers, H2O+CO2+O3 (210k synthetic lines, seed 1), TUD over "
+            "700-1500 cm^-1 @0.001 (800000 pts), N_angle=30")
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def _cpu_task(args):
+    """One CPU work item: Voigt sum of a slice of one molecule's lines for one layer, by the oracle port."""
+    mol, lo, hi, T, p = args
+    from oracle import port
+    from radtxfr_b200 import synthetic as syn
+    g = _cpu_task.__dict__
+    if "tabs" not in g:
+        g["tabs"] = syn.config2_tables()
+        g["X"] = port.make_spectral_axis(XMIN, XMAX, DV)
+    t = g["tabs"][mol]
+    cols = {k: v[lo:hi] for k, v in t.items()}
+    _, xs, ev, evw = port.absorption_coefficient_voigt(cols, T=T, p=p, OmegaGrid=g["X"], return_evals=True)
+    return ev, evw, float(xs.sum())
+
+
+def cpu_sample_tasks(lines_per_layer, layers=(0, 22, 44, 65), chunk=250, seed=0):
+    from radtxfr_b200 import synthetic as syn
+    atm = syn.standard_atmosphere()
+    sizes = {1: 30000, 2: 80000, 3: 100000}
+    total = sum(sizes.values())
+    tasks = []
+    rng = np.random.default_rng(seed)
+    for L in layers:
+        for mol, n in sizes.items():
+            want = max(chunk, int(round(lines_per_layer * n / total)))
+            nchunks = max(1, want // chunk)
+            starts = rng.choice(max(1, n // chunk), size=min(nchunks, n // chunk), replace=False) * chunk
+            for s in starts:
+                tasks.append((mol, int(s), int(min(n, s + chunk)), float(atm["Ts"][L]), float(atm["Ps"][L] / 101325.0)))
+    return tasks
+
+
+def run_cpu_sample(lines_per_layer, cores, seed=0):
+    """Returns (evals, seconds, n_tasks): the oracle port over a stratified sample, fanned over `cores`
+    processes (the reference's own idiom: multiprocessing.Pool, Generate_LWIR_TUD.py:137-149)."""
+    import multiprocessing as mp
+    tasks = cpu_sample_tasks(lines_per_layer, seed=seed)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_task, tasks[:cores])          # warm the workers (imports, table generation)
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_task, tasks, chunksize=1)
+        dt = time.perf_counter() - t0
+    return sum(r[0] for r in res), dt, len(tasks)
+
+
+def cpu_baseline(cores=None, budget_lines_per_core=2000):
+    cores = cores or os.cpu_count() or 1
+    lines = min(210000, budget_lines_per_core * cores)
+    ev, dt, nt = run_cpu_sample(lines, cores)
+    return {"value": ev / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle/port.py Voigt sum, layers 0/22/44/65 x ~%d lines x full 800000-pt grid = %d evals "
+                      "in %.1f s over %d processes" % (lines, ev, dt, cores)}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    lines = min(210000, 2000 * cores)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        ev, dt, _ = run_cpu_sample(lines, cores, seed=i)
+        if i >= args.warmup:
+            vals.append((ev, dt))
+    ev = sum(v[0] for v in vals)
+    dt = sum(v[1] for v in vals)
+    val = ev / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": "layers 0/22/44/65 x ~%d lines per step" % lines},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d evals in %.1f s over %d steps" % (ev, dt, args.steps)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for t, ln in self.rows:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            if t0 - 0.05 <= t <= t1 + 0.15:
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sample inside the timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline()        # spawned workers; runs before any kernel of ours is in flight
+
+    from radtxfr_b200 import engine, radiative_transfer as rt, synthetic as syn
+    atm = syn.standard_atmosphere()
+    tabs = syn.config2_tables()
+    t_ing = time.perf_counter()
+    db = engine.LineDB([tabs[m] for m in sorted(tabs)], dev)
+    ingest_s = time.perf_counter() - t_ing
+    X = rt.make_spectral_axis(XMIN, XMAX, DV)
+    nX, nL = X.size, atm["Ts"].size
+    grid = torch.from_numpy(X).to(dev)
+    nsteps = args.warmup + args.steps
+    Ts_all, MF_all = syn.perturbed_atmospheres(1000 + rank, nsteps)
+    Ts_all[0], MF_all[0] = atm["Ts"], atm["MFs_VAL"]          # first (warm-up) step is the unperturbed profile
+    states = []
+    for i in range(nsteps):
+        p, w = rt.layer_weights(db, Ts_all[i], atm["Ps"], atm["PLs"], MF_all[i], atm["MFs_ID"])
+        states.append((torch.from_numpy(Ts_all[i].copy()).to(dev), torch.from_numpy(np.ascontiguousarray(p)).to(dev),
+                       torch.from_numpy(w).to(dev)))
+    od = torch.empty((nL, nX), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world, 3, nX), dtype=torch.float64, device=dev) if world > 1 else None
+    h0 = engine.default_handle(dev)
+
+    def step(i):
+        T, p, w = states[i]
+        db.voigt_sum(T, p, w, grid, out=od, flags=args.flags)
+        tau, lu, ld = engine.tud(od, T[None, :], grid, atm["Zs"], [500.0], [1.0], N_ANGLE)
+        if world > 1:
+            mine = torch.stack([tau.reshape(-1), lu.reshape(-1), ld.reshape(-1)])
+            dist.all_gather_into_tensor(gathered, mine)
+        return tau, lu, ld
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    # exact eval counts of the timed steps (outside the timed region)
+    E = Ew = 0
+    for i in range(args.warmup, nsteps):
+        T, p, w = states[i]
+        e, ew = db.count_evals(T, p, w, grid)
+        E += e; Ew += ew
+    launches0 = db.handle.launches() + h0.launches()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ev[0].record()
+    for k in range(args.steps):
+        i = args.warmup + k
+        T, p, w = states[i]
+        db.voigt_sum(T, p, w, grid, out=od, flags=args.flags)
+        ev[2 * k + 1].record()
+        tau, lu, ld = engine.tud(od, T[None, :], grid, atm["Zs"], [500.0], [1.0], N_ANGLE)
+        if world > 1:
+            mine = torch.stack([tau.reshape(-1), lu.reshape(-1), ld.reshape(-1)])
+            dist.all_gather_into_tensor(gathered, mine)
+        ev[2 * k + 2].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t1 = time.perf_counter()
+    ms_total = ev[0].elapsed_time(ev[-1])
+    ms_voigt = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps))
+    ms_tud = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps))
+    launches = db.handle.launches() + h0.launches() - launches0
+    tot = torch.tensor([ms_total, float(E), float(Ew), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total = mx[0].item(); E_all, Ew_all, launches_all = sm[1].item(), sm[2].item(), sm[3].item()
+    else:
+        E_all, Ew_all, launches_all = float(E), float(Ew), float(launches)
+    clk = clocks.stop(t0, t1) if rank == 0 else None
+
+    # ---- end-to-end through the reference-facing API: numpy in, numpy out, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        opts = dict(rt.options)
+        opts["LINE_DB"] = db
+        kw = dict(Zs=atm["Zs"], Ps=atm["Ps"], PLs=atm["PLs"], MFs_ID=atm["MFs_ID"], DVOUT=DV, N_angle=N_ANGLE)
+        rt.compute_TUD(XMIN, XMAX, opts=dict(opts), Ts=Ts_all[0], MFs_VAL=MF_all[0], **kw)   # warm
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0e = time.perf_counter()
+        for k in range(args.steps):
+            i = args.warmup + k
+            Xo, tau_h, lu_h, ld_h = rt.compute_TUD(XMIN, XMAX, opts=dict(opts), Ts=Ts_all[i], MFs_VAL=MF_all[i], **kw)
+        torch.cuda.synchronize()
+        dte = time.perf_counter() - t0e
+        if world > 1:
+            t = torch.tensor([dte], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dte = t.item()
+        h2d = 8 * (nX + 2 * nL + nL * db.n_iso)
+        d2h = 8 * 3 * nX
+        e2e = {"value": E_all / dte, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": 1e3 * dte / args.steps,
+               "api": "radtxfr_b200.radiative_transfer.compute_TUD (numpy in, numpy out; line table resident)"}
+
+    if rank == 0:
+        secs = ms_total * 1e-3
+        value = E_all / secs
+        flops = 16.0 * (E - Ew) + 200.0 * Ew            # algorithmic flops, SURVEY.md 8d (rank 0's steps)
+        peak = db.handle.fp64_peak()
+        achieved = flops / (ms_voigt * 1e-3)
+        prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        traffic = None
+        if os.path.isfile(prof):
+            try:
+                traffic = json.load(open(prof)).get("voigt_tile_kernel_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "atmospheres_per_step_per_gpu": 1,
+                       "l2": "each step writes and re-reads a 422 MB optical-depth buffer (> 126 MB L2); a "
+                             "different atmosphere every step",
+                       "parallelism": "1 process per GPU, atmospheres sharded, one all_gather of (tau,Lu,Ld) per step"
+                       if world > 1 else "single GPU"},
+            "tud_spectra_per_s": world * args.steps / secs,
+            "evals_per_step": E / args.steps, "weideman_fraction": Ew / max(1, E),
+            "ms_voigt_per_step": ms_voigt / args.steps, "ms_tud_per_step": ms_tud / args.steps,
+            "ingest_s": ingest_s,
+            "roofline": {"bound": "fp64", "kernel": "voigt_tile_kernel", "achieved": achieved / 1e12,
+                         "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "measured in this run: dependent-free DFMA loop (rtx_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 figure",
+                         "flops_model": "16 flop per asymptote-branch eval, 200 per Weideman eval (SURVEY.md 8d)",
+                         "hbm_note": "the kernel's algorithmic HBM traffic is 8 B per (grid point, layer) written "
+                                     "= 422 MB per step: <1% of the step at the measured 6.4 TB/s"},
+            "clocks": clk, "gpu_launches": int(launches_all),
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--flags", type=int, default=0, help="RTX_VOIGT_* flags for rtx_voigt_sum")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        if args.warmup < 3:
+            print("note: fewer than 3 warm-up steps requested", file=sys.stderr)
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

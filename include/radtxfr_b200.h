@@ -1,0 +1,176 @@
+/*
+ * radtxfr_b200 -- C ABI of the B200-native line-by-line radiative-transfer hot path.
+ *
+ * The reference (westi024/RadTxfr) is pure Python and has no FFI of its own; its boundary for this
+ * path is the Python function surface.  Each entry point below names the reference
+ * code it replaces.  The Python shim in radtxfr_b200/ binds these with ctypes and mirrors the
+ * reference's function names and arguments; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative RTX_E_* code on failure;
+ *     rtx_last_error() returns a thread-local message for the last failure in this thread;
+ *   - "dev" pointers are device memory owned by the caller (for example torch tensor storage),
+ *     "host" pointers are ordinary host memory; all arrays are dense, C order, double unless noted;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); work is
+ *     enqueued on it and the call returns without synchronising unless stated otherwise;
+ *   - no hidden global state beyond the opaque handle; a handle is bound to one device and may be
+ *     used from one thread at a time.
+ */
+#ifndef RADTXFR_B200_H
+#define RADTXFR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTX_OK 0
+#define RTX_E_INVALID -1   /* bad argument */
+#define RTX_E_CUDA -2      /* CUDA runtime error, see rtx_last_error() */
+#define RTX_E_STATE -3     /* call order (e.g. no lines uploaded) */
+#define RTX_E_RANGE -4     /* value outside the reference's domain (e.g. TIPS 70..3000 K) */
+
+#define RTX_TIPS_NPT 119   /* TIPS-2011 temperature nodes, misc/hapi.py:5401-5415 */
+#define RTX_MAX_ANGLES 64  /* compute_TUD N_angle limit of this build (reference default 30) */
+#define RTX_MAX_LAYERS 256 /* layers per atmosphere (reference table: 66) */
+#define RTX_MAX_ALT 32     /* sensor altitudes per call */
+#define RTX_MAX_MU 8       /* view angles per call */
+
+typedef struct rtx_handle rtx_handle;
+
+const char* rtx_last_error(void);
+int rtx_version(void);
+/* Number of SMs / device name of the handle's device (for grid sizing reports). */
+int rtx_device_info(rtx_handle* h, int* sm_count, char* name, int name_len);
+
+int rtx_create(int device, rtx_handle** out);
+int rtx_destroy(rtx_handle* h);
+
+/* ---- plain device-memory helpers so that a caller without torch can drive the library ---- */
+int rtx_malloc(rtx_handle* h, uint64_t bytes, void** dev);
+int rtx_free(rtx_handle* h, void* dev);
+int rtx_memcpy_h2d(rtx_handle* h, void* dev, const void* host, uint64_t bytes, void* stream);
+int rtx_memcpy_d2h(rtx_handle* h, void* host, const void* dev, uint64_t bytes, void* stream);
+int rtx_stream_sync(rtx_handle* h, void* stream);
+
+/* ---- subsystem 1: ingest ------------------------------------------------------------------
+ * Isotopologue table: replaces the ISO / TIPS_ISO_HASH lookups of misc/hapi.py:3372-3497,
+ * 5088-5124, 9568-9582.  mass [g/mol], q_table[n_iso][RTX_TIPS_NPT] (float32 values promoted to
+ * double) on the temperature nodes tips_T[RTX_TIPS_NPT].  Host pointers, copied. */
+int rtx_set_iso_table(rtx_handle* h, int n_iso, const double* mass, const double* tips_T,
+                      const double* q_table);
+
+/* Line table: replaces hapi's LOCAL_TABLE_CACHE[table]['data'] dict-of-lists (misc/hapi.py:438-463;
+ * column meaning :497-517).  Host pointers, n rows in any order; the library sorts by line centre,
+ * precomputes the reference-temperature part of S(T) (misc/hapi.py:10173), pads and uploads SoA
+ * device buffers.  iso_idx[i] indexes the isotopologue table.  Optional columns may be NULL:
+ * gamma_self, n_self (NULL or 0 -> n_air, misc/hapi.py:11104-11109), delta_self, deltap_air,
+ * deltap_self (NULL -> 0, :11097-11125). */
+int rtx_lines_upload(rtx_handle* h, int64_t n, const double* nu, const double* sw, const double* elower,
+                     const double* gamma_air, const double* gamma_self, const double* n_air,
+                     const double* n_self, const double* delta_air, const double* deltap_air,
+                     const double* delta_self, const double* deltap_self, const int32_t* iso_idx);
+int rtx_lines_count(rtx_handle* h, int64_t* n);
+
+/* ---- subsystem 2: Voigt line sum ----------------------------------------------------------
+ * Replaces the line loop of absorptionCoefficient_Voigt (misc/hapi.py:11050-11138) together with
+ * PROFILE_VOIGT/pcqsdhc PART1/hum1_wei (misc/hapi.py:10131-10140, 9910-9915, 9833-9844), for
+ * n_states homogeneous (T, p) states at once (layers of one or many atmospheres):
+ *
+ *   out[s][i] = sum over lines  weight[s][iso(line)] * S_line(T_s) * V(grid[i]; line, T_s, p_s)
+ *
+ * restricted to the reference's window  nu-W < grid[i] <= nu+W,  W = max(wing_abs, wing_hw*Gamma0,
+ * wing_hw*GammaD)  (misc/hapi.py:11131-11134).  Lines with S(T) < s_threshold or weight 0 are
+ * skipped (:11066, :11082).
+ *   T_dev, p_dev     [n_states]          K, atm
+ *   weight_dev       [n_states][n_iso]   factor*abundance/natural_abundance (:11136-11138), times the
+ *                                        column amount when optical depth is wanted
+ *   x_air, x_self    diluent fractions (Diluent={'air':..,'self':..}, :11090-11128)
+ *   grid_dev         [nx] sorted ascending (any spacing);   out_dev [n_states][nx], overwritten
+ *   flags            RTX_VOIGT_* bits */
+#define RTX_VOIGT_DEFAULT 0
+#define RTX_VOIGT_FAST_RCP 1 /* one Newton step fewer in the reciprocal (rel. err ~1e-12 per term) */
+#define RTX_VOIGT_TILE_SHIFT 8 /* bits 8..11: force 256*K grid points per CTA, K in {1,2,4,8} (0 = automatic) */
+int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, const double* p_dev,
+                  const double* weight_dev, double x_air, double x_self, double wing_abs, double wing_hw,
+                  double s_threshold, const double* grid_dev, int64_t nx, double* out_dev, int flags,
+                  void* stream);
+
+/* Exact count of (line, grid point) pairs inside the reference's window ("evals") and
+ * of those in the Weideman region |x|+y<15, for the same arguments; counts_dev[2] (uint64, device)
+ * is overwritten. */
+int rtx_voigt_count(rtx_handle* h, int n_states, const double* T_dev, const double* p_dev,
+                    const double* weight_dev, double x_air, double x_self, double wing_abs, double wing_hw,
+                    double s_threshold, const double* grid_dev, int64_t nx, uint64_t* counts_dev,
+                    void* stream);
+
+/* Q(T) for every isotopologue: replaces PYTIPS (misc/hapi.py:10030, 5311-5388).  T_dev[n],
+ * q_dev[n][n_iso].  Temperatures outside 70..3000 K give NaN (the shim raises like hapi :9571). */
+int rtx_tips(rtx_handle* h, int n, const double* T_dev, double* q_dev, void* stream);
+
+/* ---- subsystem 3: layer integration (TUD) ------------------------------------------------
+ * Replaces the numpy body of compute_TUD after the OD loop (radiative_transfer.py:340-392) for
+ * n_atm atmospheres that share the layer altitudes Z:
+ *   od_dev   [n_atm][n_layers][nx]  optical depth per layer (layer-major, as rtx_voigt_sum writes it)
+ *   T_dev    [n_atm][n_layers]      layer temperatures;   grid_dev [nx]
+ *   Z_host   [n_layers] layer altitudes; alt_host [n_alt] sensor altitudes; mu_host [n_mu] = 1/cos(theta_r)
+ *   tau_dev, lu_dev [n_atm][nx][n_alt][n_mu];  ld_dev [n_atm][nx]
+ * Quirks of the reference are kept: layer mask Z<=alt (:348), upwelling over the first count(mask)
+ * layers (:353-356), downwelling over the layer count of the LAST altitude (:353,:370);
+ * return_od!=0 stores the optical-depth sum instead of the transmittance (:349-350). */
+int rtx_tud(rtx_handle* h, int n_atm, int n_layers, const double* od_dev, const double* T_dev,
+            const double* grid_dev, int64_t nx, const double* Z_host, const double* alt_host, int n_alt,
+            const double* mu_host, int n_mu, int n_angle, int return_od, double* tau_dev, double* lu_dev,
+            double* ld_dev, void* stream);
+
+/* planckian(X, T) in wavenumber or wavelength form (radiative_transfer.py:792-848):
+ * out_dev[nx][nT].  wavelength!=0 selects the micrometre branch (the mean(X)<50 heuristic lives in
+ * the shim). */
+int rtx_planck(rtx_handle* h, const double* X_dev, int64_t nx, const double* T_dev, int64_t nT,
+               int wavelength, double* out_dev, void* stream);
+
+/* ---- subsystem 3b: apparent radiance -----------------------------------------------------
+ * compute_LWIR_apparent_radiance (radiative_transfer.py:1017-1069):
+ *   L[x][e][a][t] = tau[x][a]*(emis[x][e]*B(X[x], Ts[a]+dT[t]) + (1-emis[x][e])*Ld[x][a]) + La[x][a]
+ * dT_dev may be NULL (n_dT is then 1 and the t axis is absent).  ls_dev (surface-leaving radiance,
+ * return_Ls=True) may be NULL. */
+int rtx_apparent_radiance(rtx_handle* h, const double* X_dev, int64_t nx, const double* emis_dev, int64_t n_emis,
+                          const double* Ts_dev, int64_t n_atm, const double* tau_dev, const double* la_dev,
+                          const double* ld_dev, const double* dT_dev, int64_t n_dT, double* L_dev,
+                          double* ls_dev, void* stream);
+
+/* Per-pixel mixed-material variant: the inner loop of LWIR_HSI_gen (LWIR_HSI_Generator.py:148-166).
+ * For pixel k: em = sum_m frac[k][m]*emis[mat[k][m]][:],  L[k][x] = tau[atm[k]][x]*(em*B(X[x],T[k]) +
+ * (1-em)*Ld[atm[k]][x]) + La[atm[k]][x].   emis_dev [n_emis][nx], tau/la/ld [n_atm][nx] (band-minor, the
+ * layout of that script), L_dev [n_pix][nx]. */
+int rtx_hsi_pixels(rtx_handle* h, const double* X_dev, int64_t nx, const double* emis_dev, int64_t n_emis,
+                   const double* tau_dev, const double* la_dev, const double* ld_dev, int64_t n_atm,
+                   int64_t n_pix, const int32_t* atm_idx_dev, const double* T_pix_dev, int n_mix,
+                   const int32_t* mat_idx_dev, const double* frac_dev, double* L_dev, void* stream);
+
+/* ---- subsystem 4: MAKO instrument line shape ---------------------------------------------
+ * The weighted-mean resampling at the heart of ILS_MAKO (triangle: radiative_transfer.py:1236-1256;
+ * Gaussian: ILS_MAKO.py:24-34).  Band centres and widths are prepared by the shim exactly as the
+ * reference does (sort, clip, gradient; :1226-1241).
+ *   mode 0: w = max(0, 1-|x-c_b|/s_b);  mode 1: w = exp(-0.5((x-c_b)/s_b)^2)/(s_b*sqrt(2pi))
+ *   X_dev [nx] ascending, Y_dev [nx][ns], centre_dev/width_dev [n_bands], out_dev [n_bands][ns]
+ *   out[b][s] = sum_x w*Y / sum_x w */
+int rtx_ils_apply(rtx_handle* h, int mode, const double* X_dev, int64_t nx, const double* Y_dev, int64_t ns,
+                  int n_bands, const double* centre_dev, const double* width_dev, double* out_dev,
+                  void* stream);
+
+/* ---- measurement helpers -------------------------------------------------------------------
+ * Dependent-free DFMA loop: writes the achieved FP64 FMA rate [flop/s] of the handle's device.
+ * Used by bench.py as the measured denominator of the Voigt kernel's FP64 roofline. */
+int rtx_measure_fp64_peak(rtx_handle* h, double* flops_per_s);
+/* The 24 Weideman coefficients the kernels use (highest power first), for the unit test that regenerates them
+ * from the FFT recipe of misc/hapi.py:9816-9824.  Host pointer, 24 doubles. */
+int rtx_weideman_coeffs(double* out24);
+/* Number of kernels this library has launched on this handle since creation. */
+int rtx_launch_count(rtx_handle* h, uint64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADTXFR_B200_H */

@@ -1,0 +1,179 @@
+// Subsystems 3b and 4: apparent radiance and the MAKO instrument line shape.
+//
+//   rtx_ils_apply          ILS_MAKO weighted-mean resampling (radiative_transfer.py:1236-1256 triangle,
+//                          ILS_MAKO.py:24-34 Gaussian) as a banded reduction: the reference materialises a
+//                          dense (nX, nB) weight matrix of which <=3 % is non-zero; here one
+//                          CTA owns one (band, block of spectra), walks only the band's support and forms the
+//                          weights on the fly.  HBM-bound: each spectrum sample in the support is read once
+//                          per band that covers it.
+//   rtx_apparent_radiance  compute_LWIR_apparent_radiance (radiative_transfer.py:1017-1069)
+//   rtx_hsi_pixels         per-pixel mixed-material radiance (LWIR_HSI_Generator.py:148-166)
+#include <math.h>
+
+#include "rtx_common.cuh"
+
+namespace {
+
+constexpr int ILS_THREADS = 256;
+constexpr int ILS_SBLK = 8;   // spectra per CTA
+
+template <int MODE>
+__global__ void __launch_bounds__(ILS_THREADS) ils_kernel(const double* __restrict__ X, int64_t nx,
+                                                          const double* __restrict__ Y, int64_t ns,
+                                                          const double* __restrict__ centre,
+                                                          const double* __restrict__ width, double* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int64_t s0 = (int64_t)blockIdx.y * ILS_SBLK;
+  const int nsb = (int)min((int64_t)ILS_SBLK, ns - s0);
+  const double c = centre[b], sg = width[b];
+  __shared__ int64_t s_range[2];
+  if (threadIdx.x == 0) {
+    if (MODE == 0) {   // triangle: w>0 only for |x-c|<s
+      s_range[0] = bisect_left_dev64(X, nx, c - sg);
+      s_range[1] = bisect_right_dev64(X, nx, c + sg);
+    } else {
+      s_range[0] = 0; s_range[1] = nx;
+    }
+  }
+  __syncthreads();
+  const int64_t lo = s_range[0], hi = s_range[1];
+  double acc[ILS_SBLK];
+#pragma unroll
+  for (int k = 0; k < ILS_SBLK; ++k) acc[k] = 0.0;
+  double wsum = 0.0;
+  const double gnorm = sg * 2.5066282746310002;   // s*sqrt(2*pi) as numpy evaluates it
+  for (int64_t i = lo + threadIdx.x; i < hi; i += ILS_THREADS) {
+    const double x = X[i];
+    double w;
+    if (MODE == 0) {
+      w = 1.0 - fabs(x - c) / sg;                 // tri(), radiative_transfer.py:1236-1239
+      if (w < 0.0) w = 0.0;
+    } else {
+      const double u = (x - c) / sg;
+      w = exp(-0.5 * (u * u)) / gnorm;            // g(), ILS_MAKO.py:24
+    }
+    wsum += w;
+    const double* __restrict__ yr = Y + i * ns + s0;
+#pragma unroll
+    for (int k = 0; k < ILS_SBLK; ++k)
+      if (k < nsb) acc[k] = fma(w, yr[k], acc[k]);
+  }
+  // block reduction (fixed order -> deterministic)
+  __shared__ double s_red[ILS_THREADS / 32][ILS_SBLK + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wsum += __shfl_down_sync(0xffffffffu, wsum, o);
+#pragma unroll
+    for (int k = 0; k < ILS_SBLK; ++k) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < ILS_SBLK; ++k) s_red[warp][k] = acc[k];
+    s_red[warp][ILS_SBLK] = wsum;
+  }
+  __syncthreads();
+  if (threadIdx.x < nsb) {
+    double a = 0.0, wt = 0.0;
+    for (int q = 0; q < ILS_THREADS / 32; ++q) { a += s_red[q][threadIdx.x]; wt += s_red[q][ILS_SBLK]; }
+    out[(int64_t)b * ns + s0 + threadIdx.x] = a / wt;   // Y_out = sum(ILS*Y)/N
+  }
+}
+
+// thread per (x, a, t): one Planck evaluation shared by all emissivities
+__global__ void apparent_kernel(const double* __restrict__ X, int64_t nx, const double* __restrict__ emis,
+                                int64_t nE, const double* __restrict__ Ts, int64_t nA,
+                                const double* __restrict__ tau, const double* __restrict__ la,
+                                const double* __restrict__ ld, const double* __restrict__ dT, int64_t nT,
+                                double* __restrict__ L, double* __restrict__ Ls) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nx * nA * nT) return;
+  const int64_t t = i % nT, a = (i / nT) % nA, x = i / (nT * nA);
+  const double T = dT ? Ts[a] + dT[t] : Ts[a];          // T_ = Ts[:,None] + dT[None,:]
+  const double B = planck_wn(X[x], T);
+  const double tu = tau[x * nA + a], up = la[x * nA + a], dn = ld[x * nA + a];
+  for (int64_t e = 0; e < nE; ++e) {
+    const double em = emis[x * nE + e];
+    const double ls = em * B + (1.0 - em) * dn;         // Ls = em*B + (1-em)*Ld
+    const int64_t o = ((x * nE + e) * nA + a) * nT + t;
+    L[o] = tu * ls + up;                                // L = tau*Ls + La
+    if (Ls) Ls[o] = ls;
+  }
+}
+
+__global__ void hsi_kernel(const double* __restrict__ X, int64_t nx, const double* __restrict__ emis,
+                           const double* __restrict__ tau, const double* __restrict__ la,
+                           const double* __restrict__ ld, int64_t n_pix, const int32_t* __restrict__ atm,
+                           const double* __restrict__ Tp, int n_mix, const int32_t* __restrict__ mat,
+                           const double* __restrict__ frac, double* __restrict__ L) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pix * nx) return;
+  const int64_t k = i / nx, x = i % nx;
+  double em = 0.0;
+  for (int m = 0; m < n_mix; ++m) em += frac[k * n_mix + m] * emis[(int64_t)mat[k * n_mix + m] * nx + x];
+  const int64_t ar = (int64_t)atm[k] * nx + x;
+  const double B = planck_wn(X[x], Tp[k]);
+  const double ls = em * B + (1.0 - em) * ld[ar];
+  L[i] = tau[ar] * ls + la[ar];
+}
+
+}  // namespace
+
+extern "C" int rtx_ils_apply(rtx_handle* h, int mode, const double* X_dev, int64_t nx, const double* Y_dev, int64_t ns,
+                             int n_bands, const double* centre_dev, const double* width_dev, double* out_dev,
+                             void* stream) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  RTX_REQUIRE(mode == 0 || mode == 1, "rtx_ils_apply: mode must be 0 (triangle) or 1 (Gaussian)");
+  RTX_REQUIRE(nx > 0 && ns > 0 && n_bands >= 0, "rtx_ils_apply: bad sizes");
+  if (n_bands == 0) return RTX_OK;
+  RTX_REQUIRE(X_dev && Y_dev && centre_dev && width_dev && out_dev, "rtx_ils_apply: null pointer");
+  const int64_t sblocks = (ns + ILS_SBLK - 1) / ILS_SBLK;
+  RTX_REQUIRE(sblocks <= 65535, "rtx_ils_apply: too many spectra for one call (max 524280)");
+  DeviceGuard guard(h->device);
+  dim3 grid((unsigned)n_bands, (unsigned)sblocks);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == 0) ils_kernel<0><<<grid, ILS_THREADS, 0, st>>>(X_dev, nx, Y_dev, ns, centre_dev, width_dev, out_dev);
+  else ils_kernel<1><<<grid, ILS_THREADS, 0, st>>>(X_dev, nx, Y_dev, ns, centre_dev, width_dev, out_dev);
+  RTX_CUDA(cudaGetLastError());
+  h->launches++;
+  return RTX_OK;
+}
+
+extern "C" int rtx_apparent_radiance(rtx_handle* h, const double* X_dev, int64_t nx, const double* emis_dev,
+                                     int64_t n_emis, const double* Ts_dev, int64_t n_atm, const double* tau_dev,
+                                     const double* la_dev, const double* ld_dev, const double* dT_dev, int64_t n_dT,
+                                     double* L_dev, double* ls_dev, void* stream) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  RTX_REQUIRE(nx > 0 && n_emis > 0 && n_atm > 0, "rtx_apparent_radiance: bad sizes");
+  RTX_REQUIRE(X_dev && emis_dev && Ts_dev && tau_dev && la_dev && ld_dev && L_dev, "rtx_apparent_radiance: null pointer");
+  if (!dT_dev) n_dT = 1;
+  RTX_REQUIRE(n_dT > 0, "rtx_apparent_radiance: n_dT must be positive");
+  DeviceGuard guard(h->device);
+  const int64_t total = nx * n_atm * n_dT;
+  const int64_t blocks = (total + 255) / 256;
+  RTX_REQUIRE(blocks <= 2147483647LL, "rtx_apparent_radiance: problem too large for one launch");
+  apparent_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      X_dev, nx, emis_dev, n_emis, Ts_dev, n_atm, tau_dev, la_dev, ld_dev, dT_dev, n_dT, L_dev, ls_dev);
+  RTX_CUDA(cudaGetLastError());
+  h->launches++;
+  return RTX_OK;
+}
+
+extern "C" int rtx_hsi_pixels(rtx_handle* h, const double* X_dev, int64_t nx, const double* emis_dev, int64_t n_emis,
+                              const double* tau_dev, const double* la_dev, const double* ld_dev, int64_t n_atm,
+                              int64_t n_pix, const int32_t* atm_idx_dev, const double* T_pix_dev, int n_mix,
+                              const int32_t* mat_idx_dev, const double* frac_dev, double* L_dev, void* stream) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  RTX_REQUIRE(nx > 0 && n_emis > 0 && n_atm > 0 && n_pix > 0 && n_mix > 0, "rtx_hsi_pixels: bad sizes");
+  RTX_REQUIRE(X_dev && emis_dev && tau_dev && la_dev && ld_dev && atm_idx_dev && T_pix_dev && mat_idx_dev &&
+                  frac_dev && L_dev, "rtx_hsi_pixels: null pointer");
+  DeviceGuard guard(h->device);
+  const int64_t total = n_pix * nx;
+  const int64_t blocks = (total + 255) / 256;
+  RTX_REQUIRE(blocks <= 2147483647LL, "rtx_hsi_pixels: problem too large for one launch");
+  hsi_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      X_dev, nx, emis_dev, tau_dev, la_dev, ld_dev, n_pix, atm_idx_dev, T_pix_dev, n_mix, mat_idx_dev, frac_dev, L_dev);
+  RTX_CUDA(cudaGetLastError());
+  h->launches++;
+  return RTX_OK;
+}

@@ -1,0 +1,155 @@
+// Subsystem 3: layer integration -- transmittance, upwelling and downwelling radiance (TUD).
+//
+// Replaces the numpy body of compute_TUD after the optical-depth loop (radiative_transfer.py:340-392).
+// One thread owns one (grid point, atmosphere); optical depths are read layer-major so that a warp reads
+// 256 contiguous bytes per layer.  The work is FP64-exp bound (2113 exp per grid point at 66 layers and 30
+// angles), so the kernel keeps a block of angle accumulators in registers and reads each
+// layer's optical depth once per angle block; Planck radiances are recomputed in registers instead of
+// being materialised as the reference's (nX, nL) array.
+#include <math.h>
+
+#include "rtx_common.cuh"
+
+namespace {
+
+constexpr int TUD_THREADS = 128;
+constexpr int ANGLE_BLOCK = 16;
+
+struct TudParams {
+  int n_atm, n_layers, n_alt, n_mu, n_angle, n_down, return_od, max_cnt;
+  int64_t nx;
+  const double *od, *T, *grid;
+  double *tau, *lu, *ld;
+  double mu[RTX_MAX_MU];
+  int cnt[RTX_MAX_ALT];
+  uint32_t mask[RTX_MAX_ALT][RTX_MAX_LAYERS / 32];
+  double inv_cos[RTX_MAX_ANGLES];   // only angles with a non-zero quadrature weight
+  double wgt[RTX_MAX_ANGLES];       // cos(th)*sin(th)
+  double wsum;                      // sum of cos(th)*sin(th) over ALL angles
+};
+
+__global__ void __launch_bounds__(TUD_THREADS) tud_kernel(const TudParams P) {
+  const int64_t x = (int64_t)blockIdx.x * TUD_THREADS + threadIdx.x;
+  if (x >= P.nx) return;
+  const int atm = blockIdx.y;
+  const double nu = P.grid[x];
+  const double* __restrict__ od = P.od + ((int64_t)atm * P.n_layers) * P.nx + x;
+  const double* __restrict__ T = P.T + (int64_t)atm * P.n_layers;
+  const int64_t obase = ((int64_t)atm * P.nx + x) * P.n_alt * P.n_mu;
+
+  // ---- upwelling: Lu <- t*Lu + (1-t)*B_k bottom-up, snapshot at every altitude's layer count
+  //      (radiative_transfer.py:353-356)
+  for (int m = 0; m < P.n_mu; ++m) {
+    const double mu = P.mu[m];
+    double lu = 0.0;
+    for (int a = 0; a < P.n_alt; ++a)
+      if (P.cnt[a] == 0) P.lu[obase + (int64_t)a * P.n_mu + m] = 0.0;
+    for (int k = 0; k < P.max_cnt; ++k) {
+      const double o = od[(int64_t)k * P.nx];
+      const double B = planck_wn(nu, T[k]);
+      const double t = exp(-o * mu);
+      lu = t * lu + (1.0 - t) * B;
+      for (int a = 0; a < P.n_alt; ++a)
+        if (P.cnt[a] == k + 1) P.lu[obase + (int64_t)a * P.n_mu + m] = lu;
+    }
+    // ---- transmittance: exp(-sum_{Z<=zs} OD*mu) (radiative_transfer.py:348-352)
+    for (int a = 0; a < P.n_alt; ++a) {
+      double s = 0.0;
+      for (int k = 0; k < P.n_layers; ++k)
+        if ((P.mask[a][k >> 5] >> (k & 31)) & 1u) s += od[(int64_t)k * P.nx] * mu;
+      P.tau[obase + (int64_t)a * P.n_mu + m] = P.return_od ? s : exp(-1.0 * s);
+    }
+  }
+
+  // ---- downwelling: per angle Ld <- t*Ld + (1-t)*B_j top-down, then the cos-weighted hemispheric mean
+  //      (radiative_transfer.py:368-373, 387-389)
+  double ldsum = 0.0;
+  for (int a0 = 0; a0 < P.n_angle; a0 += ANGLE_BLOCK) {
+    double acc[ANGLE_BLOCK];
+#pragma unroll
+    for (int a = 0; a < ANGLE_BLOCK; ++a) acc[a] = 0.0;
+    for (int j = P.n_down - 1; j >= 0; --j) {
+      const double o = od[(int64_t)j * P.nx];
+      const double B = planck_wn(nu, T[j]);
+#pragma unroll
+      for (int a = 0; a < ANGLE_BLOCK; ++a) {
+        if (a0 + a < P.n_angle) {
+          const double t = exp(-o * P.inv_cos[a0 + a]);
+          acc[a] = t * acc[a] + (1.0 - t) * B;
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < ANGLE_BLOCK; ++a)
+      if (a0 + a < P.n_angle) ldsum += acc[a] * P.wgt[a0 + a];
+  }
+  P.ld[(int64_t)atm * P.nx + x] = ldsum / P.wsum;
+}
+
+__global__ void planck_kernel(const double* __restrict__ X, int64_t nx, const double* __restrict__ T, int64_t nT,
+                              int wavelength, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nx * nT) return;
+  const double x = X[i / nT], t = T[i % nT];
+  out[i] = wavelength ? planck_um(x, t) : planck_wn(x, t);
+}
+
+}  // namespace
+
+extern "C" int rtx_tud(rtx_handle* h, int n_atm, int n_layers, const double* od_dev, const double* T_dev,
+                       const double* grid_dev, int64_t nx, const double* Z_host, const double* alt_host, int n_alt,
+                       const double* mu_host, int n_mu, int n_angle, int return_od, double* tau_dev, double* lu_dev,
+                       double* ld_dev, void* stream) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  RTX_REQUIRE(n_atm > 0 && n_atm <= 65535 && nx > 0, "rtx_tud: n_atm must be in 1..65535 and nx positive");
+  RTX_REQUIRE(n_layers > 0 && n_layers <= RTX_MAX_LAYERS, "rtx_tud: n_layers out of range");
+  RTX_REQUIRE(n_alt > 0 && n_alt <= RTX_MAX_ALT, "rtx_tud: n_alt out of range");
+  RTX_REQUIRE(n_mu > 0 && n_mu <= RTX_MAX_MU, "rtx_tud: n_mu out of range");
+  RTX_REQUIRE(n_angle > 0 && n_angle <= RTX_MAX_ANGLES, "rtx_tud: N_angle out of range");
+  RTX_REQUIRE(od_dev && T_dev && grid_dev && Z_host && alt_host && mu_host && tau_dev && lu_dev && ld_dev,
+              "rtx_tud: null pointer");
+  DeviceGuard guard(h->device);
+  TudParams P{};
+  P.n_atm = n_atm; P.n_layers = n_layers; P.n_alt = n_alt; P.n_mu = n_mu; P.return_od = return_od ? 1 : 0;
+  P.nx = nx; P.od = od_dev; P.T = T_dev; P.grid = grid_dev; P.tau = tau_dev; P.lu = lu_dev; P.ld = ld_dev;
+  for (int m = 0; m < n_mu; ++m) P.mu[m] = mu_host[m];
+  P.max_cnt = 0;
+  for (int a = 0; a < n_alt; ++a) {
+    int c = 0;
+    for (int k = 0; k < n_layers; ++k)
+      if (Z_host[k] <= alt_host[a]) { P.mask[a][k >> 5] |= (1u << (k & 31)); ++c; }   // ix = Z <= zs
+    P.cnt[a] = c;                                                                     // nL = np.sum(ix)
+    if (c > P.max_cnt) P.max_cnt = c;
+  }
+  P.n_down = P.cnt[n_alt - 1];   // the reference's nL after the altitude loop (radiative_transfer.py:353, 370)
+  // angles = linspace(0, pi/2, nA, endpoint=False) (radiative_transfer.py:368)
+  const double step = (M_PI / 2.0) / n_angle;
+  P.wsum = 0.0;
+  int kept = 0;
+  for (int i = 0; i < n_angle; ++i) {
+    const double th = i * step;
+    const double w = cos(th) * sin(th);
+    P.wsum += w;
+    if (w != 0.0) { P.inv_cos[kept] = 1.0 / cos(th); P.wgt[kept] = w; ++kept; }
+  }
+  P.n_angle = kept;
+  if (P.wsum == 0.0) P.wsum = nan("");   // N_angle=1: the reference divides 0 by 0
+  dim3 grid((unsigned)((nx + TUD_THREADS - 1) / TUD_THREADS), (unsigned)n_atm);
+  tud_kernel<<<grid, TUD_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  RTX_CUDA(cudaGetLastError());
+  h->launches++;
+  return RTX_OK;
+}
+
+extern "C" int rtx_planck(rtx_handle* h, const double* X_dev, int64_t nx, const double* T_dev, int64_t nT,
+                          int wavelength, double* out_dev, void* stream) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  RTX_REQUIRE(nx > 0 && nT > 0 && X_dev && T_dev && out_dev, "rtx_planck: bad arguments");
+  DeviceGuard guard(h->device);
+  const int64_t total = nx * nT;
+  planck_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(X_dev, nx, T_dev, nT,
+                                                                                              wavelength, out_dev);
+  RTX_CUDA(cudaGetLastError());
+  h->launches++;
+  return RTX_OK;
+}

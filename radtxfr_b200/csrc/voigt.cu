@@ -1,0 +1,642 @@
+// Subsystem 2: Voigt line sum (sm_100a).
+//
+// Replaces the per-line Python loop of absorptionCoefficient_Voigt (misc/hapi.py:11050-11138) and the
+// profile it calls (PROFILE_VOIGT -> pcqsdhc PART1 -> hum1_wei, misc/hapi.py:10131-10140, 9910-9915,
+// 9833-9844) for many homogeneous (T, p) states at once.
+//
+// Design (B200-first, not a translation):
+//   * one CTA per (wavenumber tile, state).  The tile of the spectral grid is staged in shared memory by
+//     one TMA bulk copy (cp.async.bulk + mbarrier) and kept there: the prologue bisects it exactly like
+//     the reference bisects its grid (window membership is decided on the same doubles), and the
+//     evaluation passes read it back.
+//   * the CTA streams only the lines that can reach its tile (device-side binning on the sorted line
+//     centres with a conservative per-state wing bound), 256 lines per chunk.  One thread derives one
+//     line's state (S(T), Gamma_D, Gamma_0, shift, wing, window indices, Weideman core indices) and the
+//     survivors are compacted deterministically (ballot + scan, no atomics) into two shared lists.
+//   * pass 1 ("wide" lines): each warp owns 32*K contiguous grid points (K per lane, lane-strided),
+//     accumulators in registers.
+//     Outside the Weideman core the reference's w(z) is the one-term Humlicek asymptote, for which
+//       S*V = a*(q+e)/((q+f)*q+e^2),  q=(omega-nu0')^2, a=amp*Gamma0/pi, e=GammaD^2/(2 ln2)+Gamma0^2,
+//       f=2*Gamma0^2-GammaD^2/ln2                                   (closed form)
+//     = 9 FP64 pipe operations per (line, grid point) incl. a Newton-refined MUFU.RCP64H reciprocal.
+//   * pass 2 ("segments"): the Weideman cores of wide lines and the whole window of narrow lines are
+//     evaluated lane-per-point by the warp that owns that part of the tile (shared-memory accumulator, no
+//     atomics), so the 24-term rational series never diverges against the cheap branch inside a warp.
+//   * FP64 throughout; summation order is fixed (line order within a CTA), so results are bit-reproducible
+//     run to run and independent of how the grid is sharded across GPUs.
+#include <math.h>
+
+#include <algorithm>
+
+#include "rtx_common.cuh"
+
+namespace {
+
+constexpr int NT = 256;         // threads per CTA
+constexpr int LCHUNK = 256;     // lines per prologue chunk (one per thread)
+constexpr int NARROW_MAX = 64;  // windows of at most this many tile points go to pass 2 entirely
+
+__constant__ double c_weideman[24] = {
+    // Weideman N=24 coefficients, highest power first.  tests/test_host_logic.py regenerates them from the
+    // FFT recipe (misc/hapi.py:9816-9824) and compares with the values exported by rtx_weideman_coeffs().
+    -1.5137469056014652e-10, 4.904820416137823e-09,  1.3310453109352295e-09, -3.0082823610602605e-08,
+    -1.9122258957660688e-08, 1.87383434459447e-07,   2.5682641329013596e-07, -1.085647579377311e-06,
+    -3.038893184278043e-06,  4.1394617242916025e-06, 3.0471066082970273e-05, 2.4331415462208058e-05,
+    -0.00020748431511423976, -0.0007816642995623942, -0.000493642690128576,  0.006215006362949158,
+    0.03372336685531593,     0.10838723484566715,    0.26549639598807695,    0.5361139535729114,
+    0.9257087138588673,      1.394819673379119,      1.85628649920554,       2.1978589365315417};
+const double h_weideman[24] = {
+    -1.5137469056014652e-10, 4.904820416137823e-09,  1.3310453109352295e-09, -3.0082823610602605e-08,
+    -1.9122258957660688e-08, 1.87383434459447e-07,   2.5682641329013596e-07, -1.085647579377311e-06,
+    -3.038893184278043e-06,  4.1394617242916025e-06, 3.0471066082970273e-05, 2.4331415462208058e-05,
+    -0.00020748431511423976, -0.0007816642995623942, -0.000493642690128576,  0.006215006362949158,
+    0.03372336685531593,     0.10838723484566715,    0.26549639598807695,    0.5361139535729114,
+    0.9257087138588673,      1.394819673379119,      1.85628649920554,       2.1978589365315417};
+
+struct VoigtParams {
+  const double *nu, *s0, *elower, *gamma_air, *gamma_self, *n_air, *n_self, *delta_air, *deltap_air,
+      *delta_self, *deltap_self;
+  const int32_t* iso;
+  int64_t n_lines;
+  const double *T, *p, *weight;  // [n_states], [n_states], [n_states][n_iso]
+  const double *st_q, *st_d;     // [n_states][n_iso]: Q(Tref)/Q(T), Doppler factor
+  int n_iso, n_states;
+  double x_air, x_self, wing_abs, wing_hw, s_thr;
+  const double* grid;
+  int64_t nx;
+  int n_tiles;
+  const int32_t* bins;  // [n_states][n_tiles][2]
+  double* out;
+  int has_self, has_deltap, use_tma;
+};
+
+// Everything the reference derives for one line at one (T, p): misc/hapi.py:11058-11131.
+struct LineState {
+  double nu, sg0, W, gamD, gam0, amp;
+  bool keep;
+};
+
+__device__ __forceinline__ LineState line_state(const VoigtParams& P, int64_t li, int s, double T, double p,
+                                                double lnr) {
+  LineState L;
+  const double nu = P.nu[li];
+  const int iso = P.iso[li];
+  const double wgt = P.weight[(int64_t)s * P.n_iso + iso];
+  // S(T) = sw*Qref/Q * ch/zn, EnvironmentDependency_Intensity (misc/hapi.py:10169-10175); zn is folded
+  // into s0 at ingest.
+  const double ch = exp(-RTX_C2_HAPI * P.elower[li] / T) * (1.0 - exp(-RTX_C2_HAPI * nu / T));
+  const double S = P.s0[li] * P.st_q[(int64_t)s * P.n_iso + iso] * ch;
+  L.keep = !(S < P.s_thr) && (wgt != 0.0);                       // :11066, :11082
+  L.gamD = P.st_d[(int64_t)s * P.n_iso + iso] * nu;              // :11087 (unshifted centre)
+  // Gamma0 and Shift0 over the diluents, :11090-11128
+  double g0 = 0.0, sh = 0.0;
+  {
+    const double rp = exp(P.n_air[li] * lnr);                    // (Tref/T)**n_air
+    g0 += P.x_air * (P.gamma_air[li] * p * rp);
+    double d = P.delta_air[li];
+    if (P.has_deltap) d += P.deltap_air[li] * (T - RTX_TREF);
+    sh += P.x_air * (d * p);
+  }
+  if (P.has_self) {
+    const double rp = exp(P.n_self[li] * lnr);
+    g0 += P.x_self * (P.gamma_self[li] * p * rp);
+    double d = P.delta_self[li];
+    if (P.has_deltap) d += P.deltap_self[li] * (T - RTX_TREF);
+    sh += P.x_self * (d * p);
+  }
+  L.gam0 = g0;
+  L.nu = nu;
+  L.sg0 = nu + sh;
+  L.W = fmax(fmax(P.wing_abs, P.wing_hw * g0), P.wing_hw * L.gamD);  // :11131
+  L.amp = wgt * S;
+  return L;
+}
+
+// |x|+y < 15 exactly as hum1_wei tests it (misc/hapi.py:9841) on x = -((sg0-sg)*cte), y = Gam0*cte
+// (misc/hapi.py:9911-9913); explicit _rn intrinsics keep ptxas from contracting into an FMA.
+__device__ __forceinline__ bool in_weideman(double omega, double sg0, double cte, double y) {
+  const double x = __dmul_rn(omega - sg0, cte);
+  return __dadd_rn(fabs(x), y) < 15.0;
+}
+
+template <bool FAST>
+__device__ __forceinline__ double rcp_nr(double x) {
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));   // MUFU.RCP64H
+  const double e = fma(-x, r0, 1.0);
+  if (FAST) return fma(r0, e, r0);
+  const double t = fma(e, e, e);
+  return fma(r0, t, r0);                                   // r0*(1+e+e^2): cubic convergence
+}
+
+// Humlicek one-term branch of hum1_wei folded with the Voigt prefactor (closed form, App. A.3).
+template <bool FAST>
+__device__ __forceinline__ double cheap_term(double omega, double sg0, double a, double ae, double f,
+                                             double g, double acc) {
+  const double d = omega - sg0;
+  const double q = d * d;
+  const double num = fma(a, q, ae);
+  const double den = fma(q + f, q, g);
+  return fma(num, rcp_nr<FAST>(den), acc);
+}
+
+// Re w(x+iy) by Weideman's 24-term rational series, misc/hapi.py:9812-9827 (cef).
+__device__ __forceinline__ double weideman_re(double x, double y) {
+  const double L = RTX_WEIDEMAN_L;
+  const double dr = L + y, nr = L - y;          // L-iz = dr - i x ;  L+iz = nr + i x
+  const double m2 = dr * dr + x * x;
+  const double inv = 1.0 / m2;
+  const double Zr = (nr * dr - x * x) * inv;
+  const double Zi = (2.0 * L * x) * inv;
+  double pr = c_weideman[0], pi = 0.0;
+#pragma unroll
+  for (int k = 1; k < 24; ++k) {
+    const double tr = pr * Zr - pi * Zi + c_weideman[k];
+    pi = pr * Zi + pi * Zr;
+    pr = tr;
+  }
+  const double ir = dr * inv, ii = x * inv;     // 1/(L-iz)
+  const double qr = ir * ir - ii * ii, qi = 2.0 * ir * ii;
+  return 2.0 * (pr * qr - pi * qi) + RTX_INV_SQRT_PI * ir;
+}
+
+struct __align__(16) WideRec {
+  double sg0, a, ae, f, g;
+  short lo, hi, clo, chi;
+};
+struct __align__(16) SegRec {
+  double sg0, cte, y, cw, a, ae, f, g;
+  int s, e;
+};
+
+// ---------------------------------------------------------------------------------------------
+// per-state tables: Q(Tref)/Q(T) by TIPS-2011 Lagrange interpolation (misc/hapi.py:5311-5388, 9568-9582),
+// Doppler factor sqrt(2kT ln2/(m c^2)) (misc/hapi.py:11085-11087), conservative wing bound.
+__device__ __forceinline__ double tips_lagrange(double aa, const double* __restrict__ A,
+                                                const double* __restrict__ B, int npt) {
+  int I = -1;
+  for (int c = 2; c <= npt; ++c)
+    if (A[c - 1] >= aa) { I = c; break; }
+  if (I < 0) return nan("");
+  if (I < 3 || I == npt) {
+    const int J = (I < 3 ? 3 : npt) - 1;
+    const double a0 = A[J - 2], a1 = A[J - 1], a2 = A[J];
+    const double w0 = (aa - a1) * (aa - a2) / ((a0 - a1) * (a0 - a2));
+    const double w1 = (aa - a0) * (aa - a2) / ((a1 - a0) * (a1 - a2));
+    const double w2 = (aa - a0) * (aa - a1) / ((a2 - a0) * (a2 - a1));
+    return w0 * B[J - 2] + w1 * B[J - 1] + w2 * B[J];
+  }
+  const int J = I - 1;
+  const double a0 = A[J - 2], a1 = A[J - 1], a2 = A[J], a3 = A[J + 1];
+  const double w0 = (aa - a1) * (aa - a2) * (aa - a3) / ((a0 - a1) * (a0 - a2) * (a0 - a3));
+  const double w1 = (aa - a0) * (aa - a2) * (aa - a3) / ((a1 - a0) * (a1 - a2) * (a1 - a3));
+  const double w2 = (aa - a0) * (aa - a1) * (aa - a3) / ((a2 - a0) * (a2 - a1) * (a2 - a3));
+  const double w3 = (aa - a0) * (aa - a1) * (aa - a2) / ((a3 - a0) * (a3 - a1) * (a3 - a2));
+  return w0 * B[J - 2] + w1 * B[J - 1] + w2 * B[J] + w3 * B[J + 1];
+}
+
+struct PrepParams {
+  int n_states, n_iso;
+  const double *T, *p, *mass, *tipsT, *q, *qref;
+  double *st_q, *st_d, *st_wb;
+  double x_air, x_self, wing_abs, wing_hw;
+  double nu_max, gair_max, gself_max, nair_min, nair_max, nself_min, nself_max;
+};
+
+__global__ void state_prep_kernel(PrepParams P) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P.n_states) return;
+  const double T = P.T[s], p = P.p[s];
+  const bool ok = (T >= 70.0) && (T <= 3000.0);   // misc/hapi.py:9571
+  double dmax = 0.0;
+  for (int j = 0; j < P.n_iso; ++j) {
+    const double Q = ok ? tips_lagrange(T, P.tipsT, P.q + (int64_t)j * RTX_TIPS_NPT, RTX_TIPS_NPT) : nan("");
+    P.st_q[(int64_t)s * P.n_iso + j] = P.qref[j] / Q;
+    const double m = P.mass[j] * RTX_CMASS * 1000.0;
+    const double d = sqrt(2.0 * RTX_CBOLTZ * T * RTX_LN2 / m / (RTX_CLIGHT * RTX_CLIGHT));
+    P.st_d[(int64_t)s * P.n_iso + j] = d;
+    dmax = fmax(dmax, d);
+  }
+  const double lnr = log(RTX_TREF / T);
+  const double ra = fmax(exp(P.nair_min * lnr), exp(P.nair_max * lnr));
+  const double rs = fmax(exp(P.nself_min * lnr), exp(P.nself_max * lnr));
+  const double g0 = fabs(p) * (fabs(P.x_air) * P.gair_max * ra + fabs(P.x_self) * P.gself_max * rs);
+  double wb = fmax(fmax(P.wing_abs, P.wing_hw * g0), P.wing_hw * dmax * P.nu_max);
+  P.st_wb[s] = wb * (1.0 + 1e-6) + 1e-9;
+}
+
+__global__ void tips_kernel(int n, int n_iso, const double* __restrict__ T, const double* __restrict__ tipsT,
+                            const double* __restrict__ q, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * n_iso) return;
+  const int s = (int)(i / n_iso), j = (int)(i % n_iso);
+  const double t = T[s];
+  out[i] = (t >= 70.0 && t <= 3000.0) ? tips_lagrange(t, tipsT, q + (int64_t)j * RTX_TIPS_NPT, RTX_TIPS_NPT)
+                                      : nan("");
+}
+
+// candidate line range of every (state, tile): lines with nu in [tile_lo - Wb, tile_hi + Wb]
+__global__ void bin_kernel(int n_states, int n_tiles, int tile_pts, const double* __restrict__ grid, int64_t nx,
+                           const double* __restrict__ nu, int64_t n_lines, const double* __restrict__ st_wb,
+                           int32_t* __restrict__ bins) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_states * n_tiles) return;
+  const int s = (int)(i / n_tiles), t = (int)(i % n_tiles);
+  const int64_t p0 = (int64_t)t * tile_pts;
+  const int64_t p1 = min(nx, p0 + tile_pts) - 1;
+  const double wb = st_wb[s];
+  const int64_t first = bisect_left_dev64(nu, n_lines, grid[p0] - wb);
+  const int64_t last = bisect_right_dev64(nu, n_lines, grid[p1] + wb);
+  bins[2 * i] = (int32_t)first;
+  bins[2 * i + 1] = (int32_t)last;
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int K, bool FAST>
+__global__ void __launch_bounds__(NT, 2) voigt_tile_kernel(const VoigtParams P) {
+  constexpr int TILE = K * NT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* s_grid = reinterpret_cast<double*>(smem_raw);                 // TILE
+  double* s_acc2 = s_grid + TILE;                                       // TILE
+  WideRec* s_wide = reinterpret_cast<WideRec*>(s_acc2 + TILE);          // LCHUNK
+  SegRec* s_seg = reinterpret_cast<SegRec*>(s_wide + LCHUNK);           // LCHUNK
+  __shared__ int s_cnt[2][NT / 32];
+  __shared__ __align__(8) unsigned long long s_bar;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x % P.n_tiles;
+  const int s = blockIdx.x / P.n_tiles;
+  const int64_t p0 = (int64_t)tile * TILE;
+  const int npts = (int)min((int64_t)TILE, P.nx - p0);
+
+  // ---- stage the grid tile: one TMA bulk copy signalled through an mbarrier --------------------
+  const int tma_pts = P.use_tma ? (npts & ~1) : 0;
+  if (tma_pts > 0) {
+    if (tid == 0) {
+      const uint32_t bar = smem_u32(&s_bar);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const uint32_t bytes = (uint32_t)tma_pts * 8u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(s_grid)),
+          "l"(P.grid + p0), "r"(bytes), "r"(bar)
+          : "memory");
+    }
+  }
+  for (int i = tma_pts + tid; i < TILE; i += NT) s_grid[i] = (i < npts) ? P.grid[p0 + i] : 1.7976931348623157e308;
+  for (int i = tid; i < TILE; i += NT) s_acc2[i] = 0.0;
+  __syncthreads();   // barrier init visible to all waiters; padding + acc2 written
+  if (tma_pts > 0) {
+    const uint32_t bar = smem_u32(&s_bar);
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+          : "=r"(done)
+          : "r"(bar), "r"(0u)
+          : "memory");
+    }
+  }
+
+  double w[K], acc[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) { w[j] = s_grid[warp * (32 * K) + j * 32 + lane]; acc[j] = 0.0; }
+
+  const double T = P.T[s], p = P.p[s];
+  const double lnr = log(RTX_TREF / T);
+  const int64_t bi = 2 * ((int64_t)s * P.n_tiles + tile);
+  const int first = P.bins[bi], last = P.bins[bi + 1];
+  const int own_lo = warp * (TILE / (NT / 32)), own_hi = own_lo + TILE / (NT / 32);
+
+  for (int c0 = first; c0 < last; c0 += LCHUNK) {
+    // ---- prologue: one thread, one line ------------------------------------------------------
+    const int li = c0 + tid;
+    bool is_wide = false, has_seg = false;
+    WideRec wr;
+    SegRec sr;
+    if (li < last) {
+      const LineState L = line_state(P, li, s, T, p, lnr);
+      if (L.keep) {
+        const int lo = bisect_right_dev(s_grid, TILE, L.nu - L.W);      // misc/hapi.py:11133
+        const int hi = bisect_right_dev(s_grid, TILE, L.nu + L.W);      // misc/hapi.py:11134
+        if (hi > lo) {
+          const double cte = RTX_SQRT_LN2 / L.gamD;                      // misc/hapi.py:9900
+          const double y = L.gam0 * cte;                                 // misc/hapi.py:9913
+          const double h = L.gamD * L.gamD / RTX_LN2;                    // 1/cte^2
+          const double g2 = L.gam0 * L.gam0;
+          const double e = 0.5 * h + g2;
+          const double a = L.amp * L.gam0 / RTX_PI;
+          sr.sg0 = wr.sg0 = L.sg0;
+          sr.a = wr.a = a;
+          sr.ae = wr.ae = a * e;
+          sr.f = wr.f = 2.0 * g2 - h;
+          sr.g = wr.g = e * e;
+          sr.cte = cte;
+          sr.y = y;
+          sr.cw = L.amp * (cte / RTX_SQRT_PI);
+          int clo = lo, chi = lo;                                        // empty Weideman core
+          if (y < 15.0) {
+            // the mask |x|+y<15 is a contiguous index range around sg0; find it with the exact predicate
+            int m = bisect_left_dev(s_grid, TILE, L.sg0);
+            m = max(lo, min(hi, m));
+            int a0 = lo, a1 = m;                                         // first true in [lo, m)
+            while (a0 < a1) {
+              const int mid = (a0 + a1) >> 1;
+              if (in_weideman(s_grid[mid], L.sg0, cte, y)) a1 = mid; else a0 = mid + 1;
+            }
+            clo = a0;
+            a0 = m; a1 = hi;                                             // first false in [m, hi)
+            while (a0 < a1) {
+              const int mid = (a0 + a1) >> 1;
+              if (in_weideman(s_grid[mid], L.sg0, cte, y)) a0 = mid + 1; else a1 = mid;
+            }
+            chi = a0;
+          }
+          if (hi - lo <= NARROW_MAX) {
+            has_seg = true; sr.s = lo; sr.e = hi;
+          } else {
+            is_wide = true;
+            wr.lo = (short)lo; wr.hi = (short)hi; wr.clo = (short)clo; wr.chi = (short)chi;
+            if (chi > clo) { has_seg = true; sr.s = clo; sr.e = chi; }
+          }
+        }
+      }
+    }
+    // ---- deterministic compaction ----------------------------------------------------------------
+    const unsigned bw = __ballot_sync(0xffffffffu, is_wide), bs = __ballot_sync(0xffffffffu, has_seg);
+    const unsigned lt = (1u << lane) - 1u;
+    if (lane == 0) { s_cnt[0][warp] = __popc(bw); s_cnt[1][warp] = __popc(bs); }
+    __syncthreads();
+    int offw = 0, offs = 0, n_wide = 0, n_seg = 0;
+#pragma unroll
+    for (int k = 0; k < NT / 32; ++k) {
+      const int cw = s_cnt[0][k], cs = s_cnt[1][k];
+      if (k < warp) { offw += cw; offs += cs; }
+      n_wide += cw; n_seg += cs;
+    }
+    if (is_wide) s_wide[offw + __popc(bw & lt)] = wr;
+    if (has_seg) s_seg[offs + __popc(bs & lt)] = sr;
+    __syncthreads();
+
+    // ---- pass 1: wide lines, register accumulators ------------------------------------------------
+    // A warp owns 32*K contiguous points (lane-strided), so a window that spans the warp's slice takes
+    // the test-free path; only the two slices holding the window's ends pay for per-point predicates.
+    for (int l = 0; l < n_wide; ++l) {
+      const WideRec& rr = s_wide[l];
+      const int lo = rr.lo, hi = rr.hi;
+      if (hi <= own_lo || lo >= own_hi) continue;
+      const int clo = rr.clo, chi = rr.chi;
+      const double sg0 = rr.sg0, a = rr.a, ae = rr.ae, f = rr.f, g = rr.g;
+      if (lo <= own_lo && hi >= own_hi && (chi <= clo || chi <= own_lo || clo >= own_hi)) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const int i = own_lo + j * 32 + lane;
+          const bool in = (i >= lo) && (i < hi) && !((i >= clo) && (i < chi));
+          if (in) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
+        }
+      }
+    }
+    // ---- pass 2: segments, lane per point, warp-owned slice of the tile -----------------------------
+    for (int l = 0; l < n_seg; ++l) {
+      const int ss = max(s_seg[l].s, own_lo), ee = min(s_seg[l].e, own_hi);
+      if (ss >= ee) continue;
+      const SegRec r = s_seg[l];
+      for (int i = ss + lane; i < ee; i += 32) {
+        const double om = s_grid[i];
+        const double x = __dmul_rn(om - r.sg0, r.cte);
+        double v;
+        if (__dadd_rn(fabs(x), r.y) < 15.0) v = r.cw * weideman_re(x, r.y);
+        else v = cheap_term<false>(om, r.sg0, r.a, r.ae, r.f, r.g, 0.0);
+        s_acc2[i] += v;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+
+  double* out = P.out + (int64_t)s * P.nx + p0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int i = warp * (32 * K) + j * 32 + lane;
+    if (i < npts) out[i] = acc[j] + s_acc2[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact eval counter: one thread per (line, state), bisects the whole grid.
+__global__ void count_kernel(const VoigtParams P, unsigned long long* __restrict__ counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long ev = 0, evw = 0;
+  if (i < P.n_lines * (int64_t)P.n_states) {
+    const int s = (int)(i / P.n_lines);
+    const int64_t li = i % P.n_lines;
+    const double T = P.T[s], p = P.p[s];
+    const LineState L = line_state(P, li, s, T, p, log(RTX_TREF / T));
+    if (L.keep) {
+      const int64_t lo = bisect_right_dev64(P.grid, P.nx, L.nu - L.W);
+      const int64_t hi = bisect_right_dev64(P.grid, P.nx, L.nu + L.W);
+      if (hi > lo) {
+        ev = (unsigned long long)(hi - lo);
+        const double cte = RTX_SQRT_LN2 / L.gamD, y = L.gam0 * cte;
+        if (y < 15.0) {
+          int64_t m = bisect_left_dev64(P.grid, P.nx, L.sg0);
+          m = max(lo, min(hi, m));
+          int64_t a0 = lo, a1 = m;
+          while (a0 < a1) {
+            const int64_t mid = (a0 + a1) >> 1;
+            if (in_weideman(P.grid[mid], L.sg0, cte, y)) a1 = mid; else a0 = mid + 1;
+          }
+          const int64_t clo = a0;
+          a0 = m; a1 = hi;
+          while (a0 < a1) {
+            const int64_t mid = (a0 + a1) >> 1;
+            if (in_weideman(P.grid[mid], L.sg0, cte, y)) a0 = mid + 1; else a1 = mid;
+          }
+          evw = (unsigned long long)(a0 - clo);
+        }
+      }
+    }
+  }
+  // warp reduce then one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    ev += __shfl_down_sync(0xffffffffu, ev, o);
+    evw += __shfl_down_sync(0xffffffffu, evw, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (ev | evw)) {
+    atomicAdd(&counts[0], ev);
+    atomicAdd(&counts[1], evw);
+  }
+}
+
+template <int K>
+size_t tile_smem_bytes() {
+  return (size_t)K * NT * 8 * 2 + (size_t)LCHUNK * (sizeof(WideRec) + sizeof(SegRec));
+}
+
+template <int K, bool FAST>
+int launch_tile(const VoigtParams& P, cudaStream_t st) {
+  const size_t smem = tile_smem_bytes<K>();
+  RTX_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<K, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = (int64_t)P.n_tiles * P.n_states;
+  if (blocks > 2147483647LL) { rtx_set_error("rtx_voigt_sum: too many (tile, state) pairs for one launch"); return RTX_E_INVALID; }
+  voigt_tile_kernel<K, FAST><<<(unsigned)blocks, NT, smem, st>>>(P);
+  RTX_CUDA(cudaGetLastError());
+  return RTX_OK;
+}
+
+int ensure_scratch(rtx_handle* h, size_t state_doubles, size_t bin_ints) {
+  if (state_doubles > h->state_cap) {
+    if (h->d_state) cudaFree(h->d_state);
+    h->d_state = nullptr; h->state_cap = 0;
+    RTX_CUDA(cudaMalloc(&h->d_state, state_doubles * sizeof(double)));
+    h->state_cap = state_doubles;
+  }
+  if (bin_ints > h->bins_cap) {
+    if (h->d_bins) cudaFree(h->d_bins);
+    h->d_bins = nullptr; h->bins_cap = 0;
+    RTX_CUDA(cudaMalloc(&h->d_bins, bin_ints * sizeof(int32_t)));
+    h->bins_cap = bin_ints;
+  }
+  return RTX_OK;
+}
+
+int fill_params(rtx_handle* h, VoigtParams& P, int n_states, const double* T, const double* p, const double* weight,
+                double x_air, double x_self, double wing_abs, double wing_hw, double s_thr, const double* grid,
+                int64_t nx) {
+  const LineTable& L = h->lines;
+  if (h->n_iso <= 0) { rtx_set_error("isotopologue table not set (rtx_set_iso_table)"); return RTX_E_STATE; }
+  if (L.n_pad == 0) { rtx_set_error("no line table uploaded (rtx_lines_upload)"); return RTX_E_STATE; }
+  RTX_REQUIRE(n_states > 0 && nx > 0, "n_states and nx must be positive");
+  RTX_REQUIRE(T && p && weight && grid, "null device pointer");
+  RTX_REQUIRE(x_self == 0.0 || L.gamma_self != nullptr, "Diluent 'self' requested but the table has no gamma_self column");
+  P.nu = L.nu; P.s0 = L.s0; P.elower = L.elower; P.gamma_air = L.gamma_air; P.gamma_self = L.gamma_self;
+  P.n_air = L.n_air; P.n_self = L.n_self; P.delta_air = L.delta_air; P.deltap_air = L.deltap_air;
+  P.delta_self = L.delta_self; P.deltap_self = L.deltap_self; P.iso = L.iso; P.n_lines = L.n;
+  P.T = T; P.p = p; P.weight = weight; P.n_iso = h->n_iso; P.n_states = n_states;
+  P.x_air = x_air; P.x_self = x_self; P.wing_abs = wing_abs; P.wing_hw = wing_hw; P.s_thr = s_thr;
+  P.grid = grid; P.nx = nx;
+  P.has_self = (x_self != 0.0) ? 1 : 0;
+  P.has_deltap = L.has_deltap ? 1 : 0;
+  P.use_tma = ((reinterpret_cast<uintptr_t>(grid) & 15u) == 0) ? 1 : 0;
+  return RTX_OK;
+}
+
+int run_prep(rtx_handle* h, VoigtParams& P, cudaStream_t st, double** st_wb_out) {
+  const size_t per = (size_t)P.n_states * P.n_iso;
+  int rc = ensure_scratch(h, 2 * per + P.n_states, h->bins_cap);
+  if (rc) return rc;
+  double* st_q = h->d_state;
+  double* st_d = st_q + per;
+  double* st_wb = st_d + per;
+  const LineTable& L = h->lines;
+  PrepParams Q;
+  Q.n_states = P.n_states; Q.n_iso = P.n_iso; Q.T = P.T; Q.p = P.p; Q.mass = h->d_mass; Q.tipsT = h->d_tipsT;
+  Q.q = h->d_q; Q.qref = h->d_qref; Q.st_q = st_q; Q.st_d = st_d; Q.st_wb = st_wb;
+  Q.x_air = P.x_air; Q.x_self = P.x_self; Q.wing_abs = P.wing_abs; Q.wing_hw = P.wing_hw;
+  Q.nu_max = L.nu_max; Q.gair_max = L.gair_max; Q.gself_max = L.gself_max; Q.nair_min = L.nair_min;
+  Q.nair_max = L.nair_max; Q.nself_min = L.nself_min; Q.nself_max = L.nself_max;
+  state_prep_kernel<<<(P.n_states + 127) / 128, 128, 0, st>>>(Q);
+  RTX_CUDA(cudaGetLastError());
+  h->launches++;
+  P.st_q = st_q; P.st_d = st_d;
+  *st_wb_out = st_wb;
+  return RTX_OK;
+}
+
+}  // namespace
+
+extern "C" int rtx_weideman_coeffs(double* out24) {
+  for (int i = 0; i < 24; ++i) out24[i] = h_weideman[i];
+  return RTX_OK;
+}
+
+extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, const double* p_dev,
+                             const double* weight_dev, double x_air, double x_self, double wing_abs,
+                             double wing_hw, double s_threshold, const double* grid_dev, int64_t nx,
+                             double* out_dev, int flags, void* stream) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  RTX_REQUIRE(out_dev != nullptr, "null output pointer");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VoigtParams P{};
+  int rc = fill_params(h, P, n_states, T_dev, p_dev, weight_dev, x_air, x_self, wing_abs, wing_hw, s_threshold,
+                       grid_dev, nx);
+  if (rc) return rc;
+  P.out = out_dev;
+  double* st_wb = nullptr;
+  rc = run_prep(h, P, st, &st_wb);
+  if (rc) return rc;
+  // tile size: the largest K that still gives every SM a few CTAs
+  int K = 1;
+  for (int k : {8, 4, 2}) {
+    const int64_t tiles = (nx + (int64_t)k * NT - 1) / ((int64_t)k * NT);
+    if (tiles * n_states >= 4LL * h->sm_count) { K = k; break; }
+  }
+  const int forced = (flags >> RTX_VOIGT_TILE_SHIFT) & 0xF;   // test hook: force the tile size
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) K = forced;
+  const int tile_pts = K * NT;
+  P.n_tiles = (int)((nx + tile_pts - 1) / tile_pts);
+  const size_t nb = (size_t)P.n_tiles * n_states;
+  rc = ensure_scratch(h, h->state_cap, 2 * nb);
+  if (rc) return rc;
+  P.bins = h->d_bins;
+  bin_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(n_states, P.n_tiles, tile_pts, grid_dev, nx, P.nu, P.n_lines,
+                                                          st_wb, h->d_bins);
+  RTX_CUDA(cudaGetLastError());
+  h->launches++;
+  const bool fast = (flags & RTX_VOIGT_FAST_RCP) != 0;
+  switch (K) {
+    case 8: rc = fast ? launch_tile<8, true>(P, st) : launch_tile<8, false>(P, st); break;
+    case 4: rc = fast ? launch_tile<4, true>(P, st) : launch_tile<4, false>(P, st); break;
+    case 2: rc = fast ? launch_tile<2, true>(P, st) : launch_tile<2, false>(P, st); break;
+    default: rc = fast ? launch_tile<1, true>(P, st) : launch_tile<1, false>(P, st); break;
+  }
+  if (rc) return rc;
+  h->launches++;
+  return RTX_OK;
+}
+
+extern "C" int rtx_voigt_count(rtx_handle* h, int n_states, const double* T_dev, const double* p_dev,
+                               const double* weight_dev, double x_air, double x_self, double wing_abs,
+                               double wing_hw, double s_threshold, const double* grid_dev, int64_t nx,
+                               uint64_t* counts_dev, void* stream) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  RTX_REQUIRE(counts_dev != nullptr, "null counts pointer");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VoigtParams P{};
+  int rc = fill_params(h, P, n_states, T_dev, p_dev, weight_dev, x_air, x_self, wing_abs, wing_hw, s_threshold,
+                       grid_dev, nx);
+  if (rc) return rc;
+  double* st_wb = nullptr;
+  rc = run_prep(h, P, st, &st_wb);
+  if (rc) return rc;
+  RTX_CUDA(cudaMemsetAsync(counts_dev, 0, 2 * sizeof(uint64_t), st));
+  const int64_t total = P.n_lines * (int64_t)n_states;
+  const int64_t blocks = (total + 255) / 256;
+  RTX_REQUIRE(blocks <= 2147483647LL, "rtx_voigt_count: too many (line, state) pairs");
+  count_kernel<<<(unsigned)blocks, 256, 0, st>>>(P, reinterpret_cast<unsigned long long*>(counts_dev));
+  RTX_CUDA(cudaGetLastError());
+  h->launches++;
+  return RTX_OK;
+}
+
+extern "C" int rtx_tips(rtx_handle* h, int n, const double* T_dev, double* q_dev, void* stream) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  if (h->n_iso <= 0) { rtx_set_error("isotopologue table not set (rtx_set_iso_table)"); return RTX_E_STATE; }
+  RTX_REQUIRE(n > 0 && T_dev && q_dev, "bad arguments");
+  DeviceGuard guard(h->device);
+  const int64_t total = (int64_t)n * h->n_iso;
+  tips_kernel<<<(unsigned)((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(n, h->n_iso, T_dev,
+                                                                                            h->d_tipsT, h->d_q, q_dev);
+  RTX_CUDA(cudaGetLastError());
+  h->launches++;
+  return RTX_OK;
+}

@@ -1,0 +1,397 @@
+"""Host-side engine: owns rtx handles and device buffers, and turns reference-style arguments into C-ABI calls.
+
+PyTorch is used for device memory, streams and (in distributed.py) NCCL plumbing only; every computation on
+the hot path is a kernel of libradtxfr_b200.so.  There is no CPU fallback.
+"""
+import ctypes
+import os
+import threading
+import zlib
+
+import numpy as np
+
+from . import _lib
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "spectro_tables.npz")
+_tables = None
+_lock = threading.Lock()
+
+
+def spectro_tables():
+    """Isotopologue metadata and TIPS-2011 tables (data extracted by tools/extract_reference_data.py from
+    misc/hapi.py:3372-3497 and :5401-9564)."""
+    global _tables
+    if _tables is None:
+        z = np.load(_DATA)
+        t = {k: z[k] for k in z.files}
+        t["index"] = {(int(m), int(i)): j for j, (m, i) in enumerate(zip(t["iso_M"], t["iso_I"]))}
+        _tables = t
+    return _tables
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def resolve_device(device=None):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise _lib.RtxError("radtxfr_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.RtxError("radtxfr_b200 runs on CUDA devices only, got %s" % device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _hptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(_torch().cuda.current_stream(device).cuda_stream)
+
+
+def to_device(x, device, dtype=None):
+    """numpy / sequence / torch tensor -> contiguous CUDA tensor (float64 unless dtype is given)."""
+    torch = _torch()
+    dtype = dtype or torch.float64
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype).contiguous()
+    npdt = {torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64}[dtype]
+    a = np.ascontiguousarray(np.asarray(x, dtype=npdt))
+    return torch.from_numpy(a).to(device)
+
+
+class Handle:
+    """An rtx_handle bound to one CUDA device."""
+
+    def __init__(self, device=None):
+        self.device = resolve_device(device)
+        h = ctypes.c_void_p()
+        _lib.call("rtx_create", self.device.index, ctypes.byref(h))
+        self._h = h
+
+    @property
+    def h(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            _lib.lib().rtx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launches(self):
+        n = ctypes.c_uint64()
+        _lib.call("rtx_launch_count", self._h, ctypes.byref(n))
+        return int(n.value)
+
+    def device_info(self):
+        sm = ctypes.c_int()
+        buf = ctypes.create_string_buffer(256)
+        _lib.call("rtx_device_info", self._h, ctypes.byref(sm), buf, 256)
+        return int(sm.value), buf.value.decode()
+
+    def fp64_peak(self):
+        v = ctypes.c_double()
+        _lib.call("rtx_measure_fp64_peak", self._h, ctypes.byref(v))
+        return float(v.value)
+
+
+_handles = {}
+
+
+def default_handle(device=None):
+    """Shared line-less handle of a device (TUD, Planck, ILS, apparent radiance)."""
+    dev = resolve_device(device)
+    with _lock:
+        if dev.index not in _handles:
+            _handles[dev.index] = Handle(dev)
+        return _handles[dev.index]
+
+
+# --------------------------------------------------------------------------------------------- lines
+_COLS_OPTIONAL = ("gamma_self", "n_self", "delta_self", "deltap_air", "deltap_self")
+
+
+def table_fingerprint(cols):
+    crc = 0
+    n = len(cols["nu"])
+    for k in sorted(cols):
+        v = cols[k]
+        if isinstance(v, np.ndarray):
+            crc = zlib.crc32(np.ascontiguousarray(v).view(np.uint8), crc)
+        else:
+            try:
+                crc = zlib.crc32(np.asarray(v).tobytes(), crc)
+            except Exception:
+                crc = zlib.crc32(repr(v).encode(), crc)
+        crc = zlib.crc32(k.encode(), crc)
+    return (n, crc)
+
+
+class LineDB:
+    """Device-resident line table (subsystem 1): SoA buffers sorted by line centre plus the compact
+    isotopologue table of the (M, I) pairs that occur in it.  Built from hapi-style dict-of-columns tables
+    (misc/hapi.py:438-463)."""
+
+    def __init__(self, tables, device=None):
+        """tables: one dict of columns or a list of them (hapi SourceTables)."""
+        if isinstance(tables, dict):
+            tables = [tables]
+        self.handle = Handle(device)
+        self.device = self.handle.device
+        T = spectro_tables()
+        cat = {}
+        names = ["molec_id", "local_iso_id", "nu", "sw", "elower", "gamma_air", "n_air", "delta_air"]
+        for req in names:
+            for t in tables:
+                if req not in t:
+                    if req == "delta_air":      # missing shift column -> 0 (misc/hapi.py:11115-11119)
+                        continue
+                    raise KeyError("line table lacks column %r" % req)
+        n_each = [len(t["nu"]) for t in tables]
+
+        def column(name, required, dtype=np.float64):
+            if not required and not any(name in t for t in tables):
+                return None
+            parts = []
+            for t, n in zip(tables, n_each):
+                parts.append(np.asarray(t[name], dtype=dtype) if name in t else np.zeros(n, dtype=dtype))
+            return np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(0, dtype=dtype)
+
+        mol = column("molec_id", True, np.int64)
+        iso = column("local_iso_id", True, np.int64)
+        for k in ("nu", "sw", "elower", "gamma_air", "n_air", "delta_air"):
+            cat[k] = column(k, True)
+        for k in _COLS_OPTIONAL:
+            cat[k] = column(k, False)
+        self.n_lines = int(mol.size)
+        pairs = sorted(set(zip(mol.tolist(), iso.tolist())))
+        self.pairs = pairs
+        self.pair_index = {mi: j for j, mi in enumerate(pairs)}
+        idx = np.zeros(len(pairs), dtype=np.int64)
+        for j, mi in enumerate(pairs):
+            if mi not in T["index"]:
+                raise Exception("cannot find component M,I = %d,%d." % mi)       # misc/hapi.py:11007
+            idx[j] = T["index"][mi]
+        n_iso = max(1, len(pairs))
+        self.abundance = T["iso_abundance"][idx] if len(pairs) else np.ones(1)
+        self.has_tips = T["tips_has"][idx] if len(pairs) else np.ones(1, dtype=bool)
+        mass = np.ascontiguousarray(T["iso_mass"][idx]) if len(pairs) else np.ones(1)
+        q = np.ascontiguousarray(T["tips_Q"][idx].astype(np.float64)) if len(pairs) else np.ones((1, 119))
+        tT = np.ascontiguousarray(T["tips_T"].astype(np.float64))
+        _lib.call("rtx_set_iso_table", self.handle.h, n_iso, _hptr(mass), _hptr(tT), _hptr(q))
+        self.n_iso = n_iso
+        lut = {mi: j for j, mi in enumerate(pairs)}
+        iso_idx = np.fromiter((lut[mi] for mi in zip(mol.tolist(), iso.tolist())), dtype=np.int32,
+                              count=self.n_lines)
+        self.molecules = sorted(set(m for m, _ in pairs))
+        self.iso_molecule = np.array([m for m, _ in pairs], dtype=np.int64)
+        _lib.call("rtx_lines_upload", self.handle.h, self.n_lines, _hptr(cat["nu"]), _hptr(cat["sw"]),
+                  _hptr(cat["elower"]), _hptr(cat["gamma_air"]), _hptr(cat["gamma_self"]), _hptr(cat["n_air"]),
+                  _hptr(cat["n_self"]), _hptr(cat["delta_air"]), _hptr(cat["deltap_air"]),
+                  _hptr(cat["delta_self"]), _hptr(cat["deltap_self"]), _hptr(iso_idx))
+        self.has_self = cat["gamma_self"] is not None
+        self.nu_min = float(cat["nu"].min()) if self.n_lines else 0.0
+        self.nu_max = float(cat["nu"].max()) if self.n_lines else 0.0
+
+    # -- abundance factors ------------------------------------------------------------------------
+    def iso_factors(self, Components=None, factor=1.0):
+        """factor / natural_abundance * abundance per isotopologue (misc/hapi.py:11136-11138); 0 for
+        isotopologues excluded by Components (:11066)."""
+        out = np.zeros(self.n_iso)
+        if Components is None:
+            for j in range(len(self.pairs)):
+                out[j] = factor / self.abundance[j] * self.abundance[j]
+            return out
+        T = spectro_tables()
+        for c in Components:
+            mi = (int(c[0]), int(c[1]))
+            if mi not in T["index"]:
+                raise Exception("cannot find component M,I = %d,%d." % mi)
+            if mi in self.pair_index:
+                j = self.pair_index[mi]
+                ab = c[2] if len(c) >= 3 else self.abundance[j]
+                out[j] = factor / self.abundance[j] * ab
+        return out
+
+    def check_temperatures(self, T):
+        T = np.asarray(T, dtype=float)
+        if T.size and (T.min() < 70.0 or T.max() > 3000.0):
+            raise Exception("TIPS: T must be between 70K and 3000K.")                # misc/hapi.py:9572
+
+    def check_tips(self, weights_nonzero):
+        for j, (mi, ok) in enumerate(zip(self.pairs, self.has_tips)):
+            if not ok and weights_nonzero[j]:
+                raise Exception("TIPS: no data for M,I = %d,%d." % mi)               # misc/hapi.py:9581
+
+    # -- kernels ------------------------------------------------------------------------------------
+    def voigt_sum(self, T, p, weight, grid, x_air=1.0, x_self=0.0, wing_abs=0.0, wing_hw=50.0, s_threshold=0.0,
+                  out=None, flags=0):
+        """out[s, i] = sum_lines weight[s, iso]*S(T_s)*V(grid[i]) (rtx_voigt_sum).  All arguments may be numpy
+        or CUDA tensors; returns a CUDA float64 tensor [n_states, nx]."""
+        torch = _torch()
+        dev = self.device
+        T = to_device(T, dev).reshape(-1)
+        p = to_device(p, dev).reshape(-1)
+        n_states = T.numel()
+        weight = to_device(weight, dev).reshape(n_states, self.n_iso)
+        grid = to_device(grid, dev).reshape(-1)
+        nx = grid.numel()
+        if out is None:
+            out = torch.empty((n_states, nx), dtype=torch.float64, device=dev)
+        assert out.is_contiguous() and out.numel() == n_states * nx and out.dtype == torch.float64
+        if nx == 0 or n_states == 0:
+            return out
+        if self.n_lines == 0:
+            return out.zero_()
+        _lib.call("rtx_voigt_sum", self.handle.h, n_states, _ptr(T), _ptr(p), _ptr(weight), float(x_air),
+                  float(x_self), float(wing_abs), float(wing_hw), float(s_threshold), _ptr(grid), nx, _ptr(out),
+                  int(flags), _stream(dev))
+        return out
+
+    def count_evals(self, T, p, weight, grid, x_air=1.0, x_self=0.0, wing_abs=0.0, wing_hw=50.0, s_threshold=0.0):
+        """(evals, evals in the Weideman region) exactly as SURVEY.md 8d defines them (rtx_voigt_count)."""
+        torch = _torch()
+        dev = self.device
+        T = to_device(T, dev).reshape(-1)
+        p = to_device(p, dev).reshape(-1)
+        n_states = T.numel()
+        weight = to_device(weight, dev).reshape(n_states, self.n_iso)
+        grid = to_device(grid, dev).reshape(-1)
+        if self.n_lines == 0 or grid.numel() == 0:
+            return 0, 0
+        counts = torch.zeros(2, dtype=torch.int64, device=dev)
+        # chunk the states so one launch stays below 2^31 (line, state) pairs
+        per = max(1, int(2_000_000_000 // max(1, self.n_lines)))
+        tot = np.zeros(2, dtype=np.int64)
+        for s0 in range(0, n_states, per):
+            s1 = min(n_states, s0 + per)
+            _lib.call("rtx_voigt_count", self.handle.h, s1 - s0, _ptr(T[s0:s1]), _ptr(p[s0:s1]),
+                      _ptr(weight[s0:s1].contiguous()), float(x_air), float(x_self), float(wing_abs),
+                      float(wing_hw), float(s_threshold), _ptr(grid), grid.numel(), _ptr(counts), _stream(dev))
+            tot += counts.cpu().numpy()
+        return int(tot[0]), int(tot[1])
+
+    def tips(self, T):
+        """Q(T) for every isotopologue of this table: tensor [n, n_iso] (rtx_tips)."""
+        torch = _torch()
+        T = to_device(T, self.device).reshape(-1)
+        out = torch.empty((T.numel(), self.n_iso), dtype=torch.float64, device=self.device)
+        _lib.call("rtx_tips", self.handle.h, T.numel(), _ptr(T), _ptr(out), _stream(self.device))
+        return out
+
+
+# --------------------------------------------------------------------------------------------- line-less ops
+def tud(od, T_layers, grid, Z, altitudes, mu, n_angle, return_od=False, device=None):
+    """rtx_tud.  od [n_atm, nL, nx] (or [nL, nx]), T_layers [n_atm, nL]; returns (tau, lu, ld) CUDA tensors of
+    shapes [n_atm, nx, n_alt, n_mu], same, [n_atm, nx]."""
+    torch = _torch()
+    dev = od.device if isinstance(od, torch.Tensor) and od.is_cuda else resolve_device(device)
+    h = default_handle(dev)
+    od = to_device(od, dev)
+    if od.dim() == 2:
+        od = od.unsqueeze(0)
+    n_atm, nL, nx = od.shape
+    T_layers = to_device(T_layers, dev).reshape(n_atm, nL)
+    grid = to_device(grid, dev).reshape(-1)
+    assert grid.numel() == nx
+    Z = np.ascontiguousarray(np.asarray(Z, dtype=np.float64).ravel())
+    alt = np.ascontiguousarray(np.asarray(altitudes, dtype=np.float64).ravel())
+    mu = np.ascontiguousarray(np.asarray(mu, dtype=np.float64).ravel())
+    assert Z.size == nL
+    tau = torch.empty((n_atm, nx, alt.size, mu.size), dtype=torch.float64, device=dev)
+    lu = torch.empty_like(tau)
+    ld = torch.empty((n_atm, nx), dtype=torch.float64, device=dev)
+    _lib.call("rtx_tud", h.h, n_atm, nL, _ptr(od), _ptr(T_layers), _ptr(grid), nx, _hptr(Z), _hptr(alt), alt.size,
+              _hptr(mu), mu.size, int(n_angle), int(bool(return_od)), _ptr(tau), _ptr(lu), _ptr(ld), _stream(dev))
+    return tau, lu, ld
+
+
+def planck(X, T, wavelength=False, device=None):
+    torch = _torch()
+    dev = resolve_device(device if not (isinstance(X, torch.Tensor) and X.is_cuda) else X.device)
+    h = default_handle(dev)
+    X = to_device(X, dev).reshape(-1)
+    T = to_device(T, dev).reshape(-1)
+    out = torch.empty((X.numel(), T.numel()), dtype=torch.float64, device=dev)
+    if out.numel():
+        _lib.call("rtx_planck", h.h, _ptr(X), X.numel(), _ptr(T), T.numel(), int(bool(wavelength)), _ptr(out),
+                  _stream(dev))
+    return out
+
+
+def ils_apply(mode, X, Y, centres, widths, device=None):
+    """rtx_ils_apply: Y [nx, ns] -> [n_bands, ns]."""
+    torch = _torch()
+    dev = resolve_device(device if not (isinstance(Y, torch.Tensor) and Y.is_cuda) else Y.device)
+    h = default_handle(dev)
+    X = to_device(X, dev).reshape(-1)
+    Y = to_device(Y, dev)
+    assert Y.dim() == 2 and Y.shape[0] == X.numel()
+    c = to_device(centres, dev).reshape(-1)
+    w = to_device(widths, dev).reshape(-1)
+    out = torch.empty((c.numel(), Y.shape[1]), dtype=torch.float64, device=dev)
+    if out.numel():
+        _lib.call("rtx_ils_apply", h.h, int(mode), _ptr(X), X.numel(), _ptr(Y), Y.shape[1], c.numel(), _ptr(c),
+                  _ptr(w), _ptr(out), _stream(dev))
+    return out
+
+
+def apparent_radiance(X, emis, Ts, tau, La, Ld, dT=None, return_Ls=False, device=None):
+    torch = _torch()
+    dev = resolve_device(device if not (isinstance(tau, torch.Tensor) and tau.is_cuda) else tau.device)
+    h = default_handle(dev)
+    X = to_device(X, dev).reshape(-1)
+    nx = X.numel()
+    emis = to_device(emis, dev).reshape(nx, -1)
+    Ts = to_device(Ts, dev).reshape(-1)
+    nA = Ts.numel()
+    tau, La, Ld = (to_device(a, dev).reshape(nx, nA) for a in (tau, La, Ld))
+    dTt = to_device(dT, dev).reshape(-1) if dT is not None else None
+    nT = dTt.numel() if dTt is not None else 1
+    shape = (nx, emis.shape[1], nA) + ((nT,) if dTt is not None else ())
+    L = torch.empty(shape, dtype=torch.float64, device=dev)
+    Ls = torch.empty_like(L) if return_Ls else None
+    if L.numel():
+        _lib.call("rtx_apparent_radiance", h.h, _ptr(X), nx, _ptr(emis), emis.shape[1], _ptr(Ts), nA, _ptr(tau),
+                  _ptr(La), _ptr(Ld), _ptr(dTt), nT, _ptr(L), _ptr(Ls), _stream(dev))
+    return (L, Ls) if return_Ls else L
+
+
+def hsi_pixels(X, emis, tau, La, Ld, atm_idx, T_pix, mat_idx, frac, device=None):
+    """rtx_hsi_pixels: emis [n_emis, nx], tau/La/Ld [n_atm, nx], per-pixel atm_idx [n_pix], T_pix [n_pix],
+    mat_idx/frac [n_pix, n_mix] -> L [n_pix, nx]."""
+    torch = _torch()
+    dev = resolve_device(device if not (isinstance(tau, torch.Tensor) and tau.is_cuda) else tau.device)
+    h = default_handle(dev)
+    X = to_device(X, dev).reshape(-1)
+    nx = X.numel()
+    emis = to_device(emis, dev).reshape(-1, nx)
+    tau, La, Ld = (to_device(a, dev).reshape(-1, nx) for a in (tau, La, Ld))
+    atm_idx = to_device(atm_idx, dev, torch.int32).reshape(-1)
+    n_pix = atm_idx.numel()
+    T_pix = to_device(T_pix, dev).reshape(n_pix)
+    mat_idx = to_device(mat_idx, dev, torch.int32).reshape(n_pix, -1)
+    frac = to_device(frac, dev).reshape(n_pix, mat_idx.shape[1])
+    L = torch.empty((n_pix, nx), dtype=torch.float64, device=dev)
+    if L.numel():
+        _lib.call("rtx_hsi_pixels", h.h, _ptr(X), nx, _ptr(emis), emis.shape[0], _ptr(tau), _ptr(La), _ptr(Ld),
+                  tau.shape[0], n_pix, _ptr(atm_idx), _ptr(T_pix), mat_idx.shape[1], _ptr(mat_idx), _ptr(frac),
+                  _ptr(L), _stream(dev))
+    return L

@@ -1,0 +1,305 @@
+"""Drop-in for the hot-path functions of the reference's radiative_transfer.py.
+
+Same names, arguments, return values and quirks as the reference for
+    make_spectral_axis, compute_TUD, compute_OD, planckian, compute_LWIR_apparent_radiance, ILS_MAKO
+(radiative_transfer.py:251-271, 274-392, 395-456, 792-848, 1017-1069, 1072-1263).  The arithmetic runs in the
+sm_100a kernels of libradtxfr_b200.so; numpy in -> numpy out, CUDA tensors in -> CUDA tensors out.
+
+What replaces LBLRTM: the reference obtains each layer's optical depth from an external LBLRTM binary reading a
+TAPE3 line file (radiative_transfer.py:459-501), neither of which ships with it.  Here compute_OD is the hapi
+Voigt line sum over a device-resident line database:
+    OD = sum_m  (MF_VAL_m*1e-6) * volumeConcentration(p, T) * (PL*1e5) * sigma_m(omega; T, p)
+Register the database once with set_line_database({molec_id: table}) (tables are hapi-style dicts of columns).
+No continuum model (MT_CKD lives inside LBLRTM).
+"""
+import numpy as np
+
+from . import engine, hapi_compat
+
+c1 = 1.19104295315e-16  # [J m^2 / s]  radiative_transfer.py:71
+c2 = 1.43877736830e-02  # [m K]        radiative_transfer.py:72
+
+StdAtmos = engine.spectro_tables()["std_atmos"].copy()      # radiative_transfer.py:75-148
+
+# Default options dictionary: the keys compute_TUD / compute_OD read (radiative_transfer.py:152-183).  As in the
+# reference this dict is module-level and MUTABLE: every call does opts.update(kwargs), so settings are sticky
+# across calls.  That behaviour is kept on purpose -- this is a drop-in.
+options = {
+    "T": 296.0,             # [K]
+    "P": 101325.0,          # [Pa]
+    "PL": 1.0,              # [km]
+    "MF_ID": np.array([]),
+    "MF_VAL": np.array([]),
+    "DVOUT": 0.0005,        # [cm^-1]
+    "Zs": StdAtmos[:, 1],   # [km]
+    "Ts": StdAtmos[:, 5],   # [K]
+    "Ps": StdAtmos[:, 4],   # [Pa]
+    "PLs": StdAtmos[:, 3],  # [km]
+    "MFs_VAL": StdAtmos[:, 6:14] * 1e6,  # [ppmv]
+    "MFs_ID": np.array([1, 2, 3, 4, 5, 6, 7, 22]),
+    "theta_r": 0,
+    "N_angle": 30,
+    "Altitudes": np.asarray([500]),
+    "save": False,
+    "returnOD": False,
+    # --- additions of this implementation -----------------------------------------------------
+    "LINE_DB": None,        # engine.LineDB, set through set_line_database()
+    "voigt": {},            # extra Voigt settings: OmegaWing, OmegaWingHW, IntensityThreshold, Diluent
+}
+
+
+def set_line_database(tables_by_mol, device=None, opts=options):
+    """Upload the line tables ({molec_id: dict of hapi columns}) once; stands in for the TAPE3 file of the
+    reference (radiative_transfer.py:151,491).  Returns the engine.LineDB."""
+    if isinstance(tables_by_mol, engine.LineDB):
+        db = tables_by_mol
+    else:
+        tabs = [tables_by_mol[m] for m in sorted(tables_by_mol)]
+        db = engine.LineDB(tabs, device)
+    opts["LINE_DB"] = db
+    return db
+
+
+def make_spectral_axis(Xmin, Xmax, DVOUT):
+    """radiative_transfer.py:251-271 (with the int() the reference needs on numpy >= 1.18)."""
+    nX = int(np.ceil((Xmax - Xmin) / DVOUT))
+    return np.linspace(Xmin, Xmax, nX)
+
+
+def _voigt_settings(opts):
+    v = dict(opts.get("voigt") or {})
+    dil = v.get("Diluent") or {"air": 1.0}
+    x_air = float(sum(val for k, val in dil.items() if k.lower() == "air"))
+    x_self = float(sum(val for k, val in dil.items() if k.lower() == "self"))
+    return dict(x_air=x_air, x_self=x_self, wing_abs=float(v.get("OmegaWing", 0.0)),
+                wing_hw=float(v.get("OmegaWingHW", 50.0)), s_threshold=float(v.get("IntensityThreshold", 0.0)))
+
+
+def layer_weights(db, T, P_pa, PL_km, MF_VAL, MF_ID):
+    """Per-(layer, isotopologue) column amounts: (MF_VAL*1e-6)*volumeConcentration(p,T)*(PL*1e5) for the
+    molecule of each isotopologue, times hapi's abundance factor (misc/hapi.py:11136).
+    T, P_pa, PL_km: [...]; MF_VAL: [..., nMol]; returns p [atm] and weights [..., n_iso]."""
+    T = np.asarray(T, dtype=float)
+    p = np.asarray(P_pa, dtype=float) / 101325.0
+    PL = np.asarray(PL_km, dtype=float)
+    MF_VAL = np.asarray(MF_VAL, dtype=float)
+    ids = [int(m) for m in np.asarray(MF_ID).ravel()]
+    base = db.iso_factors(None, 1.0)
+    w = np.zeros(T.shape + (db.n_iso,))
+    nconc = hapi_compat.volumeConcentration(p, T)
+    for j, mol in enumerate(db.iso_molecule.tolist()):
+        if mol in ids:
+            k = ids.index(mol)
+            w[..., j] = (MF_VAL[..., k] * 1e-6) * nconc * (PL * 1e5) * base[j]
+    return p, w
+
+
+def _require_db(opts):
+    db = opts.get("LINE_DB")
+    if db is None:
+        raise RuntimeError("no line database: call radtxfr_b200.radiative_transfer.set_line_database(...) first "
+                           "(it replaces the TAPE3 file the reference hands to LBLRTM)")
+    return db
+
+
+def compute_OD(Xmin_in, Xmax_in, opts=options, **kwargs):
+    """Optical depth of a single homogeneous layer: contract of radiative_transfer.py:395-456
+    (returns X_out = linspace(Xmin, Xmax, ceil(range/DVOUT)) and OD on it)."""
+    opts.update(kwargs)
+    db = _require_db(opts)
+    DVOUT = opts.get("DVOUT", 0.025)
+    X = make_spectral_axis(Xmin_in, Xmax_in, DVOUT)
+    T = np.array([float(opts["T"])])
+    p, w = layer_weights(db, T, np.array([float(opts["P"])]), np.array([float(opts["PL"])]),
+                         np.asarray(opts["MF_VAL"], dtype=float).reshape(1, -1), opts["MF_ID"])
+    db.check_temperatures(T)
+    od = db.voigt_sum(T, p, w, X, **_voigt_settings(opts))[0]
+    return X, od.cpu().numpy()
+
+
+def compute_TUD(Xmin, Xmax, opts=options, **kwargs):
+    """Monochromatic transmittance, upwelling and downwelling radiance: radiative_transfer.py:274-392.
+    Returns X, tau, Lu, Ld with the reference's shapes (squeeze rules :357-365)."""
+    opts.update(kwargs)
+    db = _require_db(opts)
+    Z = np.asarray(opts["Zs"], dtype=float)
+    T = np.asarray(opts["Ts"], dtype=float)
+    P = np.asarray(opts["Ps"], dtype=float)
+    PL = np.asarray(opts["PLs"], dtype=float)
+    MF = np.asarray(opts["MFs_VAL"], dtype=float)
+    ID = opts["MFs_ID"]
+    nA = opts["N_angle"]
+    Z_s = np.array([opts["Altitudes"]]).ravel()
+    mu_s = np.array([1.0 / np.cos(opts["theta_r"])]).ravel()
+    returnOD = opts["returnOD"]
+
+    X_ = make_spectral_axis(Xmin, Xmax, opts["DVOUT"])
+    db.check_temperatures(T)
+    p, w = layer_weights(db, T, P, PL, MF, ID)
+    grid = engine.to_device(X_, db.device)
+    od = db.voigt_sum(T, p, w, grid, **_voigt_settings(opts))                  # [nL, nX], layer-major
+    tau, lu, ld = engine.tud(od, T[None, :], grid, Z, Z_s, mu_s, nA, returnOD)
+    if opts["save"]:
+        B = engine.planck(grid, T).cpu().numpy()
+        np.savez("ComputeTUD.npz", OD=od.cpu().numpy().T, B=B, tau=tau[0].cpu().numpy(), Lu=lu[0].cpu().numpy(),
+                 X=X_, angles=np.linspace(0, np.pi / 2.0, nA, endpoint=False), Z_s=Z_s, mu_s=mu_s)
+    tau_ = tau[0].cpu().numpy()
+    Lu_ = lu[0].cpu().numpy()
+    Ld_ = ld[0].cpu().numpy()
+    if (len(Z_s) == 1) and (len(mu_s) == 1):
+        tau_, Lu_ = tau_[:, 0, 0], Lu_[:, 0, 0]
+    if (len(Z_s) == 1) and not (len(mu_s) == 1):
+        tau_, Lu_ = tau_[:, 0, :], Lu_[:, 0, :]
+    if not (len(Z_s) == 1) and (len(mu_s) == 1):
+        tau_, Lu_ = tau_[:, :, 0], Lu_[:, :, 0]
+    return X_, tau_, Lu_, Ld_
+
+
+def compute_TUD_batch(Xmin, Xmax, Ts, MFs_VAL, opts=options, atm_chunk=None, ils=None, **kwargs):
+    """Batched form of the production loop `for jj: compute_TUD(..., MFs_VAL=MFs_VAL[jj], Ts=Ts[jj])`
+    (Generate_LWIR_TUD.py:117-122): Ts [n_atm, nL], MFs_VAL [n_atm, nL, nMol]; everything else as compute_TUD.
+    Returns X and CUDA tensors tau, Lu [n_atm, nX, nAlt, nMu], Ld [n_atm, nX] -- or, with ils='triangle'|'gauss',
+    the MAKO-band products (X_out, tau, Lu, Ld) with nX replaced by the band count."""
+    torch = engine._torch()
+    opts.update(kwargs)
+    db = _require_db(opts)
+    Z = np.asarray(opts["Zs"], dtype=float)
+    P = np.asarray(opts["Ps"], dtype=float)
+    PL = np.asarray(opts["PLs"], dtype=float)
+    Ts = np.asarray(Ts, dtype=float)
+    MF = np.asarray(MFs_VAL, dtype=float)
+    n_atm, nL = Ts.shape
+    Z_s = np.array([opts["Altitudes"]]).ravel()
+    mu_s = np.array([1.0 / np.cos(opts["theta_r"])]).ravel()
+    X_ = make_spectral_axis(Xmin, Xmax, opts["DVOUT"])
+    nX = X_.size
+    db.check_temperatures(Ts)
+    grid = engine.to_device(X_, db.device)
+    if atm_chunk is None:
+        atm_chunk = max(1, min(n_atm, int(4e9 // (8 * nL * nX))))           # <= 4 GB of optical depth at a time
+    vs = _voigt_settings(opts)
+    outs = []
+    band = None
+    if ils is not None:
+        band = _mako_bands(X_, None, 1.0, 0.0, 1.0) if ils == "triangle" else _mako_bands_gauss()
+    od_buf = torch.empty((atm_chunk * nL, nX), dtype=torch.float64, device=db.device)
+    for a0 in range(0, n_atm, atm_chunk):
+        a1 = min(n_atm, a0 + atm_chunk)
+        na = a1 - a0
+        p, w = layer_weights(db, Ts[a0:a1], P[None, :], PL[None, :], MF[a0:a1], opts["MFs_ID"])
+        pb = np.broadcast_to(p, (na, nL))
+        od = db.voigt_sum(Ts[a0:a1].reshape(-1), np.ascontiguousarray(pb).reshape(-1), w.reshape(na * nL, -1), grid,
+                          out=od_buf[: na * nL], **vs)
+        tau, lu, ld = engine.tud(od.view(na, nL, nX), Ts[a0:a1], grid, Z, Z_s, mu_s, opts["N_angle"],
+                                 opts["returnOD"])
+        if band is not None:
+            mode = 0 if ils == "triangle" else 1
+            na_, nx_, nal, nmu = tau.shape
+            Y = torch.cat([tau.permute(1, 0, 2, 3).reshape(nX, -1), lu.permute(1, 0, 2, 3).reshape(nX, -1),
+                           ld.permute(1, 0).reshape(nX, -1)], dim=1).contiguous()
+            R = engine.ils_apply(mode, grid, Y, band[1], band[2])
+            nb = R.shape[0]
+            k = na * nal * nmu
+            tau = R[:, :k].reshape(nb, na, nal, nmu).permute(1, 0, 2, 3).contiguous()
+            lu = R[:, k:2 * k].reshape(nb, na, nal, nmu).permute(1, 0, 2, 3).contiguous()
+            ld = R[:, 2 * k:].reshape(nb, na).permute(1, 0).contiguous()
+        outs.append((tau, lu, ld))
+    tau = torch.cat([o[0] for o in outs], dim=0)
+    lu = torch.cat([o[1] for o in outs], dim=0)
+    ld = torch.cat([o[2] for o in outs], dim=0)
+    return (band[0] if band is not None else X_), tau, lu, ld
+
+
+def planckian(X_in, T_in, wavelength=False):
+    """Planck spectral radiance, radiative_transfer.py:792-848: output shape (X.size, *T.shape), in
+    uW/(cm^2 sr cm^-1), or uW/(cm^2 sr um) for wavelength input (also chosen when mean(X) < 50, :834)."""
+    torch = engine._torch()
+    as_tensor = isinstance(X_in, torch.Tensor) or isinstance(T_in, torch.Tensor)
+    if as_tensor:
+        X = X_in if isinstance(X_in, torch.Tensor) else torch.as_tensor(np.asarray(X_in, dtype=float))
+        T = T_in if isinstance(T_in, torch.Tensor) else torch.as_tensor(np.asarray(T_in, dtype=float))
+        X = X.reshape(-1).double()
+        dimsT = tuple(T.shape)
+        mean_small = bool(X.mean().item() < 50) if X.numel() else False
+    else:
+        X = np.asarray(np.copy(X_in), dtype=float).flatten()
+        T = np.asarray(np.copy(T_in), dtype=float)
+        dimsT = T.shape
+        mean_small = bool(np.mean(X) < 50) if X.size else False
+    use_wl = bool(wavelength or mean_small)
+    if use_wl and not wavelength:
+        print("Assumes X given in µm; returning L in µF")
+    L = engine.planck(X, T.reshape(-1) if as_tensor else T.flatten(), use_wl)
+    n = L.shape[0]
+    if as_tensor:
+        return L.reshape((n,) + dimsT)
+    return np.reshape(L.cpu().numpy(), (n, *dimsT))
+
+
+def compute_LWIR_apparent_radiance(X, emis, Ts, tau, La, Ld, dT=None, return_Ls=False):
+    """L = tau*(emis*B(T) + (1-emis)*Ld) + La for every (emissivity, atmosphere[, dT]) combination:
+    radiative_transfer.py:1017-1069.  Shapes: X (nX,), emis (nX,nE), Ts (nA,), tau/La/Ld (nX,nA), dT (nT,) ->
+    L (nX,nE,nA) or (nX,nE,nA,nT)."""
+    torch = engine._torch()
+    as_tensor = any(isinstance(a, torch.Tensor) for a in (emis, tau, La, Ld))
+    out = engine.apparent_radiance(X, emis, Ts, tau, La, Ld, dT=dT, return_Ls=return_Ls)
+    if as_tensor:
+        return out
+    if return_Ls:
+        return out[0].cpu().numpy(), out[1].cpu().numpy()
+    return out.cpu().numpy()
+
+
+def _mako_um():
+    return engine.spectro_tables()["mako_um"]          # radiative_transfer.py:1092-1223
+
+
+def _mako_bands(X, resFactor, fwhm_sf, shift, scale):
+    """Band centres / triangle half-bases exactly as radiative_transfer.py:1226-1241 derives them."""
+    X_out = _mako_um()
+    if resFactor is not None:
+        _x0 = np.linspace(0, 1, len(X_out))
+        _x1 = np.linspace(0, 1, int(len(X_out) * resFactor))
+        X_out = np.interp(_x1, _x0, X_out)
+    X_out = np.sort(10000.0 / X_out)
+    xmin, xmax = float(np.min(X)), float(np.max(X))
+    X_out = X_out[(X_out > xmin) & (X_out < xmax)]
+    if X_out.size == 0:
+        return X_out, X_out, X_out
+    sigma_out = fwhm_sf * np.abs(np.gradient(X_out)) * 1.6 if X_out.size > 1 else np.full(1, np.nan)
+    return X_out, scale * X_out + shift, sigma_out
+
+
+def _mako_bands_gauss():
+    X_out = np.sort(10000.0 / _mako_um())               # ILS_MAKO.py:20-21
+    return X_out, X_out, np.abs(np.gradient(X_out))
+
+
+def _ils(mode, X, Y, bands, returnX):
+    torch = engine._torch()
+    X_out, centres, widths = bands
+    as_tensor = isinstance(Y, torch.Tensor)
+    one_d = (Y.dim() if as_tensor else np.ndim(Y)) == 1
+    if as_tensor:
+        Y2 = Y.reshape(-1, 1) if one_d else Y
+        Xd = X
+    else:
+        Y2 = np.asarray(Y, dtype=float)
+        Y2 = Y2[:, None] if one_d else Y2
+        Xd = np.asarray(X, dtype=float)
+    out = engine.ils_apply(mode, Xd, Y2, centres, widths)
+    if one_d:
+        out = out[:, 0]
+    if not as_tensor:
+        out = out.cpu().numpy()
+    if returnX:
+        return X_out, out
+    return out
+
+
+def ILS_MAKO(X, Y, resFactor=None, returnX=True, fwhm_sf=1.0, shift=0.0, scale=1.0):
+    """Apply the MAKO triangle instrument line shape: radiative_transfer.py:1072-1263."""
+    torch = engine._torch()
+    Xh = X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(X, dtype=float)
+    bands = _mako_bands(Xh, resFactor, fwhm_sf, shift, scale)
+    return _ils(0, X, Y, bands, returnX)

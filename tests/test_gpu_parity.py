@@ -1,0 +1,305 @@
+"""GPU parity tests: the CUDA path (through the Python shim -> ctypes -> C ABI) against the CPU oracle
+(oracle/port.py) on the same seeded inputs, and against the golden vectors minted from the reference.
+
+Tolerance (SURVEY.md 8c, FP64 path): |gpu-ref| <= 1e-9*|ref| + 1e-12*max|ref| per output array, and max relative
+error <= 1e-9 over points with |ref| >= 1e-6*max|ref|.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import golden, assert_parity
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+
+pytestmark = pytest.mark.gpu
+
+RTOL, FLOOR = 1e-9, 1e-12
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from radtxfr_b200 import hapi_compat, radiative_transfer, ILS_MAKO, engine, synthetic
+    from oracle import port
+    return dict(torch=torch, hapi=hapi_compat, rt=radiative_transfer, ilsg=ILS_MAKO, engine=engine, syn=synthetic,
+                port=port)
+
+
+def test_library_is_native(mods):
+    """The product path must be the in-tree CUDA library, on a B200."""
+    from radtxfr_b200 import _lib
+    assert os.path.isfile(_lib.LIB_PATH)
+    h = mods["engine"].default_handle()
+    sm, name = h.device_info()
+    assert sm > 0 and name
+    maps = open("/proc/self/maps").read()
+    assert "libradtxfr_b200.so" in maps
+
+
+def test_tips_device(mods):
+    g = golden("tips.npz")
+    for (m, i), row in zip(g["mi"], g["Q"]):
+        for T, q in zip(g["T"], row):
+            got = mods["hapi"].PYTIPS(int(m), int(i), float(T))
+            assert abs(got - q) <= 1e-13 * abs(q), (m, i, T, got, q)
+    with pytest.raises(Exception):
+        mods["hapi"].PYTIPS(1, 1, 69.0)
+
+
+def test_xsect_golden_cases(mods):
+    """absorptionCoefficient_Voigt against the reference's own outputs (tests/golden/xsect.npz)."""
+    import make_golden as mg
+    hapi, syn = mods["hapi"], mods["syn"]
+    g = golden("xsect.npz")
+    for name, seed, n, (lo, hi, npts), T, p, kw in mg.XS_CASES:
+        cols = syn.synthetic_lines(seed, n, lo - 25.0, hi + 25.0, 1)
+        hapi.storeTable("t_" + name, cols)
+        grid = np.linspace(lo, hi, npts)
+        om, xs = hapi.absorptionCoefficient_Voigt(SourceTables="t_" + name, Environment={"T": T, "p": p},
+                                                  OmegaGrid=grid, **kw)
+        assert isinstance(xs, np.ndarray) and xs.dtype == np.float64 and np.array_equal(om, grid)
+        assert_parity(xs, g["xs_" + name], RTOL, FLOOR, "xsect " + name)
+
+
+@pytest.mark.parametrize("K", [1, 2, 4, 8])
+@pytest.mark.parametrize("fast", [0, 1])
+def test_voigt_all_tile_sizes(mods, K, fast):
+    """Every tile-size instantiation of the kernel, both reciprocal variants, on a multi-state problem that
+    mixes wide (1 atm) and narrow (top of atmosphere) lines."""
+    port, syn, engine = mods["port"], mods["syn"], mods["engine"]
+    cols = syn.synthetic_lines(50, 400, 985.0, 1015.0, 1)
+    db = engine.LineDB(cols)
+    grid = np.linspace(990.0, 1010.0, 5003)
+    states = [(296.0, 1.0), (250.0, 0.2), (225.53, 7.3 / 101325.0), (216.7, 0.02)]
+    T = np.array([s[0] for s in states]); p = np.array([s[1] for s in states])
+    w = np.tile(db.iso_factors(None, 1.0), (len(states), 1))
+    out = db.voigt_sum(T, p, w, grid, flags=fast | (K << 8)).cpu().numpy()
+    for k, (Tk, pk) in enumerate(states):
+        _, ref = port.absorption_coefficient_voigt(cols, T=Tk, p=pk, OmegaGrid=grid)
+        assert_parity(out[k], ref, RTOL, FLOOR, "K=%d fast=%d state %d" % (K, fast, k))
+
+
+def test_voigt_eval_counter(mods):
+    port, syn, engine = mods["port"], mods["syn"], mods["engine"]
+    cols = syn.synthetic_lines(51, 300, 985.0, 1015.0, 1)
+    db = engine.LineDB(cols)
+    grid = np.linspace(990.0, 1010.0, 4001)
+    tot = totw = 0
+    states = [(296.0, 1.0), (230.0, 0.01), (225.53, 7.3 / 101325.0)]
+    for Tk, pk in states:
+        _, _, e, ew = port.absorption_coefficient_voigt(cols, T=Tk, p=pk, OmegaGrid=grid, return_evals=True)
+        tot += e; totw += ew
+    T = np.array([s[0] for s in states]); p = np.array([s[1] for s in states])
+    w = np.tile(db.iso_factors(None, 1.0), (len(states), 1))
+    e, ew = db.count_evals(T, p, w, grid)
+    assert (e, ew) == (tot, totw) and ew > 0
+
+
+def test_voigt_edge_cases(mods):
+    torch, port, syn, engine, hapi = (mods[k] for k in ("torch", "port", "syn", "engine", "hapi"))
+    cols = syn.synthetic_lines(52, 100, 800.0, 900.0, 1)
+    # unsorted table rows, lines far outside the grid, single-point and empty grids, non-uniform grid
+    perm = np.random.default_rng(0).permutation(100)
+    shuffled = {k: np.asarray(v)[perm] for k, v in cols.items()}
+    hapi.storeTable("edge", shuffled)
+    rng = np.random.default_rng(1)
+    grid = np.sort(np.concatenate([rng.uniform(840, 860, 700), np.linspace(845, 846, 301)]))
+    _, xs = hapi.absorptionCoefficient_Voigt(SourceTables="edge", OmegaGrid=grid, Environment={"T": 260.0, "p": 0.5})
+    _, ref = port.absorption_coefficient_voigt(cols, T=260.0, p=0.5, OmegaGrid=grid)
+    assert_parity(xs, ref, RTOL, FLOOR, "non-uniform grid")
+    _, xs1 = hapi.absorptionCoefficient_Voigt(SourceTables="edge", OmegaGrid=np.array([850.0]))
+    _, ref1 = port.absorption_coefficient_voigt(cols, OmegaGrid=np.array([850.0]))
+    assert_parity(xs1, ref1, RTOL, FLOOR, "one point")
+    _, xs0 = hapi.absorptionCoefficient_Voigt(SourceTables="edge", OmegaGrid=np.zeros(0))
+    assert xs0.shape == (0,)
+    far = np.linspace(2000.0, 2010.0, 101)
+    _, xsf = hapi.absorptionCoefficient_Voigt(SourceTables="edge", OmegaGrid=far)
+    assert np.array_equal(xsf, np.zeros(101))
+    # empty table
+    empty = {k: np.asarray(v)[:0] for k, v in cols.items()}
+    hapi.storeTable("empty", empty)
+    _, xse = hapi.absorptionCoefficient_Voigt(SourceTables="empty", OmegaGrid=far)
+    assert np.array_equal(xse, np.zeros(101))
+    # missing table / bad GammaL
+    with pytest.raises(Exception, match="no such table"):
+        hapi.absorptionCoefficient_Voigt(SourceTables="nope", OmegaGrid=far)
+    with pytest.raises(Exception, match="Unknown GammaL"):
+        hapi.absorptionCoefficient_Voigt(SourceTables="edge", OmegaGrid=far, GammaL="gamma_h2")
+    with pytest.raises(Exception, match="TIPS"):
+        hapi.absorptionCoefficient_Voigt(SourceTables="edge", OmegaGrid=far, Environment={"T": 50.0, "p": 1.0})
+    # misaligned device grid (8-byte but not 16-byte aligned) takes the non-TMA staging path
+    db = engine.LineDB(cols)
+    g = torch.from_numpy(np.concatenate([[0.0], np.linspace(840, 860, 3001)])).cuda()[1:]
+    assert g.data_ptr() % 16 == 8
+    w = db.iso_factors(None, 1.0)[None, :]
+    o1 = db.voigt_sum(np.array([296.0]), np.array([1.0]), w, g).cpu().numpy()
+    o2 = db.voigt_sum(np.array([296.0]), np.array([1.0]), w, g.clone()).cpu().numpy()
+    assert np.array_equal(o1, o2)
+    # tensors in -> tensors out
+    om, xt = hapi.absorptionCoefficient_Voigt(SourceTables="edge", OmegaGrid=torch.from_numpy(grid).cuda(),
+                                              Environment={"T": 260.0, "p": 0.5})
+    assert xt.is_cuda and np.array_equal(xt.cpu().numpy(), xs)
+
+
+def test_voigt_two_tables_and_deterministic(mods):
+    port, syn, hapi = mods["port"], mods["syn"], mods["hapi"]
+    a = syn.synthetic_lines(53, 150, 900.0, 1000.0, 1)
+    b = syn.synthetic_lines(54, 150, 900.0, 1000.0, 2)
+    hapi.storeTable("ta", a); hapi.storeTable("tb", b)
+    grid = np.linspace(920.0, 980.0, 6001)
+    _, xs = hapi.absorptionCoefficient_Voigt(SourceTables=["ta", "tb"], OmegaGrid=grid)
+    _, ra = port.absorption_coefficient_voigt(a, OmegaGrid=grid)
+    _, rb = port.absorption_coefficient_voigt(b, OmegaGrid=grid)
+    assert_parity(xs, ra + rb, RTOL, FLOOR, "two tables")
+    _, xs2 = hapi.absorptionCoefficient_Voigt(SourceTables=["ta", "tb"], OmegaGrid=grid)
+    assert np.array_equal(xs, xs2)            # bit-reproducible run to run
+
+
+def _tud_setup(mods):
+    import make_golden as mg
+    atm, tabs = mg.tud_inputs()
+    rt = mods["rt"]
+    opts = dict(rt.options)
+    rt.set_line_database(tabs, opts=opts)
+    kw = dict(Zs=atm["Zs"], Ts=atm["Ts"], Ps=atm["Ps"], PLs=atm["PLs"], MFs_VAL=atm["MFs_VAL"], MFs_ID=atm["MFs_ID"],
+              DVOUT=0.05)
+    return atm, tabs, opts, kw
+
+
+def test_tud_golden(mods):
+    """compute_TUD against the reference's own outputs (tests/golden/tud.npz), incl. the nL-overwrite quirk."""
+    rt = mods["rt"]
+    g = golden("tud.npz")
+    atm, tabs, opts, kw = _tud_setup(mods)
+    X, tau, Lu, Ld = rt.compute_TUD(700.0, 750.0, opts=dict(opts), **kw)
+    assert np.array_equal(X, g["X"]) and tau.shape == X.shape and Ld.shape == X.shape
+    for a, b, w in ((tau, g["tau"], "tau"), (Lu, g["Lu"], "Lu"), (Ld, g["Ld"], "Ld")):
+        assert_parity(a, b, RTOL, FLOOR, w)
+    X, tau, Lu, Ld = rt.compute_TUD(700.0, 750.0, opts=dict(opts), Altitudes=np.array([1.0, 10.0, 500.0, 3.0]),
+                                    N_angle=7, **kw)
+    assert tau.shape == (X.size, 4)
+    for a, b, w in ((tau, g["tau_alt"], "tau_alt"), (Lu, g["Lu_alt"], "Lu_alt"), (Ld, g["Ld_alt"], "Ld_alt")):
+        assert_parity(a, b, RTOL, FLOOR, w)
+    X, tau, Lu, Ld = rt.compute_TUD(700.0, 750.0, opts=dict(opts), returnOD=True, theta_r=0.6, N_angle=4, **kw)
+    for a, b, w in ((tau, g["tau_od"], "tau_od"), (Lu, g["Lu_od"], "Lu_od"), (Ld, g["Ld_od"], "Ld_od")):
+        assert_parity(a, b, RTOL, FLOOR, w)
+
+
+def test_tud_sticky_options_and_compute_od(mods):
+    rt, port = mods["rt"], mods["port"]
+    atm, tabs, opts, kw = _tud_setup(mods)
+    o = dict(opts)
+    rt.compute_TUD(700.0, 710.0, opts=o, returnOD=True, **kw)
+    assert o["returnOD"] is True and o["DVOUT"] == 0.05       # opts.update(kwargs): settings stick (ref :303)
+    X, od = rt.compute_OD(700.0, 750.0, opts=dict(opts), T=atm["Ts"][3], P=atm["Ps"][3], PL=atm["PLs"][3],
+                          MF_VAL=atm["MFs_VAL"][3], MF_ID=atm["MFs_ID"], DVOUT=0.05)
+    ref = port.layer_od(tabs, X, atm["Ts"][3], atm["Ps"][3], atm["PLs"][3], atm["MFs_VAL"][3], atm["MFs_ID"])
+    assert_parity(od, ref, RTOL, FLOOR, "compute_OD")
+    with pytest.raises(RuntimeError, match="line database"):
+        rt.compute_TUD(700.0, 710.0, opts={k: v for k, v in rt.options.items() if k != "LINE_DB"})
+
+
+def test_tud_batch_matches_single(mods):
+    rt, syn = mods["rt"], mods["syn"]
+    atm, tabs, opts, kw = _tud_setup(mods)
+    Ts, MF = syn.perturbed_atmospheres(2, 5)
+    o = dict(opts)
+    X, tau, lu, ld = rt.compute_TUD_batch(700.0, 730.0, Ts, MF[:, :, :], opts=o, atm_chunk=2,
+                                          **{k: v for k, v in kw.items() if k not in ("Ts", "MFs_VAL")})
+    assert tau.shape == (5, X.size, 1, 1)
+    for j in (0, 3, 4):
+        Xs, t1, u1, d1 = rt.compute_TUD(700.0, 730.0, opts=dict(opts), **dict(kw, Ts=Ts[j], MFs_VAL=MF[j]))
+        assert np.array_equal(tau[j, :, 0, 0].cpu().numpy(), t1)
+        assert np.array_equal(lu[j, :, 0, 0].cpu().numpy(), u1)
+        assert np.array_equal(ld[j].cpu().numpy(), d1)
+    Xb, tb, ub, db_ = rt.compute_TUD_batch(700.0, 1400.0, Ts[:2], MF[:2], opts=dict(opts), ils="triangle",
+                                           **dict({k: v for k, v in kw.items() if k not in ("Ts", "MFs_VAL")}, DVOUT=0.25))
+    Xs, t1, u1, d1 = rt.compute_TUD(700.0, 1400.0, opts=dict(opts), **dict(kw, Ts=Ts[1], MFs_VAL=MF[1], DVOUT=0.25))
+    xo, tt = rt.ILS_MAKO(Xs, t1)
+    assert np.array_equal(xo, Xb) and np.array_equal(tb[1, :, 0, 0].cpu().numpy(), tt)
+
+
+def test_sensor_golden(mods):
+    rt, ilsg = mods["rt"], mods["ilsg"]
+    g = golden("sensor.npz")
+    X, Y1, Y2 = g["X"], g["Y1"], g["Y2"]
+    Xo, t1 = rt.ILS_MAKO(X, Y1)
+    assert np.array_equal(Xo, g["Xo"]) and t1.shape == (128,)
+    assert_parity(t1, g["tri1"], RTOL, FLOOR, "tri 1-D")
+    t2 = rt.ILS_MAKO(X, Y2, returnX=False)
+    assert t2.shape == (128, 5)
+    assert_parity(t2, g["tri2"], RTOL, FLOOR, "tri 2-D")
+    Xr, t3 = rt.ILS_MAKO(X, Y2, resFactor=2, fwhm_sf=0.8, shift=0.3, scale=1.001)
+    assert np.array_equal(Xr, g["Xo_res"])
+    assert_parity(t3, g["tri_res"], RTOL, FLOOR, "tri resFactor")
+    Xc, t4 = rt.ILS_MAKO(g["Xc"], Y2[:4001])
+    assert np.array_equal(Xc, g["Xo_clip"])
+    assert_parity(t4, g["tri_clip"], RTOL, FLOOR, "tri clipped")
+    Xg, g1 = ilsg.ILS_MAKO(X, Y1)
+    assert np.array_equal(Xg, g["Xg"])
+    assert_parity(g1, g["gauss1"], RTOL, FLOOR, "gauss 1-D")
+    assert_parity(ilsg.ILS_MAKO(X, Y2)[1], g["gauss2"], RTOL, FLOOR, "gauss 2-D")
+    args = (g["Xo"], g["emis"], g["Ts"], g["tau"], g["La"], g["Ld"])
+    assert_parity(rt.compute_LWIR_apparent_radiance(*args), g["L0"], RTOL, FLOOR, "apparent")
+    L1, Ls1 = rt.compute_LWIR_apparent_radiance(*args, dT=g["dT"], return_Ls=True)
+    assert L1.shape == g["L1"].shape
+    assert_parity(L1, g["L1"], RTOL, FLOOR, "apparent dT")
+    assert_parity(Ls1, g["Ls1"], RTOL, FLOOR, "apparent Ls")
+    assert_parity(rt.planckian(500.0, 296.0), g["planck_kat"], RTOL, FLOOR, "planck kat")
+    assert_parity(rt.planckian(np.linspace(700, 1500, 8001), np.array([280.0, 300.0])), g["planck_grid"], RTOL, FLOOR)
+    Pw = rt.planckian(np.linspace(7.5, 13.5, 61), np.array([[280.0, 300.0], [310., 250.]]), wavelength=True)
+    assert Pw.shape == (61, 2, 2)
+    assert_parity(Pw, g["planck_um"], RTOL, FLOOR, "planck um")
+
+
+def test_hsi_pixels(mods):
+    engine, port, syn = mods["engine"], mods["port"], mods["syn"]
+    rng = np.random.default_rng(7)
+    X = port.mako_axis(np.array([700.0, 1400.0]))
+    nE, nA, nP = 9, 4, 1000
+    emis = syn.synthetic_emissivities(3, nE, X).T.copy()
+    tau = rng.uniform(0.2, 1, (nA, X.size)); La = rng.uniform(0, 300, (nA, X.size)); Ld = rng.uniform(0, 600, (nA, X.size))
+    atm = rng.integers(0, nA, nP); Tp = rng.uniform(270, 320, nP)
+    mat = rng.integers(0, nE, (nP, 2)); fr = rng.uniform(0, 1, (nP, 2)); fr /= fr.sum(1)[:, None]
+    L = engine.hsi_pixels(X, emis, tau, La, Ld, atm, Tp, mat, fr).cpu().numpy()
+    em = np.array([np.dot(fr[i], emis[mat[i]]) for i in range(nP)])       # LWIR_HSI_Generator.py:159
+    B = port.planckian(X, Tp).T
+    ref = tau[atm] * (em * B + (1 - em) * Ld[atm]) + La[atm]
+    assert_parity(L, ref, RTOL, FLOOR, "hsi pixels")
+
+
+def test_full_size_properties(mods):
+    """Config-2-sized grid (800 000 points, 66 layers): size-independent properties instead of a CPU oracle run.
+    (1) linearity in the column amounts, (2) bit-reproducibility, (3) tile-size independence, (4) the first 2 000
+    points of three layers against the oracle, (5) TUD invariants: 0<tau<=1, Lu -> B where the column is opaque."""
+    torch, rt, syn, engine, port = (mods[k] for k in ("torch", "rt", "syn", "engine", "port"))
+    atm = syn.standard_atmosphere()
+    tabs = syn.config2_tables(scale=0.02)
+    db = engine.LineDB([tabs[m] for m in sorted(tabs)])
+    X = rt.make_spectral_axis(700.0, 1500.0, 0.001)
+    assert X.size == 800000
+    p, w = rt.layer_weights(db, atm["Ts"], atm["Ps"], atm["PLs"], atm["MFs_VAL"], atm["MFs_ID"])
+    grid = torch.from_numpy(X).cuda()
+    od = db.voigt_sum(atm["Ts"], p, w, grid)
+    assert torch.isfinite(od).all() and (od >= 0).all()
+    od2 = db.voigt_sum(atm["Ts"], p, 2.0 * w, grid)
+    assert torch.equal(od2, 2.0 * od)                                   # exact: power-of-two scaling
+    assert torch.equal(od, db.voigt_sum(atm["Ts"], p, w, grid))         # bit-reproducible
+    od_k2 = db.voigt_sum(atm["Ts"], p, w, grid, flags=2 << 8)
+    err = (od_k2 - od).abs().max().item() / od.abs().max().item()
+    assert err < 1e-13
+    sub = slice(0, 2000)
+    for layer in (0, 30, 65):
+        ref = port.layer_od(tabs, X[sub], atm["Ts"][layer], atm["Ps"][layer], atm["PLs"][layer],
+                            atm["MFs_VAL"][layer], atm["MFs_ID"])
+        # the oracle sees only the first 2000 points, the windows are point-wise so the values must agree
+        assert_parity(od[layer, sub].cpu().numpy(), ref, RTOL, FLOOR, "layer %d" % layer)
+    tau, lu, ld = engine.tud(od, atm["Ts"][None, :], grid, atm["Zs"], [500.0], [1.0], 30)
+    tau = tau[0, :, 0, 0]; lu = lu[0, :, 0, 0]; ld = ld[0]
+    assert (tau >= 0).all() and (tau <= 1).all() and torch.isfinite(lu).all() and torch.isfinite(ld).all()
+    B0 = torch.from_numpy(port.planckian(X, atm["Ts"][:1])[:, 0]).cuda()
+    assert (ld <= B0 * (1 + 1e-12)).all()                               # downwelling never exceeds the warmest layer

@@ -1,0 +1,101 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, host-side shim logic, synthetic
+workload generators.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from radtxfr_b200 import build, _lib
+    build.build()
+    return _lib.lib()
+
+
+def test_exports_every_declared_symbol(L):
+    hdr = open(os.path.join(ROOT, "include", "radtxfr_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(rtx_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(L, name), "library does not export %s" % name
+    from radtxfr_b200 import _lib
+    assert sorted(_lib.EXPORTS) == declared, "ctypes binding and header disagree"
+
+
+def test_fails_loudly_without_gpu(L):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = ctypes.c_void_p()
+    rc = L.rtx_create(0, ctypes.byref(h))
+    assert rc < 0 and b"no CPU fallback" in L.rtx_last_error()
+    from radtxfr_b200 import hapi_compat, _lib, synthetic
+    hapi_compat.storeTable("x", synthetic.synthetic_lines(0, 10, 800, 900))
+    with pytest.raises(_lib.RtxError):
+        hapi_compat.absorptionCoefficient_Voigt(SourceTables="x", OmegaGrid=np.linspace(800, 900, 11))
+
+
+def test_weideman_coefficients_match_fft_recipe(L):
+    from oracle import port
+    a = np.zeros(24)
+    L.rtx_weideman_coeffs(a.ctypes.data_as(ctypes.c_void_p))
+    ref, Lw = port.weideman_coeffs(24)
+    assert np.array_equal(a, ref)
+    src = open(os.path.join(ROOT, "radtxfr_b200", "csrc", "rtx_common.cuh")).read()
+    assert repr(Lw) in src
+
+
+def test_null_and_state_errors(L):
+    assert L.rtx_voigt_sum(None, 1, None, None, None, 1.0, 0.0, 0.0, 50.0, 0.0, None, 1, None, 0, None) < 0
+    assert b"null handle" in L.rtx_last_error()
+    assert L.rtx_destroy(None) == 0
+
+
+def test_grids_and_bands():
+    from radtxfr_b200 import radiative_transfer as rt, hapi_compat
+    from oracle import port
+    X = rt.make_spectral_axis(700.0, 1500.0, 0.1)
+    assert X.size == 8000 and abs((X[1] - X[0]) - 0.1000125) < 1e-6
+    assert np.array_equal(X, port.make_spectral_axis(700.0, 1500.0, 0.1))
+    g = hapi_compat._hapi_grid((800.0, 1300.0), 0.01)
+    assert g.size == 50001 and g[0] == 800.0
+    Xo, c, s = rt._mako_bands(np.array([700.0, 1400.0]), None, 1.0, 0.0, 1.0)
+    assert Xo.size == 128 and abs(Xo[0] - 759.91306595) < 1e-7 and abs(Xo[-1] - 1320.81203524) < 1e-7
+    assert 4.0 < s.min() < 4.01 and 12.40 < s.max() < 12.41
+    assert np.array_equal(Xo, port.mako_axis(np.array([700.0, 1400.0])))
+    Xo2, _, _ = rt._mako_bands(np.array([700.0, 1400.0]), 2, 1.0, 0.0, 1.0)
+    assert Xo2.size == 256
+    Xo3, _, _ = rt._mako_bands(np.array([800.0, 1200.0]), None, 1.0, 0.0, 1.0)
+    assert 0 < Xo3.size < 128 and Xo3.min() > 800 and Xo3.max() < 1200
+
+
+def test_synthetic_workloads_are_seeded():
+    from radtxfr_b200 import synthetic as syn
+    a, b = syn.config1_lines(500), syn.config1_lines(500)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    assert np.all(np.diff(a["nu"]) >= 0) and a["nu"].min() >= 775 and a["nu"].max() <= 1325
+    atm = syn.standard_atmosphere()
+    assert atm["Ts"].shape == (66,) and atm["MFs_VAL"].shape == (66, 8) and atm["Ts"][0] == 287.87
+    Ts, MF = syn.perturbed_atmospheres(2, 7)
+    assert Ts.shape == (7, 66) and MF.shape == (7, 66, 8) and Ts.min() >= 180 and Ts.max() <= 330
+    assert np.array_equal(MF[:, :, 1], np.repeat(atm["MFs_VAL"][None, :, 1], 7, axis=0))   # CO2 fixed
+    t = syn.config2_tables(scale=0.001)
+    m = syn.merge_tables(t)
+    assert len(m["nu"]) == sum(len(v["nu"]) for v in t.values()) and np.all(np.diff(m["nu"]) >= 0)
+    e = syn.synthetic_emissivities(3, 5, np.linspace(760, 1320, 128))
+    assert e.shape == (128, 5) and e.min() >= 1e-4 and e.max() <= 1 - 1e-4
+
+
+def test_layer_weights_match_oracle_wiring():
+    """Host-side column amounts (no GPU): compare with the factor the oracle applies per molecule."""
+    from radtxfr_b200 import hapi_compat
+    from oracle import port
+    for p, T in ((1.0, 296.0), (0.3, 250.0)):
+        assert hapi_compat.volumeConcentration(p, T) == port.volume_concentration(p, T)
+    assert hapi_compat.abundance(1, 1) == 0.997317 and hapi_compat.molecularMass(2, 1) == 43.98983
