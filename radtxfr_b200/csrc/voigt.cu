@@ -33,7 +33,9 @@
 namespace {
 
 constexpr int NT = 256;         // threads per CTA
-constexpr int LCHUNK = 256;     // lines per prologue chunk (one per thread)
+constexpr int ROUNDS = 2;       // prologue rounds per chunk (one line per thread per round)
+constexpr int LCHUNK = NT * ROUNDS;  // lines per chunk
+constexpr int WREG = 32 * ROUNDS;    // list slots owned by one warp
 constexpr int NARROW_MAX = 64;  // windows of at most this many tile points go to pass 2 entirely
 
 __constant__ double c_weideman[24] = {
@@ -312,111 +314,121 @@ __global__ void __launch_bounds__(NT, 2) voigt_tile_kernel(const VoigtParams P) 
   const int first = P.bins[bi], last = P.bins[bi + 1];
   const int own_lo = warp * (TILE / (NT / 32)), own_hi = own_lo + TILE / (NT / 32);
 
-  for (int c0 = first; c0 < last; c0 += LCHUNK) {
-    // ---- prologue: one thread, one line ------------------------------------------------------
-    const int li = c0 + tid;
-    bool is_wide = false, has_seg = false;
-    WideRec wr;
-    SegRec sr;
-    if (li < last) {
-      const LineState L = line_state(P, li, s, T, p, lnr);
-      if (L.keep) {
-        const int lo = bisect_right_dev(s_grid, TILE, L.nu - L.W);      // misc/hapi.py:11133
-        const int hi = bisect_right_dev(s_grid, TILE, L.nu + L.W);      // misc/hapi.py:11134
-        if (hi > lo) {
-          const double cte = RTX_SQRT_LN2 / L.gamD;                      // misc/hapi.py:9900
-          const double y = L.gam0 * cte;                                 // misc/hapi.py:9913
-          const double h = L.gamD * L.gamD / RTX_LN2;                    // 1/cte^2
-          const double g2 = L.gam0 * L.gam0;
-          const double e = 0.5 * h + g2;
-          const double a = L.amp * L.gam0 / RTX_PI;
-          sr.sg0 = wr.sg0 = L.sg0;
-          sr.a = wr.a = a;
-          sr.ae = wr.ae = a * e;
-          sr.f = wr.f = 2.0 * g2 - h;
-          sr.g = wr.g = e * e;
-          sr.cte = cte;
-          sr.y = y;
-          sr.cw = L.amp * (cte / RTX_SQRT_PI);
-          int clo = lo, chi = lo;                                        // empty Weideman core
-          if (y < 15.0) {
-            // the mask |x|+y<15 is a contiguous index range around sg0; find it with the exact predicate
-            int m = bisect_left_dev(s_grid, TILE, L.sg0);
-            m = max(lo, min(hi, m));
-            int a0 = lo, a1 = m;                                         // first true in [lo, m)
-            while (a0 < a1) {
-              const int mid = (a0 + a1) >> 1;
-              if (in_weideman(s_grid[mid], L.sg0, cte, y)) a1 = mid; else a0 = mid + 1;
+  // Lines are dealt to chunks round-robin (chunk c takes candidates c, c+nchunks, ...), so every chunk spans
+  // the tile's whole candidate range and the eight warps' slices receive equal shares of every chunk.
+  const int ncand = last - first;
+  const int nchunks = (ncand + LCHUNK - 1) / LCHUNK;
+  for (int c = 0; c < nchunks; ++c) {
+    // ---- prologue: one lane, one line per round; survivors compacted per warp (ballot, no atomics) -------
+    int nw = 0, ns = 0;
+#pragma unroll 1
+    for (int r = 0; r < ROUNDS; ++r) {
+      const int k = (r * (NT / 32) + warp) * 32 + lane;
+      const int li = first + c + k * nchunks;
+      bool is_wide = false, has_seg = false;
+      WideRec wr;
+      SegRec sr;
+      if (li < last) {
+        const LineState L = line_state(P, li, s, T, p, lnr);
+        if (L.keep) {
+          const int lo = bisect_right_dev(s_grid, TILE, L.nu - L.W);      // misc/hapi.py:11133
+          const int hi = bisect_right_dev(s_grid, TILE, L.nu + L.W);      // misc/hapi.py:11134
+          if (hi > lo) {
+            const double cte = RTX_SQRT_LN2 / L.gamD;                      // misc/hapi.py:9900
+            const double y = L.gam0 * cte;                                 // misc/hapi.py:9913
+            const double h = L.gamD * L.gamD / RTX_LN2;                    // 1/cte^2
+            const double g2 = L.gam0 * L.gam0;
+            const double e = 0.5 * h + g2;
+            const double a = L.amp * L.gam0 / RTX_PI;
+            sr.sg0 = wr.sg0 = L.sg0;
+            sr.a = wr.a = a;
+            sr.ae = wr.ae = a * e;
+            sr.f = wr.f = 2.0 * g2 - h;
+            sr.g = wr.g = e * e;
+            sr.cte = cte;
+            sr.y = y;
+            sr.cw = L.amp * (cte / RTX_SQRT_PI);
+            int clo = lo, chi = lo;                                        // empty Weideman core
+            if (y < 15.0) {
+              // the mask |x|+y<15 is a contiguous index range around sg0; find it with the exact predicate
+              int m = bisect_left_dev(s_grid, TILE, L.sg0);
+              m = max(lo, min(hi, m));
+              int a0 = lo, a1 = m;                                         // first true in [lo, m)
+              while (a0 < a1) {
+                const int mid = (a0 + a1) >> 1;
+                if (in_weideman(s_grid[mid], L.sg0, cte, y)) a1 = mid; else a0 = mid + 1;
+              }
+              clo = a0;
+              a0 = m; a1 = hi;                                             // first false in [m, hi)
+              while (a0 < a1) {
+                const int mid = (a0 + a1) >> 1;
+                if (in_weideman(s_grid[mid], L.sg0, cte, y)) a0 = mid + 1; else a1 = mid;
+              }
+              chi = a0;
             }
-            clo = a0;
-            a0 = m; a1 = hi;                                             // first false in [m, hi)
-            while (a0 < a1) {
-              const int mid = (a0 + a1) >> 1;
-              if (in_weideman(s_grid[mid], L.sg0, cte, y)) a0 = mid + 1; else a1 = mid;
+            if (hi - lo <= NARROW_MAX) {
+              has_seg = true; sr.s = lo; sr.e = hi;
+            } else {
+              is_wide = true;
+              wr.lo = (short)lo; wr.hi = (short)hi; wr.clo = (short)clo; wr.chi = (short)chi;
+              if (chi > clo) { has_seg = true; sr.s = clo; sr.e = chi; }
             }
-            chi = a0;
-          }
-          if (hi - lo <= NARROW_MAX) {
-            has_seg = true; sr.s = lo; sr.e = hi;
-          } else {
-            is_wide = true;
-            wr.lo = (short)lo; wr.hi = (short)hi; wr.clo = (short)clo; wr.chi = (short)chi;
-            if (chi > clo) { has_seg = true; sr.s = clo; sr.e = chi; }
           }
         }
       }
+      const unsigned bw = __ballot_sync(0xffffffffu, is_wide), bs = __ballot_sync(0xffffffffu, has_seg);
+      const unsigned lt = (1u << lane) - 1u;
+      if (is_wide) s_wide[warp * WREG + nw + __popc(bw & lt)] = wr;
+      if (has_seg) s_seg[warp * WREG + ns + __popc(bs & lt)] = sr;
+      nw += __popc(bw);
+      ns += __popc(bs);
     }
-    // ---- deterministic compaction ----------------------------------------------------------------
-    const unsigned bw = __ballot_sync(0xffffffffu, is_wide), bs = __ballot_sync(0xffffffffu, has_seg);
-    const unsigned lt = (1u << lane) - 1u;
-    if (lane == 0) { s_cnt[0][warp] = __popc(bw); s_cnt[1][warp] = __popc(bs); }
-    __syncthreads();
-    int offw = 0, offs = 0, n_wide = 0, n_seg = 0;
-#pragma unroll
-    for (int k = 0; k < NT / 32; ++k) {
-      const int cw = s_cnt[0][k], cs = s_cnt[1][k];
-      if (k < warp) { offw += cw; offs += cs; }
-      n_wide += cw; n_seg += cs;
-    }
-    if (is_wide) s_wide[offw + __popc(bw & lt)] = wr;
-    if (has_seg) s_seg[offs + __popc(bs & lt)] = sr;
+    if (lane == 0) { s_cnt[0][warp] = nw; s_cnt[1][warp] = ns; }
     __syncthreads();
 
     // ---- pass 1: wide lines, register accumulators ------------------------------------------------
     // A warp owns 32*K contiguous points (lane-strided), so a window that spans the warp's slice takes
     // the test-free path; only the two slices holding the window's ends pay for per-point predicates.
-    for (int l = 0; l < n_wide; ++l) {
-      const WideRec& rr = s_wide[l];
-      const int lo = rr.lo, hi = rr.hi;
-      if (hi <= own_lo || lo >= own_hi) continue;
-      const int clo = rr.clo, chi = rr.chi;
-      const double sg0 = rr.sg0, a = rr.a, ae = rr.ae, f = rr.f, g = rr.g;
-      if (lo <= own_lo && hi >= own_hi && (chi <= clo || chi <= own_lo || clo >= own_hi)) {
+    for (int q = 0; q < NT / 32; ++q) {
+      const int nq = s_cnt[0][q];
+      const WideRec* __restrict__ recs = s_wide + q * WREG;
+      for (int l = 0; l < nq; ++l) {
+        const WideRec& rr = recs[l];
+        const int lo = rr.lo, hi = rr.hi;
+        if (hi <= own_lo || lo >= own_hi) continue;
+        const int clo = rr.clo, chi = rr.chi;
+        const double sg0 = rr.sg0, a = rr.a, ae = rr.ae, f = rr.f, g = rr.g;
+        if (lo <= own_lo && hi >= own_hi && (chi <= clo || chi <= own_lo || clo >= own_hi)) {
 #pragma unroll
-        for (int j = 0; j < K; ++j) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
-      } else {
+          for (int j = 0; j < K; ++j) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-          const int i = own_lo + j * 32 + lane;
-          const bool in = (i >= lo) && (i < hi) && !((i >= clo) && (i < chi));
-          if (in) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
+          for (int j = 0; j < K; ++j) {
+            const int i = own_lo + j * 32 + lane;
+            const bool in = (i >= lo) && (i < hi) && !((i >= clo) && (i < chi));
+            if (in) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
+          }
         }
       }
     }
     // ---- pass 2: segments, lane per point, warp-owned slice of the tile -----------------------------
-    for (int l = 0; l < n_seg; ++l) {
-      const int ss = max(s_seg[l].s, own_lo), ee = min(s_seg[l].e, own_hi);
-      if (ss >= ee) continue;
-      const SegRec r = s_seg[l];
-      for (int i = ss + lane; i < ee; i += 32) {
-        const double om = s_grid[i];
-        const double x = __dmul_rn(om - r.sg0, r.cte);
-        double v;
-        if (__dadd_rn(fabs(x), r.y) < 15.0) v = r.cw * weideman_re(x, r.y);
-        else v = cheap_term<false>(om, r.sg0, r.a, r.ae, r.f, r.g, 0.0);
-        s_acc2[i] += v;
+    for (int q = 0; q < NT / 32; ++q) {
+      const int nq = s_cnt[1][q];
+      const SegRec* __restrict__ recs = s_seg + q * WREG;
+      for (int l = 0; l < nq; ++l) {
+        const int ss = max(recs[l].s, own_lo), ee = min(recs[l].e, own_hi);
+        if (ss >= ee) continue;
+        const SegRec r = recs[l];
+        for (int i = ss + lane; i < ee; i += 32) {
+          const double om = s_grid[i];
+          const double x = __dmul_rn(om - r.sg0, r.cte);
+          double v;
+          if (__dadd_rn(fabs(x), r.y) < 15.0) v = r.cw * weideman_re(x, r.y);
+          else v = cheap_term<false>(om, r.sg0, r.a, r.ae, r.f, r.g, 0.0);
+          s_acc2[i] += v;
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
     __syncthreads();
   }
