@@ -8,7 +8,7 @@ from ctypes import (POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64,
                     create_string_buffer)
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libradtxfr_b200.so")
+LIB_PATH = os.environ.get("RADTXFR_LIB", os.path.join(_PKG, "libradtxfr_b200.so"))
 
 _lib = None
 

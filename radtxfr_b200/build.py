@@ -15,6 +15,9 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libradtxfr_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+# experiment hooks: RADTXFR_NVCC_DEFS="-DRTX_ROUNDS=1 ..." adds defines, RADTXFR_LIB overrides the output/load path
+EXTRA_DEFS = os.environ.get("RADTXFR_NVCC_DEFS", "").split()
+LIB = os.environ.get("RADTXFR_LIB", LIB)
 
 
 def sources():
@@ -41,7 +44,7 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
     for src in sources():
         obj = os.path.join(PKG, "build", os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-c", src, "-o", obj]
+        cmd = [nvcc, "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", *EXTRA_DEFS, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

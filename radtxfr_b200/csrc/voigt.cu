@@ -33,7 +33,14 @@
 namespace {
 
 constexpr int NT = 256;         // threads per CTA
-constexpr int ROUNDS = 2;       // prologue rounds per chunk (one line per thread per round)
+#ifndef RTX_ROUNDS
+#define RTX_ROUNDS 2
+#endif
+#ifndef RTX_MINBLOCKS
+#define RTX_MINBLOCKS 2
+#endif
+
+constexpr int ROUNDS = RTX_ROUNDS;  // prologue rounds per chunk (one line per thread per round)
 constexpr int LCHUNK = NT * ROUNDS;  // lines per chunk
 constexpr int WREG = 32 * ROUNDS;    // list slots owned by one warp
 constexpr int NARROW_MAX = 64;  // windows of at most this many tile points go to pass 2 entirely
@@ -142,30 +149,53 @@ __device__ __forceinline__ double cheap_term(double omega, double sg0, double a,
   return fma(num, rcp_nr<FAST>(den), acc);
 }
 
-// Re w(x+iy) by Weideman's 24-term rational series, misc/hapi.py:9812-9827 (cef).
+// Re w(x+iy) by Weideman's 24-term rational series, misc/hapi.py:9812-9827 (cef):
+//   Z = (L+iz)/(L-iz),  w = 2 p(Z)/(L-iz)^2 + (1/sqrt(pi))/(L-iz),  p = polyval(a, Z).
+// p has real coefficients, so it is evaluated at the complex point Z with the real two-term recurrence
+//   u_k = a_k + s u_{k+1} - t u_{k+2},  s = 2 Re Z, t = |Z|^2,   p(Z) = Z u_1 + a_0 - t u_2
+// (2 FMAs per coefficient instead of the 4 of a complex Horner step; degree 23, so rounding-error growth is
+// bounded by a few hundred ulp -- far inside the 1e-9 parity tolerance, and tested against the oracle).
 __device__ __forceinline__ double weideman_re(double x, double y) {
   const double L = RTX_WEIDEMAN_L;
   const double dr = L + y, nr = L - y;          // L-iz = dr - i x ;  L+iz = nr + i x
-  const double m2 = dr * dr + x * x;
-  const double inv = 1.0 / m2;
-  const double Zr = (nr * dr - x * x) * inv;
+  const double m2 = fma(dr, dr, x * x);
+  const double inv = rcp_nr<false>(m2);
+  const double Zr = fma(nr, dr, -(x * x)) * inv;
   const double Zi = (2.0 * L * x) * inv;
-  double pr = c_weideman[0], pi = 0.0;
+  const double s = 2.0 * Zr, t = -fma(Zr, Zr, Zi * Zi);   // t holds -|Z|^2
+  double u2 = c_weideman[0];
+  double u1 = fma(s, u2, c_weideman[1]);
 #pragma unroll
-  for (int k = 1; k < 24; ++k) {
-    const double tr = pr * Zr - pi * Zi + c_weideman[k];
-    pi = pr * Zi + pi * Zr;
-    pr = tr;
+  for (int k = 2; k < 23; ++k) {
+    const double u0 = fma(s, u1, fma(t, u2, c_weideman[k]));
+    u2 = u1;
+    u1 = u0;
   }
+  const double pr = fma(Zr, u1, fma(t, u2, c_weideman[23]));
+  const double pi = Zi * u1;
   const double ir = dr * inv, ii = x * inv;     // 1/(L-iz)
-  const double qr = ir * ir - ii * ii, qi = 2.0 * ir * ii;
-  return 2.0 * (pr * qr - pi * qi) + RTX_INV_SQRT_PI * ir;
+  const double qr = fma(ir, ir, -(ii * ii)), qi = 2.0 * ir * ii;
+  return fma(2.0, fma(pr, qr, -(pi * qi)), RTX_INV_SQRT_PI * ir);
 }
 
 struct __align__(16) WideRec {
   double sg0, a, ae, f, g;
   short lo, hi, clo, chi;
 };
+// per wide line: bit q = the window touches warp q's slice, bit 8+q = it covers the slice with no Weideman point
+// inside (test-free path)
+__device__ __forceinline__ unsigned slice_masks(int lo, int hi, int clo, int chi, int slice) {
+  unsigned m = 0;
+#pragma unroll
+  for (int q = 0; q < NT / 32; ++q) {
+    const int a = q * slice, b = a + slice;
+    const bool touch = (hi > a) && (lo < b);
+    const bool full = (lo <= a) && (hi >= b) && ((chi <= clo) || (chi <= a) || (clo >= b));
+    m |= (touch ? 1u : 0u) << q;
+    m |= (full ? 1u : 0u) << (8 + q);
+  }
+  return m;
+}
 struct __align__(16) SegRec {
   double sg0, cte, y, cw, a, ae, f, g;
   int s, e;
@@ -257,7 +287,7 @@ __global__ void bin_kernel(int n_states, int n_tiles, int tile_pts, const double
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int K, bool FAST>
-__global__ void __launch_bounds__(NT, 2) voigt_tile_kernel(const VoigtParams P) {
+__global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const VoigtParams P) {
   constexpr int TILE = K * NT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* s_grid = reinterpret_cast<double*>(smem_raw);                 // TILE
@@ -265,6 +295,7 @@ __global__ void __launch_bounds__(NT, 2) voigt_tile_kernel(const VoigtParams P) 
   WideRec* s_wide = reinterpret_cast<WideRec*>(s_acc2 + TILE);          // LCHUNK
   SegRec* s_seg = reinterpret_cast<SegRec*>(s_wide + LCHUNK);           // LCHUNK
   __shared__ int s_cnt[2][NT / 32];
+  __shared__ unsigned short s_wflag[LCHUNK];
   __shared__ __align__(8) unsigned long long s_bar;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -304,9 +335,12 @@ __global__ void __launch_bounds__(NT, 2) voigt_tile_kernel(const VoigtParams P) 
     }
   }
 
-  double w[K], acc[K];
+  double acc[K];
+  double w[K];
 #pragma unroll
-  for (int j = 0; j < K; ++j) { w[j] = s_grid[warp * (32 * K) + j * 32 + lane]; acc[j] = 0.0; }
+  for (int j = 0; j < K; ++j) w[j] = s_grid[warp * (32 * K) + j * 32 + lane];
+#pragma unroll
+  for (int j = 0; j < K; ++j) acc[j] = 0.0;
 
   const double T = P.T[s], p = P.p[s];
   const double lnr = log(RTX_TREF / T);
@@ -378,7 +412,11 @@ __global__ void __launch_bounds__(NT, 2) voigt_tile_kernel(const VoigtParams P) 
       }
       const unsigned bw = __ballot_sync(0xffffffffu, is_wide), bs = __ballot_sync(0xffffffffu, has_seg);
       const unsigned lt = (1u << lane) - 1u;
-      if (is_wide) s_wide[warp * WREG + nw + __popc(bw & lt)] = wr;
+      if (is_wide) {
+        const int slot = warp * WREG + nw + __popc(bw & lt);
+        s_wide[slot] = wr;
+        s_wflag[slot] = (unsigned short)slice_masks(wr.lo, wr.hi, wr.clo, wr.chi, 32 * K);
+      }
       if (has_seg) s_seg[warp * WREG + ns + __popc(bs & lt)] = sr;
       nw += __popc(bw);
       ns += __popc(bs);
@@ -392,19 +430,40 @@ __global__ void __launch_bounds__(NT, 2) voigt_tile_kernel(const VoigtParams P) 
     for (int q = 0; q < NT / 32; ++q) {
       const int nq = s_cnt[0][q];
       const WideRec* __restrict__ recs = s_wide + q * WREG;
+      const unsigned short* __restrict__ flg = s_wflag + q * WREG;
       for (int l = 0; l < nq; ++l) {
+        const unsigned fl = flg[l] >> warp;
+        if (!(fl & 1u)) continue;
         const WideRec& rr = recs[l];
-        const int lo = rr.lo, hi = rr.hi;
-        if (hi <= own_lo || lo >= own_hi) continue;
-        const int clo = rr.clo, chi = rr.chi;
         const double sg0 = rr.sg0, a = rr.a, ae = rr.ae, f = rr.f, g = rr.g;
-        if (lo <= own_lo && hi >= own_hi && (chi <= clo || chi <= own_lo || clo >= own_hi)) {
+        if (fl & 0x100u) {
 #pragma unroll
           for (int j = 0; j < K; ++j) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
+          continue;
+        }
+        const int lo = rr.lo - own_lo, hi = rr.hi - own_lo;          // window in slice coordinates
+        const int clo = rr.clo - own_lo, chi = rr.chi - own_lo;
+        const bool core_here = (chi > clo) && (chi > 0) && (clo < 32 * K);
+        if (!core_here && lo > 0 && hi >= 32 * K) {
+          // the window starts inside this slice and runs past its end
+          const int j0 = lo >> 5, l0 = lo & 31;
+#pragma unroll
+          for (int j = K - 1; j >= 0; --j) {
+            if (j < j0) break;
+            if (j > j0 || lane >= l0) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
+          }
+        } else if (!core_here && lo <= 0 && hi < 32 * K) {
+          // the window ends inside this slice
+          const int j1 = (hi - 1) >> 5, l1 = hi - (j1 << 5);
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            if (j > j1) break;
+            if (j < j1 || lane < l1) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < K; ++j) {
-            const int i = own_lo + j * 32 + lane;
+            const int i = j * 32 + lane;
             const bool in = (i >= lo) && (i < hi) && !((i >= clo) && (i < chi));
             if (in) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
           }
