@@ -42,7 +42,7 @@ constexpr int NT = 256;         // threads per CTA
 
 constexpr int ROUNDS = RTX_ROUNDS;  // prologue rounds per chunk (one line per thread per round)
 constexpr int LCHUNK = NT * ROUNDS;  // lines per chunk
-constexpr int WREG = 32 * ROUNDS;    // list slots owned by one warp
+constexpr int NBLK = LCHUNK / 32;     // 32-line blocks per chunk
 constexpr int NARROW_MAX = 64;  // windows of at most this many tile points go to pass 2 entirely
 
 __constant__ double c_weideman[24] = {
@@ -294,8 +294,9 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
   double* s_acc2 = s_grid + TILE;                                       // TILE
   WideRec* s_wide = reinterpret_cast<WideRec*>(s_acc2 + TILE);          // LCHUNK
   SegRec* s_seg = reinterpret_cast<SegRec*>(s_wide + LCHUNK);           // LCHUNK
-  __shared__ int s_cnt[2][NT / 32];
-  __shared__ unsigned short s_wflag[LCHUNK];
+  // per block of 32 lines (one warp, one prologue round) and per consumer warp: which of the 32 records that warp
+  // must visit -- windows covering its whole slice, windows touching it, segments touching it
+  __shared__ unsigned s_mfull[NBLK][NT / 32], s_mtouch[NBLK][NT / 32], s_mseg[NBLK][NT / 32];
   __shared__ __align__(8) unsigned long long s_bar;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -354,7 +355,6 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
   const int nchunks = (ncand + LCHUNK - 1) / LCHUNK;
   for (int c = 0; c < nchunks; ++c) {
     // ---- prologue: one lane, one line per round; survivors compacted per warp (ballot, no atomics) -------
-    int nw = 0, ns = 0;
 #pragma unroll 1
     for (int r = 0; r < ROUNDS; ++r) {
       const int k = (r * (NT / 32) + warp) * 32 + lane;
@@ -410,37 +410,47 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
           }
         }
       }
-      const unsigned bw = __ballot_sync(0xffffffffu, is_wide), bs = __ballot_sync(0xffffffffu, has_seg);
-      const unsigned lt = (1u << lane) - 1u;
+      // records live at fixed slots; the per-consumer-warp ballots below are the (deterministic) compaction
+      const int blk = r * (NT / 32) + warp;
+      unsigned wm = 0, sm = 0;
       if (is_wide) {
-        const int slot = warp * WREG + nw + __popc(bw & lt);
-        s_wide[slot] = wr;
-        s_wflag[slot] = (unsigned short)slice_masks(wr.lo, wr.hi, wr.clo, wr.chi, 32 * K);
+        s_wide[k] = wr;
+        wm = slice_masks(wr.lo, wr.hi, wr.clo, wr.chi, 32 * K);
       }
-      if (has_seg) s_seg[warp * WREG + ns + __popc(bs & lt)] = sr;
-      nw += __popc(bw);
-      ns += __popc(bs);
+      if (has_seg) {
+        s_seg[k] = sr;
+#pragma unroll
+        for (int q = 0; q < NT / 32; ++q) sm |= ((sr.e > q * 32 * K) && (sr.s < (q + 1) * 32 * K) ? 1u : 0u) << q;
+      }
+#pragma unroll
+      for (int q = 0; q < NT / 32; ++q) {
+        const unsigned bt = __ballot_sync(0xffffffffu, (wm >> q) & 1u);
+        const unsigned bf = __ballot_sync(0xffffffffu, (wm >> (8 + q)) & 1u);
+        const unsigned bs = __ballot_sync(0xffffffffu, (sm >> q) & 1u);
+        if (lane == q) { s_mtouch[blk][q] = bt & ~bf; s_mfull[blk][q] = bf; s_mseg[blk][q] = bs; }
+      }
     }
-    if (lane == 0) { s_cnt[0][warp] = nw; s_cnt[1][warp] = ns; }
     __syncthreads();
 
     // ---- pass 1: wide lines, register accumulators ------------------------------------------------
-    // A warp owns 32*K contiguous points (lane-strided), so a window that spans the warp's slice takes
-    // the test-free path; only the two slices holding the window's ends pay for per-point predicates.
-    for (int q = 0; q < NT / 32; ++q) {
-      const int nq = s_cnt[0][q];
-      const WideRec* __restrict__ recs = s_wide + q * WREG;
-      const unsigned short* __restrict__ flg = s_wflag + q * WREG;
-      for (int l = 0; l < nq; ++l) {
-        const unsigned fl = flg[l] >> warp;
-        if (!(fl & 1u)) continue;
-        const WideRec& rr = recs[l];
+    // A warp owns 32*K contiguous points (lane-strided).  Windows that span the warp's slice take the test-free
+    // path; only the slices holding a window end (or a Weideman core) pay for per-point predicates.
+#pragma unroll 1
+    for (int blk = 0; blk < NBLK; ++blk) {
+      const WideRec* __restrict__ recs = s_wide + blk * 32;
+      unsigned m = s_mfull[blk][warp];
+      while (m) {
+        const WideRec& rr = recs[__ffs(m) - 1];
+        m &= m - 1;
         const double sg0 = rr.sg0, a = rr.a, ae = rr.ae, f = rr.f, g = rr.g;
-        if (fl & 0x100u) {
 #pragma unroll
-          for (int j = 0; j < K; ++j) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
-          continue;
-        }
+        for (int j = 0; j < K; ++j) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
+      }
+      m = s_mtouch[blk][warp];
+      while (m) {
+        const WideRec& rr = recs[__ffs(m) - 1];
+        m &= m - 1;
+        const double sg0 = rr.sg0, a = rr.a, ae = rr.ae, f = rr.f, g = rr.g;
         const int lo = rr.lo - own_lo, hi = rr.hi - own_lo;          // window in slice coordinates
         const int clo = rr.clo - own_lo, chi = rr.chi - own_lo;
         const bool core_here = (chi > clo) && (chi > 0) && (clo < 32 * K);
@@ -471,13 +481,14 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
       }
     }
     // ---- pass 2: segments, lane per point, warp-owned slice of the tile -----------------------------
-    for (int q = 0; q < NT / 32; ++q) {
-      const int nq = s_cnt[1][q];
-      const SegRec* __restrict__ recs = s_seg + q * WREG;
-      for (int l = 0; l < nq; ++l) {
-        const int ss = max(recs[l].s, own_lo), ee = min(recs[l].e, own_hi);
-        if (ss >= ee) continue;
-        const SegRec r = recs[l];
+#pragma unroll 1
+    for (int blk = 0; blk < NBLK; ++blk) {
+      const SegRec* __restrict__ recs = s_seg + blk * 32;
+      unsigned m = s_mseg[blk][warp];
+      while (m) {
+        const SegRec r = recs[__ffs(m) - 1];
+        m &= m - 1;
+        const int ss = max(r.s, own_lo), ee = min(r.e, own_hi);
         for (int i = ss + lane; i < ee; i += 32) {
           const double om = s_grid[i];
           const double x = __dmul_rn(om - r.sg0, r.cte);
