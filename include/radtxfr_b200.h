@@ -73,6 +73,24 @@ int rtx_lines_upload(rtx_handle* h, int64_t n, const double* nu, const double* s
                      const double* delta_self, const double* deltap_self, const int32_t* iso_idx);
 int rtx_lines_count(rtx_handle* h, int64_t* n);
 
+/* Line-file readers (host only, no handle, no GPU needed).  Call with capacity 0 and NULL columns to count rows,
+ * then again with arrays of that size; any column pointer may be NULL.
+ * rtx_par_read: HITRAN 160-character rows, the format hapi stores tables in (layout misc/hapi.py:468-538; parse
+ * rules misc/hapi.py:1535-1556 -- fixed-width int()/float(), unparsable rows skipped :1650-1655).
+ * rtx_tape3_read / rtx_tape3_write: LNFL TAPE3 binary line file, the format of the reference's
+ * AER-v3.6-0500-6000.tp3 (radiative_transfer.py:151,491).  The reference has no reader for it and ships the file
+ * as a Git-LFS pointer; the layout follows LNFL conventions (see csrc/ingest.cu) and is verified only by a
+ * write/read round trip.  vmin/vmax select lines by wavenumber. */
+int rtx_par_read(const char* path, int64_t capacity, int32_t* molec_id, int32_t* local_iso_id, double* nu, double* sw,
+                 double* a, double* gamma_air, double* gamma_self, double* elower, double* n_air, double* delta_air,
+                 int64_t* n_rows);
+int rtx_tape3_write(const char* path, int64_t n, const int32_t* molec_id, const int32_t* local_iso_id,
+                    const double* nu, const double* sw, const double* gamma_air, const double* gamma_self,
+                    const double* elower, const double* n_air, const double* delta_air);
+int rtx_tape3_read(const char* path, double vmin, double vmax, int64_t capacity, int32_t* molec_id,
+                   int32_t* local_iso_id, double* nu, double* sw, double* gamma_air, double* gamma_self,
+                   double* elower, double* n_air, double* delta_air, int64_t* n_rows);
+
 /* ---- subsystem 2: Voigt line sum ----------------------------------------------------------
  * Replaces the line loop of absorptionCoefficient_Voigt (misc/hapi.py:11050-11138) together with
  * PROFILE_VOIGT/pcqsdhc PART1/hum1_wei (misc/hapi.py:10131-10140, 9910-9915, 9833-9844), for
