@@ -109,6 +109,7 @@ int rtx_tape3_read(const char* path, double vmin, double vmax, int64_t capacity,
  *   flags            RTX_VOIGT_* bits */
 #define RTX_VOIGT_DEFAULT 0
 #define RTX_VOIGT_FAST_RCP 1 /* one Newton step fewer in the reciprocal (rel. err ~1e-12 per term) */
+#define RTX_VOIGT_FP32 2 /* optional FP32 evaluation of the asymptote branch (tolerance 1e-5 instead of 1e-9) */
 #define RTX_VOIGT_TILE_SHIFT 8 /* bits 8..11: force 256*K grid points per CTA, K in {1,2,4,8} (0 = automatic) */
 int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, const double* p_dev,
                   const double* weight_dev, double x_air, double x_self, double wing_abs, double wing_hw,
@@ -147,6 +148,12 @@ int rtx_tud(rtx_handle* h, int n_atm, int n_layers, const double* od_dev, const 
  * the shim). */
 int rtx_planck(rtx_handle* h, const double* X_dev, int64_t nx, const double* T_dev, int64_t nT,
                int wavelength, double* out_dev, void* stream);
+
+/* brightnessTemperature (inverse=0; radiative_transfer.py:851-933) and BT2L (inverse=1; :936-1014), element-wise:
+ * X_dev[nx], V_dev[nx][m] (radiance or temperature), out_dev[nx][m].  Non-finite or non-positive inputs give
+ * bad_value, as the reference's ixBad mask does. */
+int rtx_brightness(rtx_handle* h, const double* X_dev, int64_t nx, const double* V_dev, int64_t m, int wavelength,
+                   int inverse, double bad_value, double* out_dev, void* stream);
 
 /* ---- subsystem 3b: apparent radiance -----------------------------------------------------
  * compute_LWIR_apparent_radiance (radiative_transfer.py:1017-1069):

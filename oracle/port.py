@@ -300,6 +300,48 @@ def planckian(X_in, T_in, wavelength=False):
     return np.reshape(L, (X.size, *dimsT))
 
 
+def brightness_temperature(X_in, L_in, wavelength=False, bad_value=np.nan, spectral_dim=0):
+    """brightnessTemperature, radiative_transfer.py:851-933."""
+    X = np.asarray(np.copy(X_in), dtype=float).flatten()[:, None]
+    L = np.asarray(np.copy(L_in), dtype=float)
+    if spectral_dim != 0:
+        L = np.swapaxes(L, 0, spectral_dim)
+    dims = L.shape if L.ndim > 1 else (L.shape[0], 1)
+    L = L.reshape(dims[0], -1)
+    with np.errstate(all="ignore"):
+        if wavelength or np.mean(X) < 50:
+            X = X * 1e-6
+            L = L * 1e4
+            T = RT_C2 / (X * np.log(1 + RT_C1 / (X ** 5 * L)))
+        else:
+            X = X * 100
+            L = L * 1e-4
+            T = RT_C2 * X / np.log(RT_C1 * X ** 3 / L + 1)
+    T[~np.isfinite(L) | (L <= 0)] = bad_value
+    T = T.reshape(dims)
+    return np.swapaxes(T, 0, spectral_dim) if spectral_dim != 0 else T
+
+
+def bt2l(X_in, T_in, wavelength=False, bad_value=np.nan, spectral_dim=0):
+    """BT2L, radiative_transfer.py:936-1014."""
+    X = np.asarray(np.copy(X_in), dtype=float).flatten()[:, None]
+    T = np.asarray(np.copy(T_in), dtype=float)
+    if spectral_dim != 0:
+        T = np.swapaxes(T, 0, spectral_dim)
+    dims = T.shape if T.ndim > 1 else (T.shape[0], 1)
+    T = T.reshape(dims[0], -1)
+    with np.errstate(all="ignore"):
+        if wavelength or np.mean(X) < 50:
+            X = X * 1e-6
+            L = RT_C1 / (X ** 5 * (np.exp(RT_C2 / (X * T)) - 1)) * 1e-4
+        else:
+            X = X * 100
+            L = RT_C1 * X ** 3 / (np.exp(RT_C2 * X / T) - 1) * 1e4
+    L[~np.isfinite(L) | (T <= 0)] = bad_value
+    L = L.reshape(dims)
+    return np.swapaxes(L, 0, spectral_dim) if spectral_dim != 0 else L
+
+
 def layer_od(tables_by_mol, X, T, P_pa, PL_km, MF_VAL_ppmv, MF_ID, **voigt_kw):
     """Optical depth of one homogeneous layer: the wiring of SURVEY.md App. B.1 that stands in for the
     reference's LBLRTM call (radiative_transfer.py:395-456 contract: returns OD on the output axis)."""

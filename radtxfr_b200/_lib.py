@@ -37,6 +37,7 @@ _SIGNATURES = {
     "rtx_tud": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int,
                 c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "rtx_planck": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p],
+    "rtx_brightness": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_double, c_void_p, c_void_p],
     "rtx_apparent_radiance": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     "rtx_hsi_pixels": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,

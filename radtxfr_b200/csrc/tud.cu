@@ -94,7 +94,44 @@ __global__ void planck_kernel(const double* __restrict__ X, int64_t nx, const do
   out[i] = wavelength ? planck_um(x, t) : planck_wn(x, t);
 }
 
+// brightnessTemperature (radiative_transfer.py:851-933) and BT2L (:936-1014), element-wise over [nx][m]
+__global__ void bt_kernel(const double* __restrict__ X, int64_t nx, const double* __restrict__ V, int64_t m,
+                          int wavelength, int inverse, double bad, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nx * m) return;
+  const double x = X[i / m], v = V[i];
+  double r;
+  if (!inverse) {                                   // radiance -> brightness temperature
+    if (wavelength) {
+      const double Xm = x * 1e-6, L = v * 1e4;      // X *= 1e-6; L *= 1e4
+      const double X2 = Xm * Xm;
+      r = RTX_RT_C2 / (Xm * log(1.0 + RTX_RT_C1 / ((X2 * X2 * Xm) * L)));
+    } else {
+      const double Xm = x * 100.0, L = v * 1e-4;    // X *= 100; L *= 1e-4
+      r = RTX_RT_C2 * Xm / log(RTX_RT_C1 * (Xm * Xm * Xm) / L + 1.0);
+    }
+    if (!isfinite(v) || v <= 0.0) r = bad;          // ixBad = ~isfinite(L) | (L <= 0)
+  } else {                                          // brightness temperature -> radiance
+    r = wavelength ? planck_um(x, v) : planck_wn(x, v);
+    if (!isfinite(r) || v <= 0.0) r = bad;          // ixBad = ~isfinite(L) | (T <= 0)
+  }
+  out[i] = r;
+}
+
 }  // namespace
+
+extern "C" int rtx_brightness(rtx_handle* h, const double* X_dev, int64_t nx, const double* V_dev, int64_t m,
+                              int wavelength, int inverse, double bad_value, double* out_dev, void* stream) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  RTX_REQUIRE(nx > 0 && m > 0 && X_dev && V_dev && out_dev, "rtx_brightness: bad arguments");
+  DeviceGuard guard(h->device);
+  const int64_t total = nx * m;
+  bt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      X_dev, nx, V_dev, m, wavelength, inverse, bad_value, out_dev);
+  RTX_CUDA(cudaGetLastError());
+  h->launches++;
+  return RTX_OK;
+}
 
 extern "C" int rtx_tud(rtx_handle* h, int n_atm, int n_layers, const double* od_dev, const double* T_dev,
                        const double* grid_dev, int64_t nx, const double* Z_host, const double* alt_host, int n_alt,

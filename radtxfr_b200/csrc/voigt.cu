@@ -182,6 +182,13 @@ struct __align__(16) WideRec {
   double sg0, a, ae, f, g;
   short lo, hi, clo, chi;
 };
+// FP32 mode reuses the WideRec slots with this layout: the line centre relative to the tile's first grid point as
+// a float pair (hi + lo), so that omega - nu0' is formed in single precision without cancellation error.
+struct __align__(16) WideRec32 {
+  float chi, clo, af, ef, ff, gf, pad0, pad1;
+  short lo, hi, core_lo, core_hi;
+};
+static_assert(sizeof(WideRec32) <= sizeof(WideRec), "WideRec32 must fit a WideRec slot");
 // per wide line: bit q = the window touches warp q's slice, bit 8+q = it covers the slice with no Weideman point
 // inside (test-free path)
 __device__ __forceinline__ unsigned slice_masks(int lo, int hi, int clo, int chi, int slice) {
@@ -286,8 +293,14 @@ __global__ void bin_kernel(int n_states, int n_tiles, int tile_pts, const double
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int K, bool FAST>
+// MODE 0: FP64, full-precision reciprocal; 1: FP64, one Newton step fewer; 2: FP32 evaluation of the asymptote branch
+// (the optional 1e-5 path of the north star): per-slot origins keep omega-nu0' accurate in single precision, partial
+// sums are kept in FP32 for at most one chunk of lines and then folded into the FP64 accumulators; the Weideman
+// cores stay in FP64.
+template <int K, int MODE>
 __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const VoigtParams P) {
+  constexpr bool FAST = (MODE == 1);
+  constexpr bool F32 = (MODE == 2);
   constexpr int TILE = K * NT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* s_grid = reinterpret_cast<double*>(smem_raw);                 // TILE
@@ -338,8 +351,15 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
 
   double acc[K];
   double w[K];
+  float w32[K], w32l[K], a32[K];
 #pragma unroll
-  for (int j = 0; j < K; ++j) w[j] = s_grid[warp * (32 * K) + j * 32 + lane];
+  for (int j = 0; j < K; ++j) {
+    w[j] = s_grid[warp * (32 * K) + j * 32 + lane];
+    const double off = w[j] - s_grid[0];                          // offset from the tile's first point, as hi + lo
+    w32[j] = (float)off;
+    w32l[j] = (float)(off - (double)w32[j]);
+    a32[j] = 0.f;
+  }
 #pragma unroll
   for (int j = 0; j < K; ++j) acc[j] = 0.0;
 
@@ -362,6 +382,7 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
       bool is_wide = false, has_seg = false;
       WideRec wr;
       SegRec sr;
+      double e_keep = 0.0;
       if (li < last) {
         const LineState L = line_state(P, li, s, T, p, lnr);
         if (L.keep) {
@@ -377,6 +398,7 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
             sr.sg0 = wr.sg0 = L.sg0;
             sr.a = wr.a = a;
             sr.ae = wr.ae = a * e;
+            e_keep = e;
             sr.f = wr.f = 2.0 * g2 - h;
             sr.g = wr.g = e * e;
             sr.cte = cte;
@@ -414,7 +436,17 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
       const int blk = r * (NT / 32) + warp;
       unsigned wm = 0, sm = 0;
       if (is_wide) {
-        s_wide[k] = wr;
+        if (F32) {
+          WideRec32 w3;
+          const double c = wr.sg0 - s_grid[0];
+          w3.chi = (float)c; w3.clo = (float)(c - (double)w3.chi);
+          w3.af = (float)wr.a; w3.ef = (float)e_keep; w3.ff = (float)wr.f; w3.gf = (float)wr.g;
+          w3.pad0 = w3.pad1 = 0.f;
+          w3.lo = wr.lo; w3.hi = wr.hi; w3.core_lo = wr.clo; w3.core_hi = wr.chi;
+          *reinterpret_cast<WideRec32*>(&s_wide[k]) = w3;
+        } else {
+          s_wide[k] = wr;
+        }
         wm = slice_masks(wr.lo, wr.hi, wr.clo, wr.chi, 32 * K);
       }
       if (has_seg) {
@@ -433,6 +465,31 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
     __syncthreads();
 
     // ---- pass 1: wide lines, register accumulators ------------------------------------------------
+#define RTX_EVAL(j)                                                                                   \
+  do {                                                                                                \
+    if (F32) {                                                                                        \
+      const float d_ = (w32[j] - chf) + (w32l[j] - clf);                                              \
+      const float q_ = d_ * d_;                                                                       \
+      const float den_ = fmaf(q_ + ff, q_, gf);                                                       \
+      float r_;                                                                                       \
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r_) : "f"(den_));                                       \
+      a32[j] = fmaf(af, (q_ + ef) * r_, a32[j]);                                                      \
+    } else {                                                                                          \
+      acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);                                      \
+    }                                                                                                 \
+  } while (0)
+#define RTX_VISIT_SETUP()                                                                             \
+  const WideRec32& r3 = *reinterpret_cast<const WideRec32*>(&rr);                                     \
+  double sg0 = 0, a = 0, ae = 0, f = 0, g = 0;                                                        \
+  float chf = 0.f, clf = 0.f, af = 0.f, ef = 0.f, ff = 0.f, gf = 0.f;                                 \
+  int wlo, whi, wclo, wchi;                                                                           \
+  if (F32) {                                                                                          \
+    chf = r3.chi; clf = r3.clo; af = r3.af; ef = r3.ef; ff = r3.ff; gf = r3.gf;                       \
+    wlo = r3.lo; whi = r3.hi; wclo = r3.core_lo; wchi = r3.core_hi;                                   \
+  } else {                                                                                            \
+    sg0 = rr.sg0; a = rr.a; ae = rr.ae; f = rr.f; g = rr.g;                                     \
+    wlo = rr.lo; whi = rr.hi; wclo = rr.clo; wchi = rr.chi;                                           \
+  }
     // A warp owns 32*K contiguous points (lane-strided).  Windows that span the warp's slice take the test-free
     // path; only the slices holding a window end (or a Weideman core) pay for per-point predicates.
 #pragma unroll 1
@@ -442,17 +499,18 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
       while (m) {
         const WideRec& rr = recs[__ffs(m) - 1];
         m &= m - 1;
-        const double sg0 = rr.sg0, a = rr.a, ae = rr.ae, f = rr.f, g = rr.g;
+        RTX_VISIT_SETUP();
+        (void)wlo; (void)whi; (void)wclo; (void)wchi;
 #pragma unroll
-        for (int j = 0; j < K; ++j) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
+        for (int j = 0; j < K; ++j) RTX_EVAL(j);
       }
       m = s_mtouch[blk][warp];
       while (m) {
         const WideRec& rr = recs[__ffs(m) - 1];
         m &= m - 1;
-        const double sg0 = rr.sg0, a = rr.a, ae = rr.ae, f = rr.f, g = rr.g;
-        const int lo = rr.lo - own_lo, hi = rr.hi - own_lo;          // window in slice coordinates
-        const int clo = rr.clo - own_lo, chi = rr.chi - own_lo;
+        RTX_VISIT_SETUP();
+        const int lo = wlo - own_lo, hi = whi - own_lo;              // window in slice coordinates
+        const int clo = wclo - own_lo, chi = wchi - own_lo;
         const bool core_here = (chi > clo) && (chi > 0) && (clo < 32 * K);
         if (!core_here && lo > 0 && hi >= 32 * K) {
           // the window starts inside this slice and runs past its end
@@ -460,7 +518,7 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
 #pragma unroll
           for (int j = K - 1; j >= 0; --j) {
             if (j < j0) break;
-            if (j > j0 || lane >= l0) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
+            if (j > j0 || lane >= l0) RTX_EVAL(j);
           }
         } else if (!core_here && lo <= 0 && hi < 32 * K) {
           // the window ends inside this slice
@@ -468,17 +526,21 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
 #pragma unroll
           for (int j = 0; j < K; ++j) {
             if (j > j1) break;
-            if (j < j1 || lane < l1) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
+            if (j < j1 || lane < l1) RTX_EVAL(j);
           }
         } else {
 #pragma unroll
           for (int j = 0; j < K; ++j) {
             const int i = j * 32 + lane;
             const bool in = (i >= lo) && (i < hi) && !((i >= clo) && (i < chi));
-            if (in) acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);
+            if (in) RTX_EVAL(j);
           }
         }
       }
+    }
+    if (F32) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) { acc[j] += (double)a32[j]; a32[j] = 0.f; }
     }
     // ---- pass 2: segments, lane per point, warp-owned slice of the tile -----------------------------
 #pragma unroll 1
@@ -562,13 +624,13 @@ size_t tile_smem_bytes() {
   return (size_t)K * NT * 8 * 2 + (size_t)LCHUNK * (sizeof(WideRec) + sizeof(SegRec));
 }
 
-template <int K, bool FAST>
+template <int K, int MODE>
 int launch_tile(const VoigtParams& P, cudaStream_t st) {
   const size_t smem = tile_smem_bytes<K>();
-  RTX_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<K, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RTX_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t blocks = (int64_t)P.n_tiles * P.n_states;
   if (blocks > 2147483647LL) { rtx_set_error("rtx_voigt_sum: too many (tile, state) pairs for one launch"); return RTX_E_INVALID; }
-  voigt_tile_kernel<K, FAST><<<(unsigned)blocks, NT, smem, st>>>(P);
+  voigt_tile_kernel<K, MODE><<<(unsigned)blocks, NT, smem, st>>>(P);
   RTX_CUDA(cudaGetLastError());
   return RTX_OK;
 }
@@ -673,13 +735,15 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
                                                           st_wb, h->d_bins);
   RTX_CUDA(cudaGetLastError());
   h->launches++;
-  const bool fast = (flags & RTX_VOIGT_FAST_RCP) != 0;
+  const int mode = (flags & RTX_VOIGT_FP32) ? 2 : ((flags & RTX_VOIGT_FAST_RCP) ? 1 : 0);
+#define RTX_LAUNCH(KK) (mode == 2 ? launch_tile<KK, 2>(P, st) : mode == 1 ? launch_tile<KK, 1>(P, st) : launch_tile<KK, 0>(P, st))
   switch (K) {
-    case 8: rc = fast ? launch_tile<8, true>(P, st) : launch_tile<8, false>(P, st); break;
-    case 4: rc = fast ? launch_tile<4, true>(P, st) : launch_tile<4, false>(P, st); break;
-    case 2: rc = fast ? launch_tile<2, true>(P, st) : launch_tile<2, false>(P, st); break;
-    default: rc = fast ? launch_tile<1, true>(P, st) : launch_tile<1, false>(P, st); break;
+    case 8: rc = RTX_LAUNCH(8); break;
+    case 4: rc = RTX_LAUNCH(4); break;
+    case 2: rc = RTX_LAUNCH(2); break;
+    default: rc = RTX_LAUNCH(1); break;
   }
+#undef RTX_LAUNCH
   if (rc) return rc;
   h->launches++;
   return RTX_OK;

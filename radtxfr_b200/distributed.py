@@ -113,7 +113,9 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, **kwargs):
     nf = 2 * Z_s.size * mu_s.size + 1
     if i1 > i0:
         grid = engine.to_device(X_[i0:i1], db.device)
-        od = db.voigt_sum(T, p, w, grid, flags=FORCE_K8, **rt._voigt_settings(opts))
+        vs = rt._voigt_settings(opts)
+        vs["flags"] |= FORCE_K8
+        od = db.voigt_sum(T, p, w, grid, **vs)
         tau, lu, ld = engine.tud(od, T[None, :], grid, Z, Z_s, mu_s, opts["N_angle"], opts["returnOD"])
         n = i1 - i0
         local = torch.cat([tau[0].reshape(n, -1).T, lu[0].reshape(n, -1).T, ld[0].reshape(1, n)], dim=0).contiguous()

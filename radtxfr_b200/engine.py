@@ -336,6 +336,20 @@ def planck(X, T, wavelength=False, device=None):
     return out
 
 
+def brightness(X, V, wavelength=False, inverse=False, bad_value=float("nan"), device=None):
+    """rtx_brightness: V [nx, m] radiance -> brightness temperature (inverse=False) or back (inverse=True)."""
+    torch = _torch()
+    dev = resolve_device(device if not (isinstance(V, torch.Tensor) and V.is_cuda) else V.device)
+    h = default_handle(dev)
+    X = to_device(X, dev).reshape(-1)
+    V = to_device(V, dev).reshape(X.numel(), -1)
+    out = torch.empty_like(V)
+    if out.numel():
+        _lib.call("rtx_brightness", h.h, _ptr(X), X.numel(), _ptr(V), V.shape[1], int(bool(wavelength)),
+                  int(bool(inverse)), float(bad_value), _ptr(out), _stream(dev))
+    return out
+
+
 def ils_apply(mode, X, Y, centres, widths, device=None):
     """rtx_ils_apply: Y [nx, ns] -> [n_bands, ns]."""
     torch = _torch()

@@ -44,7 +44,8 @@ options = {
     "returnOD": False,
     # --- additions of this implementation -----------------------------------------------------
     "LINE_DB": None,        # engine.LineDB, set through set_line_database()
-    "voigt": {},            # extra Voigt settings: OmegaWing, OmegaWingHW, IntensityThreshold, Diluent
+    "voigt": {},            # extra Voigt settings: OmegaWing, OmegaWingHW, IntensityThreshold, Diluent, and
+                            # precision: "fp64" (default, 1e-9), "fp64_fast" (one Newton step fewer), "fp32" (1e-5)
 }
 
 
@@ -71,8 +72,10 @@ def _voigt_settings(opts):
     dil = v.get("Diluent") or {"air": 1.0}
     x_air = float(sum(val for k, val in dil.items() if k.lower() == "air"))
     x_self = float(sum(val for k, val in dil.items() if k.lower() == "self"))
+    flags = {"fp64": 0, "fp64_fast": 1, "fp32": 2}[v.get("precision", "fp64")]
     return dict(x_air=x_air, x_self=x_self, wing_abs=float(v.get("OmegaWing", 0.0)),
-                wing_hw=float(v.get("OmegaWingHW", 50.0)), s_threshold=float(v.get("IntensityThreshold", 0.0)))
+                wing_hw=float(v.get("OmegaWingHW", 50.0)), s_threshold=float(v.get("IntensityThreshold", 0.0)),
+                flags=flags)
 
 
 def layer_weights(db, T, P_pa, PL_km, MF_VAL, MF_ID):
@@ -234,6 +237,48 @@ def planckian(X_in, T_in, wavelength=False):
     if as_tensor:
         return L.reshape((n,) + dimsT)
     return np.reshape(L.cpu().numpy(), (n, *dimsT))
+
+
+def _bt(X_in, V_in, wavelength, bad_value, spectral_dim, inverse):
+    torch = engine._torch()
+    as_tensor = isinstance(V_in, torch.Tensor)
+    if as_tensor:
+        V = V_in.double()
+        X = (X_in if isinstance(X_in, torch.Tensor) else torch.as_tensor(np.asarray(X_in, dtype=float))).reshape(-1).double()
+        if spectral_dim != 0:
+            V = V.swapaxes(0, spectral_dim)
+        mean_small = bool(X.mean().item() < 50)
+    else:
+        X = np.asarray(np.copy(X_in), dtype=float).flatten()
+        V = np.asarray(np.copy(V_in), dtype=float)
+        if spectral_dim != 0:
+            V = np.swapaxes(V, 0, spectral_dim)
+        mean_small = bool(np.mean(X) < 50)
+    dims = tuple(V.shape)
+    use_wl = bool(wavelength or mean_small)
+    if use_wl and not wavelength:
+        print("Assumes X given in µm and L given in µF")
+    V2 = V.reshape(dims[0], -1) if as_tensor else np.ascontiguousarray(V.reshape(dims[0], -1))
+    out = engine.brightness(X, V2.contiguous() if as_tensor else V2, use_wl, inverse, bad_value)
+    out = out if as_tensor else out.cpu().numpy()
+    if V.ndim == 1:                       # the reference returns (nX, 1) for vector input (both functions)
+        out = out.reshape(dims[0], 1)
+    else:
+        out = out.reshape(dims)
+    if spectral_dim != 0:
+        out = out.swapaxes(0, spectral_dim) if as_tensor else np.swapaxes(out, 0, spectral_dim)
+    return out
+
+
+def brightnessTemperature(X_in, L_in, wavelength=False, bad_value=np.nan, spectral_dim=0):
+    """Brightness temperature of a spectral radiance, radiative_transfer.py:851-933 (spectral axis first, or at
+    `spectral_dim`; unphysical inputs give `bad_value`)."""
+    return _bt(X_in, L_in, wavelength, bad_value, spectral_dim, False)
+
+
+def BT2L(X_in, T_in, wavelength=False, bad_value=np.nan, spectral_dim=0):
+    """Spectral radiance of a brightness temperature, radiative_transfer.py:936-1014."""
+    return _bt(X_in, T_in, wavelength, bad_value, spectral_dim, True)
 
 
 def compute_LWIR_apparent_radiance(X, emis, Ts, tau, La, Ld, dT=None, return_Ls=False):

@@ -83,6 +83,22 @@ def test_voigt_all_tile_sizes(mods, K, fast):
         assert_parity(out[k], ref, RTOL, FLOOR, "K=%d fast=%d state %d" % (K, fast, k))
 
 
+def test_voigt_fp32_option(mods):
+    """Optional FP32 evaluation of the asymptote branch (north star: 1e-5 relative, floor 1e-8)."""
+    port, syn, engine = mods["port"], mods["syn"], mods["engine"]
+    cols = syn.synthetic_lines(55, 600, 940.0, 1060.0, 1)
+    db = engine.LineDB(cols)
+    states = [(296.0, 1.0), (250.0, 0.2), (225.53, 7.3 / 101325.0), (216.7, 0.02)]
+    T = np.array([s[0] for s in states]); p = np.array([s[1] for s in states])
+    w = np.tile(db.iso_factors(None, 1.0), (len(states), 1))
+    for grid in (np.linspace(950.0, 1050.0, 100001), np.linspace(950.0, 1050.0, 10001)):
+        for K in (8, 1):
+            out = db.voigt_sum(T, p, w, grid, flags=2 | (K << 8)).cpu().numpy()
+            for k, (Tk, pk) in enumerate(states):
+                _, ref = port.absorption_coefficient_voigt(cols, T=Tk, p=pk, OmegaGrid=grid)
+                assert_parity(out[k], ref, 1e-5, 1e-8, "fp32 K=%d n=%d state %d" % (K, grid.size, k))
+
+
 def test_voigt_eval_counter(mods):
     port, syn, engine = mods["port"], mods["syn"], mods["engine"]
     cols = syn.synthetic_lines(51, 300, 985.0, 1015.0, 1)
@@ -254,6 +270,31 @@ def test_sensor_golden(mods):
     Pw = rt.planckian(np.linspace(7.5, 13.5, 61), np.array([[280.0, 300.0], [310., 250.]]), wavelength=True)
     assert Pw.shape == (61, 2, 2)
     assert_parity(Pw, g["planck_um"], RTOL, FLOOR, "planck um")
+
+
+def test_brightness_temperature_golden(mods):
+    rt = mods["rt"]
+    g = golden("bt.npz")
+    X, T, L = g["X"], g["T"], g["L"]
+    got = rt.BT2L(X, T)
+    assert got.shape == L.shape
+    assert_parity(got, L, RTOL, FLOOR, "BT2L")
+    bt = rt.brightnessTemperature(X, g["Lb"], bad_value=-5.0)
+    assert_parity(bt, g["bt"], RTOL, FLOOR, "brightnessTemperature")
+    assert bt[3, 0, 0] == -5.0 and bt[4, 1, 1] == -5.0 and bt[5, 2, 0] == -5.0
+    v = rt.brightnessTemperature(X, L[:, 0, 0])
+    assert v.shape == g["bt_vec"].shape == (X.size, 1)
+    assert_parity(v, g["bt_vec"], RTOL, FLOOR, "bt vector")
+    Lbad = rt.BT2L(X, g["Tb"])
+    assert np.isnan(Lbad[7, 0, 1]) and np.isnan(g["L_bad"][7, 0, 1])
+    m = np.isfinite(g["L_bad"])
+    assert_parity(Lbad[m], g["L_bad"][m], RTOL, FLOOR, "BT2L bad")
+    assert_parity(rt.brightnessTemperature(g["Xu"], g["Lu"], wavelength=True), g["bt_um"], RTOL, FLOOR, "bt um")
+    sd = rt.brightnessTemperature(X, np.swapaxes(L[:, :, 0], 0, 1), spectral_dim=1)
+    assert sd.shape == g["bt_sd"].shape
+    assert_parity(sd, g["bt_sd"], RTOL, FLOOR, "bt spectral_dim")
+    # round trip
+    assert_parity(rt.brightnessTemperature(X, rt.BT2L(X, T)), T, 1e-9, 1e-12, "BT round trip")
 
 
 def test_hsi_pixels(mods):

@@ -112,3 +112,16 @@ def test_sensor_model():
     assert np.array_equal(port.planckian(np.linspace(700, 1500, 8001), np.array([280.0, 300.0])), g["planck_grid"])
     assert np.array_equal(port.planckian(np.linspace(7.5, 13.5, 61), np.array([[280.0, 300.0], [310., 250.]]),
                                          wavelength=True), g["planck_um"])
+
+
+def test_brightness_temperature():
+    g = golden("bt.npz")
+    X, T, L = g["X"], g["T"], g["L"]
+    assert np.array_equal(port.bt2l(X, T), L)
+    bt = port.brightness_temperature(X, g["Lb"], bad_value=-5.0)
+    assert_parity(bt, g["bt"], what="bt", **TIGHT)
+    assert np.array_equal(port.brightness_temperature(X, L[:, 0, 0]), g["bt_vec"])
+    lb = port.bt2l(X, g["Tb"])
+    assert np.array_equal(np.isnan(lb), np.isnan(g["L_bad"]))
+    assert np.array_equal(port.brightness_temperature(g["Xu"], g["Lu"], wavelength=True), g["bt_um"])
+    assert np.array_equal(port.brightness_temperature(X, np.swapaxes(L[:, :, 0], 0, 1), spectral_dim=1), g["bt_sd"])

@@ -144,8 +144,30 @@ def g_sensor():
          planck_kat=r.planckian(500., 296.), planck_grid=Pl, planck_um=Pw)
 
 
+def g_bt():
+    r = R.rt()
+    rng = np.random.default_rng(60)
+    X = np.linspace(700.0, 1400.0, 141)
+    T = rng.uniform(220, 330, (141, 3, 2))
+    L = r.BT2L(X, T)
+    Lb = L.copy(); Lb[3, 0, 0] = -1.0; Lb[4, 1, 1] = np.nan; Lb[5, 2, 0] = 0.0
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bt = r.brightnessTemperature(X, Lb, bad_value=-5.0)
+        bt_vec = r.brightnessTemperature(X, L[:, 0, 0])
+        Tb = T.copy(); Tb[7, 0, 1] = -3.0
+        L_bad = r.BT2L(X, Tb)
+        Xu = np.linspace(7.5, 13.5, 61)
+        Lu = r.planckian(Xu, np.array([280.0, 310.0]), wavelength=True)
+        bt_um = r.brightnessTemperature(Xu, Lu, wavelength=True)
+        bt_sd = r.brightnessTemperature(X, np.swapaxes(L[:, :, 0], 0, 1), spectral_dim=1)
+    save("bt.npz", source="radiative_transfer.py:851-1014 brightnessTemperature, BT2L", X=X, T=T, L=L, Lb=Lb, bt=bt,
+         bt_vec=bt_vec, Tb=Tb, L_bad=L_bad, Xu=Xu, Lu=Lu, bt_um=bt_um, bt_sd=bt_sd)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor"]
+    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt"]
     for w in which:
         globals()["g_" + w]()

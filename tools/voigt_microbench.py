@@ -42,11 +42,12 @@ def main():
         del a0, a1
     cases = []
     for K in (8,):
-        for fast in (0, 1):
+        for fast in (0, 1, 2):
             cases.append(("cfg2 K=%d fast=%d" % (K, fast), dict(flags=fast | (K << 8)), T, pd, wd))
     # all-wide: every line +-25 cm^-1 -> almost every visit takes the test-free path
     cases.append(("wide25 K=8 fast=0", dict(flags=8 << 8, wing_abs=25.0), T[:8], pd[:8], wd[:8]))
     cases.append(("wide25 K=8 fast=1", dict(flags=1 | (8 << 8), wing_abs=25.0), T[:8], pd[:8], wd[:8]))
+    cases.append(("wide25 K=8 fp32", dict(flags=2 | (8 << 8), wing_abs=25.0), T[:8], pd[:8], wd[:8]))
     cases.append(("wide25 K=4 fast=0", dict(flags=4 << 8, wing_abs=25.0), T[:8], pd[:8], wd[:8]))
     # per-layer groups of config 2
     for name, sl in (("layers 0-9", slice(0, 10)), ("layers 10-29", slice(10, 30)), ("layers 30-49", slice(30, 50)),
