@@ -16,9 +16,9 @@
 //   * pass 1 ("wide" lines): each warp owns 32*K contiguous grid points (K per lane, lane-strided),
 //     accumulators in registers.
 //     Outside the Weideman core the reference's w(z) is the one-term Humlicek asymptote, for which
-//       S*V = a*(q+e)/((q+f)*q+e^2),  q=(omega-nu0')^2, a=amp*Gamma0/pi, e=GammaD^2/(2 ln2)+Gamma0^2,
-//       f=2*Gamma0^2-GammaD^2/ln2                                   (closed form)
-//     = 9 FP64 pipe operations per (line, grid point) incl. a Newton-refined MUFU.RCP64H reciprocal.
+//       S*V = a*(u+h)/(u^2+c),  u=(omega-nu0')^2+Gamma0^2-h/2, h=GammaD^2/ln2, c=2*h*Gamma0^2, a=amp*Gamma0/pi
+//     (closed form of SURVEY.md App. A.3 with the square completed)
+//     = 8 FP64 pipe operations per (line, grid point) incl. a Newton-refined MUFU.RCP64H reciprocal.
 //   * pass 2 ("segments"): the Weideman cores of wide lines and the whole window of narrow lines are
 //     evaluated lane-per-point by the warp that owns that part of the tile (shared-memory accumulator, no
 //     atomics), so the 24-term rational series never diverges against the cheap branch inside a warp.
@@ -138,14 +138,18 @@ __device__ __forceinline__ double rcp_nr(double x) {
   return fma(r0, t, r0);                                   // r0*(1+e+e^2): cubic convergence
 }
 
-// Humlicek one-term branch of hum1_wei folded with the Voigt prefactor (closed form, App. A.3).
+// Humlicek one-term branch of hum1_wei folded with the Voigt prefactor (closed form):
+//   S*V = a*(q+e)/(q^2+f*q+e^2),  q=(omega-nu0')^2, e=h/2+G0^2, f=2*G0^2-h, h=GD^2/ln2, a=amp*G0/pi.
+// Completing the square, with u = q + f/2 = d^2 + (G0^2 - h/2):  S*V = a*(u+h)/(u^2+c),  c = e^2-f^2/4 = 2*h*G0^2
+// -> 8 FP64-pipe operations: DADD, 3 DFMA, MUFU.RCP64H + 3 DFMA (cubic Newton), DFMA.  In the branch's domain
+// (|x|+y >= 15) u is positive and free of cancellation; c is formed from its closed form, not by subtraction.
 template <bool FAST>
-__device__ __forceinline__ double cheap_term(double omega, double sg0, double a, double ae, double f,
-                                             double g, double acc) {
+__device__ __forceinline__ double cheap_term(double omega, double sg0, double a, double ah, double m, double c,
+                                             double acc) {
   const double d = omega - sg0;
-  const double q = d * d;
-  const double num = fma(a, q, ae);
-  const double den = fma(q + f, q, g);
+  const double u = fma(d, d, m);
+  const double den = fma(u, u, c);
+  const double num = fma(a, u, ah);
   return fma(num, rcp_nr<FAST>(den), acc);
 }
 
@@ -179,13 +183,13 @@ __device__ __forceinline__ double weideman_re(double x, double y) {
 }
 
 struct __align__(16) WideRec {
-  double sg0, a, ae, f, g;
+  double sg0, a, ah, m, c;
   short lo, hi, clo, chi;
 };
 // FP32 mode reuses the WideRec slots with this layout: the line centre relative to the tile's first grid point as
 // a float pair (hi + lo), so that omega - nu0' is formed in single precision without cancellation error.
 struct __align__(16) WideRec32 {
-  float chi, clo, af, ef, ff, gf, pad0, pad1;
+  float chi, clo, af, hf, mf, cf, pad0, pad1;
   short lo, hi, core_lo, core_hi;
 };
 static_assert(sizeof(WideRec32) <= sizeof(WideRec), "WideRec32 must fit a WideRec slot");
@@ -204,7 +208,7 @@ __device__ __forceinline__ unsigned slice_masks(int lo, int hi, int clo, int chi
   return m;
 }
 struct __align__(16) SegRec {
-  double sg0, cte, y, cw, a, ae, f, g;
+  double sg0, cte, y, cw, a, ah, m, c;
   int s, e;
 };
 
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
       bool is_wide = false, has_seg = false;
       WideRec wr;
       SegRec sr;
-      double e_keep = 0.0;
+      double h_keep = 0.0;
       if (li < last) {
         const LineState L = line_state(P, li, s, T, p, lnr);
         if (L.keep) {
@@ -393,14 +397,13 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
             const double y = L.gam0 * cte;                                 // misc/hapi.py:9913
             const double h = L.gamD * L.gamD / RTX_LN2;                    // 1/cte^2
             const double g2 = L.gam0 * L.gam0;
-            const double e = 0.5 * h + g2;
             const double a = L.amp * L.gam0 / RTX_PI;
             sr.sg0 = wr.sg0 = L.sg0;
             sr.a = wr.a = a;
-            sr.ae = wr.ae = a * e;
-            e_keep = e;
-            sr.f = wr.f = 2.0 * g2 - h;
-            sr.g = wr.g = e * e;
+            sr.ah = wr.ah = a * h;
+            sr.m = wr.m = g2 - 0.5 * h;
+            sr.c = wr.c = 2.0 * h * g2;
+            h_keep = h;
             sr.cte = cte;
             sr.y = y;
             sr.cw = L.amp * (cte / RTX_SQRT_PI);
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
           WideRec32 w3;
           const double c = wr.sg0 - s_grid[0];
           w3.chi = (float)c; w3.clo = (float)(c - (double)w3.chi);
-          w3.af = (float)wr.a; w3.ef = (float)e_keep; w3.ff = (float)wr.f; w3.gf = (float)wr.g;
+          w3.af = (float)wr.a; w3.hf = (float)h_keep; w3.mf = (float)wr.m; w3.cf = (float)wr.c;
           w3.pad0 = w3.pad1 = 0.f;
           w3.lo = wr.lo; w3.hi = wr.hi; w3.core_lo = wr.clo; w3.core_hi = wr.chi;
           *reinterpret_cast<WideRec32*>(&s_wide[k]) = w3;
@@ -469,25 +472,25 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
   do {                                                                                                \
     if (F32) {                                                                                        \
       const float d_ = (w32[j] - chf) + (w32l[j] - clf);                                              \
-      const float q_ = d_ * d_;                                                                       \
-      const float den_ = fmaf(q_ + ff, q_, gf);                                                       \
+      const float u_ = fmaf(d_, d_, mf);                                                              \
+      const float den_ = fmaf(u_, u_, cf);                                                            \
       float r_;                                                                                       \
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r_) : "f"(den_));                                       \
-      a32[j] = fmaf(af, (q_ + ef) * r_, a32[j]);                                                      \
+      a32[j] = fmaf(af, (u_ + hf) * r_, a32[j]);                                                      \
     } else {                                                                                          \
-      acc[j] = cheap_term<FAST>(w[j], sg0, a, ae, f, g, acc[j]);                                      \
+      acc[j] = cheap_term<FAST>(w[j], sg0, a, ah, m, c, acc[j]);                                      \
     }                                                                                                 \
   } while (0)
 #define RTX_VISIT_SETUP()                                                                             \
   const WideRec32& r3 = *reinterpret_cast<const WideRec32*>(&rr);                                     \
-  double sg0 = 0, a = 0, ae = 0, f = 0, g = 0;                                                        \
-  float chf = 0.f, clf = 0.f, af = 0.f, ef = 0.f, ff = 0.f, gf = 0.f;                                 \
+  double sg0 = 0, a = 0, ah = 0, m = 0, c = 0;                                                        \
+  float chf = 0.f, clf = 0.f, af = 0.f, hf = 0.f, mf = 0.f, cf = 0.f;                                 \
   int wlo, whi, wclo, wchi;                                                                           \
   if (F32) {                                                                                          \
-    chf = r3.chi; clf = r3.clo; af = r3.af; ef = r3.ef; ff = r3.ff; gf = r3.gf;                       \
+    chf = r3.chi; clf = r3.clo; af = r3.af; hf = r3.hf; mf = r3.mf; cf = r3.cf;                       \
     wlo = r3.lo; whi = r3.hi; wclo = r3.core_lo; wchi = r3.core_hi;                                   \
   } else {                                                                                            \
-    sg0 = rr.sg0; a = rr.a; ae = rr.ae; f = rr.f; g = rr.g;                                     \
+    sg0 = rr.sg0; a = rr.a; ah = rr.ah; m = rr.m; c = rr.c;                                     \
     wlo = rr.lo; whi = rr.hi; wclo = rr.clo; wchi = rr.chi;                                           \
   }
     // A warp owns 32*K contiguous points (lane-strided).  Windows that span the warp's slice take the test-free
@@ -556,7 +559,7 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
           const double x = __dmul_rn(om - r.sg0, r.cte);
           double v;
           if (__dadd_rn(fabs(x), r.y) < 15.0) v = r.cw * weideman_re(x, r.y);
-          else v = cheap_term<false>(om, r.sg0, r.a, r.ae, r.f, r.g, 0.0);
+          else v = cheap_term<false>(om, r.sg0, r.a, r.ah, r.m, r.c, 0.0);
           s_acc2[i] += v;
         }
         __syncwarp();
