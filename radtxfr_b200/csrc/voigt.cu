@@ -43,7 +43,10 @@ constexpr int NT = 256;         // threads per CTA
 constexpr int ROUNDS = RTX_ROUNDS;  // prologue rounds per chunk (one line per thread per round)
 constexpr int LCHUNK = NT * ROUNDS;  // lines per chunk
 constexpr int NBLK = LCHUNK / 32;     // 32-line blocks per chunk
-constexpr int NARROW_MAX = 64;  // windows of at most this many tile points go to pass 2 entirely
+#ifndef RTX_NARROW_MAX
+#define RTX_NARROW_MAX 64
+#endif
+constexpr int NARROW_MAX = RTX_NARROW_MAX;  // windows of at most this many tile points go to pass 2 entirely
 
 __constant__ double c_weideman[24] = {
     // Weideman N=24 coefficients, highest power first.  tests/test_host_logic.py regenerates them from the

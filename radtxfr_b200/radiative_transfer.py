@@ -61,6 +61,53 @@ def set_line_database(tables_by_mol, device=None, opts=options):
     return db
 
 
+_axis_cache = {}
+_workspace = {}
+
+
+def _device_axis(Xmin, Xmax, DVOUT, device):
+    """(host axis, device copy): the device copy of a spectral axis is kept across calls (LRU of 4)."""
+    X_ = make_spectral_axis(Xmin, Xmax, DVOUT)
+    key = (float(Xmin), float(Xmax), int(X_.size), str(device))
+    hit = _axis_cache.get(key)
+    if hit is None:
+        if len(_axis_cache) >= 4:
+            _axis_cache.pop(next(iter(_axis_cache)))
+        hit = _axis_cache[key] = engine.to_device(X_, device)
+    return X_, hit
+
+
+def _od_workspace(device, n_states, nx):
+    """Grow-only optical-depth buffer per device: avoids a 0.4 GB allocation per compute_TUD call."""
+    torch = engine._torch()
+    need = n_states * nx
+    buf = _workspace.get(str(device))
+    if buf is None or buf.numel() < need:
+        buf = None
+        _workspace.pop(str(device), None)
+        buf = _workspace[str(device)] = torch.empty(need, dtype=torch.float64, device=device)
+    return buf[:need].view(n_states, nx)
+
+
+def _to_host(*tensors):
+    """Device tensors -> fresh numpy arrays through one persistent pinned staging buffer (one sync)."""
+    torch = engine._torch()
+    total = sum(t.numel() for t in tensors)
+    key = "pinned"
+    stage = _workspace.get(key)
+    if stage is None or stage.numel() < total:
+        stage = _workspace[key] = torch.empty(max(total, 1), dtype=torch.float64, pin_memory=True)
+    off = 0
+    views = []
+    for t in tensors:
+        v = stage[off:off + t.numel()]
+        v.copy_(t.reshape(-1), non_blocking=True)
+        views.append((v, tuple(t.shape)))
+        off += t.numel()
+    torch.cuda.current_stream(tensors[0].device).synchronize()
+    return [v.numpy().reshape(shape).copy() for v, shape in views]
+
+
 def make_spectral_axis(Xmin, Xmax, DVOUT):
     """radiative_transfer.py:251-271 (with the int() the reference needs on numpy >= 1.18)."""
     nX = int(np.ceil((Xmax - Xmin) / DVOUT))
@@ -136,19 +183,17 @@ def compute_TUD(Xmin, Xmax, opts=options, **kwargs):
     mu_s = np.array([1.0 / np.cos(opts["theta_r"])]).ravel()
     returnOD = opts["returnOD"]
 
-    X_ = make_spectral_axis(Xmin, Xmax, opts["DVOUT"])
+    X_, grid = _device_axis(Xmin, Xmax, opts["DVOUT"], db.device)
     db.check_temperatures(T)
     p, w = layer_weights(db, T, P, PL, MF, ID)
-    grid = engine.to_device(X_, db.device)
-    od = db.voigt_sum(T, p, w, grid, **_voigt_settings(opts))                  # [nL, nX], layer-major
+    od = db.voigt_sum(T, p, w, grid, out=_od_workspace(db.device, T.size, X_.size),
+                      **_voigt_settings(opts))                                  # [nL, nX], layer-major
     tau, lu, ld = engine.tud(od, T[None, :], grid, Z, Z_s, mu_s, nA, returnOD)
     if opts["save"]:
         B = engine.planck(grid, T).cpu().numpy()
         np.savez("ComputeTUD.npz", OD=od.cpu().numpy().T, B=B, tau=tau[0].cpu().numpy(), Lu=lu[0].cpu().numpy(),
                  X=X_, angles=np.linspace(0, np.pi / 2.0, nA, endpoint=False), Z_s=Z_s, mu_s=mu_s)
-    tau_ = tau[0].cpu().numpy()
-    Lu_ = lu[0].cpu().numpy()
-    Ld_ = ld[0].cpu().numpy()
+    tau_, Lu_, Ld_ = _to_host(tau[0], lu[0], ld[0])
     if (len(Z_s) == 1) and (len(mu_s) == 1):
         tau_, Lu_ = tau_[:, 0, 0], Lu_[:, 0, 0]
     if (len(Z_s) == 1) and not (len(mu_s) == 1):

@@ -55,7 +55,7 @@ def main():
         for K in (8,):
             cases.append((name + " K=%d" % K, dict(flags=K << 8), T[sl], pd[sl], wd[sl].contiguous()))
     for name, kw, Tt, pp, ww in cases:
-        if only is not None and only not in name:
+        if only is not None and only not in name.replace(" ", "_"):
             continue
         n = Tt.numel()
         ev, evw = db.count_evals(Tt, pp, ww, grid, **{k: v for k, v in kw.items() if k != "flags"})
