@@ -31,6 +31,7 @@ struct TudParams {
 __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) {
   const int64_t x = (int64_t)blockIdx.x * TUD_THREADS + threadIdx.x;
   if (x >= P.nx) return;
+  const unsigned lanes = __activemask();   // the last block of the grid may be partial
   const int atm = blockIdx.y;
   const double nu = P.grid[x];
   const double* __restrict__ od = P.od + ((int64_t)atm * P.n_layers) * P.nx + x;
@@ -69,14 +70,31 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
   double ldsum = 0.0;
   for (int a0 = 0; a0 < P.n_angle; a0 += ANGLE_BLOCK) {
     double acc[ANGLE_BLOCK], sec[ANGLE_BLOCK];
+    double secmax = 1.0;
 #pragma unroll
     for (int a = 0; a < ANGLE_BLOCK; ++a) {
       acc[a] = 0.0;
       sec[a] = (a0 + a < P.n_angle) ? P.inv_cos[a0 + a] : 1.0;   // padding angles get weight 0 below
+      secmax = fmax(secmax, sec[a]);
     }
     for (int j = P.n_down - 1; j >= 0; --j) {
       const double ao = -fabs(od[(int64_t)j * P.nx]);     // optical depths are non-negative
       const double B = planck_wn(nu, T[j]);
+      // optically thin layer for every lane of the warp and every angle of the block (|x| <= 2^-9): the degree-5
+      // Taylor polynomial is exact to < 1e-19 and needs no range reduction
+      if (__all_sync(lanes, ao * secmax >= -1.953125e-3)) {
+#pragma unroll
+        for (int a = 0; a < ANGLE_BLOCK; ++a) {
+          const double x = ao * sec[a];
+          double t = fma(x, 8.333333333333333e-03, 4.1666666666666664e-02);
+          t = fma(t, x, 1.6666666666666666e-01);
+          t = fma(t, x, 0.5);
+          t = fma(t, x, 1.0);
+          t = fma(t, x, 1.0);
+          acc[a] = t * acc[a] + (1.0 - t) * B;
+        }
+        continue;
+      }
       double xa[ANGLE_BLOCK], tt[ANGLE_BLOCK], r[ANGLE_BLOCK], pz[ANGLE_BLOCK];
 #pragma unroll
       for (int a = 0; a < ANGLE_BLOCK; ++a) {
