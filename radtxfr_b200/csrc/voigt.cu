@@ -33,11 +33,13 @@
 namespace {
 
 constexpr int NT = 256;         // threads per CTA
+// 3 CTAs (24 warps) per SM: 80 registers per thread and 64 KB of shared memory per CTA; measured 7 % faster on
+// config 2 than 2 CTAs with 126 registers and 512-line chunks.
 #ifndef RTX_ROUNDS
-#define RTX_ROUNDS 2
+#define RTX_ROUNDS 1
 #endif
 #ifndef RTX_MINBLOCKS
-#define RTX_MINBLOCKS 2
+#define RTX_MINBLOCKS 3
 #endif
 
 constexpr int ROUNDS = RTX_ROUNDS;  // prologue rounds per chunk (one line per thread per round)
