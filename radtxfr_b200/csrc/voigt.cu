@@ -299,6 +299,38 @@ __global__ void bin_kernel(int n_states, int n_tiles, int tile_pts, const double
   bins[2 * i + 1] = (int32_t)last;
 }
 
+// Searches on the shared-memory tile with an arithmetic first guess.  The answers are defined by exact comparisons
+// on the grid values (identical to bisect); the guess only shortens the walk: on a uniform grid it is off by at
+// most one, on an irregular grid the walk is bounded and falls back to bisection.
+struct TileScale { double g0, inv_dv; int n; };
+
+__device__ __forceinline__ int guess_index(const TileScale& ts, double v) {
+  const double t = (v - ts.g0) * ts.inv_dv;
+  return (int)fmin(fmax(t, -1.0), (double)ts.n) + 1;          // ~ number of elements <= v
+}
+// number of elements <= v among a[0..n)   (== bisect_right)
+__device__ __forceinline__ int count_le(const double* a, const TileScale& ts, double v) {
+  int g = min(max(guess_index(ts, v), 0), ts.n);
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    if (g > 0 && v < a[g - 1]) { --g; continue; }
+    if (g < ts.n && !(v < a[g])) { ++g; continue; }
+    return g;
+  }
+  return bisect_right_dev(a, ts.n, v);
+}
+// number of elements < v among a[0..n)   (== bisect_left)
+__device__ __forceinline__ int count_lt(const double* a, const TileScale& ts, double v) {
+  int g = min(max(guess_index(ts, v), 0), ts.n);
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    if (g > 0 && !(a[g - 1] < v)) { --g; continue; }
+    if (g < ts.n && a[g] < v) { ++g; continue; }
+    return g;
+  }
+  return bisect_left_dev(a, ts.n, v);
+}
+
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -372,6 +404,10 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
 #pragma unroll
   for (int j = 0; j < K; ++j) acc[j] = 0.0;
 
+  TileScale ts;
+  ts.g0 = s_grid[0];
+  ts.n = npts;
+  ts.inv_dv = (npts > 1 && s_grid[npts - 1] > s_grid[0]) ? (double)(npts - 1) / (s_grid[npts - 1] - s_grid[0]) : 0.0;
   const double T = P.T[s], p = P.p[s];
   const double lnr = log(RTX_TREF / T);
   const int64_t bi = 2 * ((int64_t)s * P.n_tiles + tile);
@@ -395,8 +431,8 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
       if (li < last) {
         const LineState L = line_state(P, li, s, T, p, lnr);
         if (L.keep) {
-          const int lo = bisect_right_dev(s_grid, TILE, L.nu - L.W);      // misc/hapi.py:11133
-          const int hi = bisect_right_dev(s_grid, TILE, L.nu + L.W);      // misc/hapi.py:11134
+          const int lo = count_le(s_grid, ts, L.nu - L.W);                // bisect(Omegas, nu-W), misc/hapi.py:11133
+          const int hi = count_le(s_grid, ts, L.nu + L.W);                // bisect(Omegas, nu+W), misc/hapi.py:11134
           if (hi > lo) {
             const double cte = RTX_SQRT_LN2 / L.gamD;                      // misc/hapi.py:9900
             const double y = L.gam0 * cte;                                 // misc/hapi.py:9913
@@ -415,20 +451,49 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
             int clo = lo, chi = lo;                                        // empty Weideman core
             if (y < 15.0) {
               // the mask |x|+y<15 is a contiguous index range around sg0; find it with the exact predicate
-              int m = bisect_left_dev(s_grid, TILE, L.sg0);
+              // (exact predicate of hum1_wei; it is monotone on either side of sg0, so each end is found by a
+              // short walk from the arithmetic estimate sg0 -+ (15-y)/cte, with bisection as the fallback)
+              int m = count_lt(s_grid, ts, L.sg0);
               m = max(lo, min(hi, m));
-              int a0 = lo, a1 = m;                                         // first true in [lo, m)
-              while (a0 < a1) {
-                const int mid = (a0 + a1) >> 1;
-                if (in_weideman(s_grid[mid], L.sg0, cte, y)) a1 = mid; else a0 = mid + 1;
+              const double hw = (15.0 - y) / cte;
+              {   // first true in [lo, m)
+                int g = max(lo, min(m, count_lt(s_grid, ts, L.sg0 - hw)));
+                bool done = false;
+#pragma unroll 1
+                for (int it = 0; it < 4 && !done; ++it) {
+                  if (g > lo && in_weideman(s_grid[g - 1], L.sg0, cte, y)) --g;
+                  else if (g < m && !in_weideman(s_grid[g], L.sg0, cte, y)) ++g;
+                  else done = true;
+                }
+                if (!done) {
+                  int a0 = lo, a1 = m;
+                  while (a0 < a1) {
+                    const int mid = (a0 + a1) >> 1;
+                    if (in_weideman(s_grid[mid], L.sg0, cte, y)) a1 = mid; else a0 = mid + 1;
+                  }
+                  g = a0;
+                }
+                clo = g;
               }
-              clo = a0;
-              a0 = m; a1 = hi;                                             // first false in [m, hi)
-              while (a0 < a1) {
-                const int mid = (a0 + a1) >> 1;
-                if (in_weideman(s_grid[mid], L.sg0, cte, y)) a0 = mid + 1; else a1 = mid;
+              {   // first false in [m, hi)
+                int g = max(m, min(hi, count_le(s_grid, ts, L.sg0 + hw)));
+                bool done = false;
+#pragma unroll 1
+                for (int it = 0; it < 4 && !done; ++it) {
+                  if (g > m && !in_weideman(s_grid[g - 1], L.sg0, cte, y)) --g;
+                  else if (g < hi && in_weideman(s_grid[g], L.sg0, cte, y)) ++g;
+                  else done = true;
+                }
+                if (!done) {
+                  int a0 = m, a1 = hi;
+                  while (a0 < a1) {
+                    const int mid = (a0 + a1) >> 1;
+                    if (in_weideman(s_grid[mid], L.sg0, cte, y)) a0 = mid + 1; else a1 = mid;
+                  }
+                  g = a0;
+                }
+                chi = g;
               }
-              chi = a0;
             }
             if (hi - lo <= NARROW_MAX) {
               has_seg = true; sr.s = lo; sr.e = hi;
