@@ -284,7 +284,7 @@ def gpu_arm(args):
             t = torch.tensor([dte], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dte = t.item()
-        h2d = 8 * (nX + 2 * nL + nL * db.n_iso)
+        h2d = 8 * (3 * nL + nL * db.n_iso)      # T, p, T (TUD) and column amounts; the spectral axis is cached on the device
         d2h = 8 * 3 * nX
         e2e = {"value": E_all / dte, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * dte / args.steps,
