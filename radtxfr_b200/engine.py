@@ -181,7 +181,9 @@ class LineDB:
         for k in _COLS_OPTIONAL:
             cat[k] = column(k, False)
         self.n_lines = int(mol.size)
-        pairs = sorted(set(zip(mol.tolist(), iso.tolist())))
+        key = mol * 1000 + iso                               # vectorised (M, I) grouping
+        ukey, inverse = np.unique(key, return_inverse=True) if key.size else (np.zeros(0, np.int64), np.zeros(0, np.int64))
+        pairs = [(int(k // 1000), int(k % 1000)) for k in ukey]  # sorted like sorted(set(zip(M, I)))
         self.pairs = pairs
         self.pair_index = {mi: j for j, mi in enumerate(pairs)}
         idx = np.zeros(len(pairs), dtype=np.int64)
@@ -197,9 +199,7 @@ class LineDB:
         tT = np.ascontiguousarray(T["tips_T"].astype(np.float64))
         _lib.call("rtx_set_iso_table", self.handle.h, n_iso, _hptr(mass), _hptr(tT), _hptr(q))
         self.n_iso = n_iso
-        lut = {mi: j for j, mi in enumerate(pairs)}
-        iso_idx = np.fromiter((lut[mi] for mi in zip(mol.tolist(), iso.tolist())), dtype=np.int32,
-                              count=self.n_lines)
+        iso_idx = np.ascontiguousarray(inverse.astype(np.int32))
         self.molecules = sorted(set(m for m, _ in pairs))
         self.iso_molecule = np.array([m for m, _ in pairs], dtype=np.int64)
         _lib.call("rtx_lines_upload", self.handle.h, self.n_lines, _hptr(cat["nu"]), _hptr(cat["sw"]),

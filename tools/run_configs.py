@@ -1,0 +1,177 @@
+"""Run the BASELINE.json configurations other than the bench's config 2 end to end and print one JSON line each
+(timings + a parity spot-check against the CPU oracle).  Config 5 is launched under torchrun on 8 GPUs:
+
+    python tools/run_configs.py 1 3 4
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29551 \
+        tools/run_configs.py 5
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from radtxfr_b200 import engine, hapi_compat, radiative_transfer as rt, synthetic as syn  # noqa: E402
+from radtxfr_b200 import distributed as D  # noqa: E402
+from oracle import port  # noqa: E402  (checker only)
+
+
+def parity(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    m = np.max(np.abs(b))
+    ok = bool(np.all(np.abs(a - b) <= 1e-9 * np.abs(b) + 1e-12 * m))
+    big = (np.abs(b) >= 1e-6 * m) & (np.abs(b) > 0)
+    return ok, float(np.max(np.abs(a - b)[big] / np.abs(b[big]))) if big.any() else 0.0
+
+
+def timed(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = fn()
+    torch.cuda.synchronize()
+    return r, (time.perf_counter() - t0) / reps
+
+
+def config1():
+    cols = syn.config1_lines()
+    hapi_compat.storeTable("cfg1", cols)
+    grid = np.linspace(800.0, 1300.0, 50001)
+    env = {"T": 296.0, "p": 1.0}
+    (om, xs), dt = timed(lambda: hapi_compat.absorptionCoefficient_Voigt(SourceTables="cfg1", Environment=env, OmegaGrid=grid))
+    db = hapi_compat.line_database(["cfg1"])
+    ev, evw = db.count_evals([296.0], [1.0], db.iso_factors(None, 1.0)[None, :], grid)
+    gd = torch.from_numpy(grid).cuda(); w = torch.from_numpy(db.iso_factors(None, 1.0)[None, :]).cuda()
+    Tt = torch.tensor([296.0], dtype=torch.float64, device="cuda"); pp = torch.tensor([1.0], dtype=torch.float64, device="cuda")
+    out = torch.empty((1, grid.size), dtype=torch.float64, device="cuda")
+    _, dk = timed(lambda: db.voigt_sum(Tt, pp, w, gd, out=out), reps=50)
+    t0 = time.perf_counter()
+    _, ref = port.absorption_coefficient_voigt(cols, T=296.0, p=1.0, OmegaGrid=grid)
+    tcpu = time.perf_counter() - t0
+    ok, rel = parity(xs, ref)
+    return {"config": 1, "what": "single-layer H2O Voigt cross-section 296 K / 1 atm, 800-1300 @0.01, 20000 synthetic lines",
+            "evals": ev, "api_ms": 1e3 * dt, "kernels_ms": 1e3 * dk, "evals_per_s_api": ev / dt, "evals_per_s_kernels": ev / dk,
+            "oracle_1core_s": tcpu, "oracle_evals_per_s": ev / tcpu, "parity_ok": ok, "max_rel_err": rel,
+            "note": "launch-bound: 196 CTAs of 256 points (K=1), one wave"}
+
+
+def config3(n_atm=256):
+    atm = syn.standard_atmosphere(); tabs = syn.config2_tables()
+    opts = dict(rt.options); rt.set_line_database(tabs, opts=opts)
+    Ts, MF = syn.perturbed_atmospheres(2, n_atm)
+    kw = dict(Zs=atm["Zs"], Ps=atm["Ps"], PLs=atm["PLs"], MFs_ID=atm["MFs_ID"], DVOUT=0.01, N_angle=30)
+    rt.compute_TUD_batch(700.0, 1500.0, Ts[:8], MF[:8], opts=dict(opts), ils="triangle", **kw)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    X, tau, lu, ld = rt.compute_TUD_batch(700.0, 1500.0, Ts, MF, opts=dict(opts), ils="triangle", **kw)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    # parity on one atmosphere over a sub-band against the oracle
+    j = 17
+    o = dict(opts)
+    Xs, t1, u1, d1 = rt.compute_TUD(900.0, 905.0, opts=o, **dict(kw, Ts=Ts[j], MFs_VAL=MF[j]))
+    sub = {m: {k: v[(t["nu"] > 890) & (t["nu"] < 915)] for k, v in t.items()} for m, t in tabs.items()}
+    Xr, tr, ur, dr = port.compute_tud(sub, 900.0, 905.0, Zs=atm["Zs"], Ts=Ts[j], Ps=atm["Ps"], PLs=atm["PLs"],
+                                      MFs_VAL=MF[j], MFs_ID=atm["MFs_ID"], DVOUT=0.01)
+    oks = [parity(a, b) for a, b in ((t1, tr), (u1, ur), (d1, dr))]
+    return {"config": 3, "what": "%d perturbed atmospheres, TUD 700-1500 @0.01 (80000 pts) + MAKO ILS, 1 GPU" % n_atm,
+            "seconds": dt, "tud_spectra_per_s": n_atm / dt, "out_shape": list(tau.shape),
+            "parity_ok": all(o_[0] for o_ in oks), "max_rel_err": max(o_[1] for o_ in oks)}
+
+
+def config4():
+    atm = syn.standard_atmosphere(); tabs = syn.config2_tables()
+    opts = dict(rt.options); rt.set_line_database(tabs, opts=opts)
+    nA, nE = 16, 64
+    Ts, MF = syn.perturbed_atmospheres(2, nA)
+    kw = dict(Zs=atm["Zs"], Ps=atm["Ps"], PLs=atm["PLs"], MFs_ID=atm["MFs_ID"], DVOUT=0.01, N_angle=30)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    Xb, tau, lu, ld = rt.compute_TUD_batch(700.0, 1500.0, Ts, MF, opts=dict(opts), ils="triangle", **kw)
+    torch.cuda.synchronize(); t_tud = time.perf_counter() - t0
+    nB = Xb.size
+    Xh = rt.make_spectral_axis(700.0, 1500.0, 0.01)
+    emis_hi = syn.synthetic_emissivities(3, nE, Xh)
+    _, emis_b = rt.ILS_MAKO(Xh, emis_hi)                                  # [nB, nE]
+    rng = np.random.default_rng(3)
+    nP = 512 * 512
+    atm_idx = rng.integers(0, nA, nP).astype(np.int32)
+    mat = rng.integers(0, nE, (nP, 2)).astype(np.int32)
+    fr = rng.random((nP, 2)); fr /= fr.sum(axis=1)[:, None]
+    Tsurf = Ts[:, 0]
+    Tp = Tsurf[atm_idx] + 3.0 * rng.standard_normal(nP)
+    dev = dict(X=torch.from_numpy(Xb).cuda(), emis=torch.from_numpy(np.ascontiguousarray(emis_b.T)).cuda(),
+               tau=tau[:, :, 0, 0].contiguous(), la=lu[:, :, 0, 0].contiguous(), ld=ld.contiguous(),
+               atm=torch.from_numpy(atm_idx).cuda(), T=torch.from_numpy(Tp).cuda(), mat=torch.from_numpy(mat).cuda(),
+               fr=torch.from_numpy(fr).cuda())
+    f = lambda: engine.hsi_pixels(dev["X"], dev["emis"], dev["tau"], dev["la"], dev["ld"], dev["atm"], dev["T"], dev["mat"], dev["fr"])
+    L, dt = timed(f, reps=10)
+    cube = L.view(512, 512, nB)
+    # parity on 2000 pixels
+    idx = rng.choice(nP, 2000, replace=False)
+    tb, lb, db_ = (a.cpu().numpy() for a in (dev["tau"], dev["la"], dev["ld"]))
+    em = np.array([np.dot(fr[i], emis_b.T[mat[i]]) for i in idx])
+    B = port.planckian(Xb, Tp[idx]).T
+    ref = tb[atm_idx[idx]] * (em * B + (1 - em) * db_[atm_idx[idx]]) + lb[atm_idx[idx]]
+    ok, rel = parity(L.cpu().numpy()[idx], ref)
+    return {"config": 4, "what": "LWIR apparent radiance for a 512x512x%d HSI cube, %d atmospheres, %d emissivities, 2-material mixes" % (nB, nA, nE),
+            "tud_plus_ils_s": t_tud, "cube_ms": 1e3 * dt, "cube_bytes": int(L.numel() * 8),
+            "cube_GBps_written": L.numel() * 8 / dt / 1e9, "cube_shape": list(cube.shape), "parity_ok": ok, "max_rel_err": rel}
+
+
+def config5(n_lines=5_000_000, nx=11_000_000, n_layers=60):
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    atm = syn.standard_atmosphere()
+    mols = [1, 2, 3, 4, 5, 6, 7, 22]
+    share = [0.25, 0.25, 0.2, 0.08, 0.05, 0.12, 0.03, 0.02]
+    tabs = {}
+    for k, (m, s) in enumerate(zip(mols, share)):
+        tabs[m] = syn.synthetic_lines(4000 + k, int(n_lines * s), 475.0, 6025.0, m, (1,), (1.0,))
+    t0 = time.perf_counter()
+    opts = dict(rt.options)
+    db = rt.set_line_database(tabs, opts=opts)
+    ingest_s = time.perf_counter() - t0
+    dv = (6000.0 - 500.0) / nx
+    kw = dict(Zs=atm["Zs"][:n_layers], Ts=atm["Ts"][:n_layers], Ps=atm["Ps"][:n_layers], PLs=atm["PLs"][:n_layers],
+              MFs_VAL=atm["MFs_VAL"][:n_layers], MFs_ID=atm["MFs_ID"], DVOUT=dv, N_angle=30)
+    D.compute_TUD_banded(500.0, 6000.0, dict(opts), **kw)           # warm-up
+    dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    X, tau, Lu, Ld = D.compute_TUD_banded(500.0, 6000.0, dict(opts), **kw)
+    torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
+    # exact evals of this rank's band
+    bands = D.plan_bands(X.size, world)
+    i0, i1 = bands[rank]
+    p, w = rt.layer_weights(db, kw["Ts"], kw["Ps"], kw["PLs"], kw["MFs_VAL"], kw["MFs_ID"])
+    ev, _ = db.count_evals(kw["Ts"], p, w, torch.from_numpy(X[i0:i1]).cuda())
+    tot = torch.tensor([float(ev)], dtype=torch.float64, device="cuda"); dist.all_reduce(tot)
+    out = None
+    if rank == 0:
+        # parity: 3000 points of the first band against the oracle (lines within reach only)
+        sl = slice(200000, 203000)
+        lo, hi = X[sl][0] - 40.0, X[sl][-1] + 40.0
+        sub = {m: {k: v[(t["nu"] > lo) & (t["nu"] < hi)] for k, v in t.items()} for m, t in tabs.items()}
+        OD = np.zeros((3000, n_layers))
+        for L in range(n_layers):
+            OD[:, L] = port.layer_od(sub, X[sl], kw["Ts"][L], kw["Ps"][L], kw["PLs"][L], kw["MFs_VAL"][L], kw["MFs_ID"])
+        tr, ur, dr = port.tud_from_od(X[sl], OD, kw["Zs"], kw["Ts"])
+        oks = [parity(a[sl], b) for a, b in ((tau, tr), (Lu, ur), (Ld, dr))]
+        out = {"config": 5, "what": "wide band 500-6000 cm^-1, %d points x %d layers, %d synthetic lines of 8 molecules, "
+               "sharded by wavenumber band over %d GPUs, one all_gather" % (X.size, n_layers, n_lines, world),
+               "seconds": dt, "evals": tot.item(), "evals_per_s": tot.item() / dt, "ingest_s": ingest_s,
+               "band_points": [b - a for a, b in bands], "parity_ok": all(o_[0] for o_ in oks),
+               "max_rel_err": max(o_[1] for o_ in oks)}
+    dist.barrier()
+    dist.destroy_process_group()
+    return out
+
+
+if __name__ == "__main__":
+    for c in sys.argv[1:]:
+        r = {"1": config1, "3": config3, "4": config4, "5": config5}[c]()
+        if r is not None:
+            print(json.dumps(r), flush=True)
