@@ -185,6 +185,19 @@ int rtx_ils_apply(rtx_handle* h, int mode, const double* X_dev, int64_t nx, cons
                   int n_bands, const double* centre_dev, const double* width_dev, double* out_dev,
                   void* stream);
 
+/* ---- reduceResolution / smooth (radiative_transfer.py:1266-1350), the step after TUD in the production driver
+ * (Generate_LWIR_TUD.py:82-85,124-126).
+ * rtx_smooth_sym: column-wise for Y_dev[n][m]: symmetric=0 gives smooth(y) (the reference's reflect-pad / convolve
+ * with the NORMALISED window window_dev[window_len] / trim, :1266-1323), symmetric=1 gives
+ * 0.5*(smooth(y) + smooth(y[::-1])[::-1]) as reduceResolution uses it (:1330).
+ * rtx_spline_eval: C2 cubic-spline interpolation of the columns of Y_dev[n][m] on the knots X_dev[n] (ascending) at
+ * Xo_dev[n_out] -> out_dev[n_out][m]; equals scipy interp1d(kind="cubic") to rounding for points at least 40 knots
+ * away from the ends of the data (reduceResolution's own output axis always is). */
+int rtx_smooth_sym(rtx_handle* h, const double* Y_dev, int64_t n, int64_t m, const double* window_dev, int window_len,
+                   int symmetric, double* out_dev, void* stream);
+int rtx_spline_eval(rtx_handle* h, const double* X_dev, const double* Y_dev, int64_t n, int64_t m,
+                    const double* Xo_dev, int64_t n_out, double* out_dev, void* stream);
+
 /* ---- measurement helpers -------------------------------------------------------------------
  * Dependent-free DFMA loop: writes the achieved FP64 FMA rate [flop/s] of the handle's device.
  * Used by bench.py as the measured denominator of the Voigt kernel's FP64 roofline. */

@@ -474,3 +474,39 @@ def ils_mako_gauss(X, Y):
     if Y.ndim == 1:
         out = out[:, 0]
     return Xo, out
+
+
+# ----------------------------------------------------------------------------- resolution reduction
+def smooth(x, window_len=11, window="hanning"):
+    """smooth, radiative_transfer.py:1266-1323."""
+    x = np.asarray(x, dtype=float)
+    if x.ndim != 1 or x.size < window_len or window_len < 3:
+        return x
+    s = np.r_[x[window_len - 1:0:-1], x, x[-2:-window_len - 1:-1]]
+    w = np.ones(window_len, "d") if window == "flat" else getattr(np, window)(window_len)
+    y = np.convolve(w / w.sum(), s, mode="valid")
+    return y[int(np.ceil(window_len / 2 - 1)):-int(np.floor(window_len / 2))]
+
+
+def reduce_resolution(X, Y, dX, N=4, window="hanning", X_out=None):
+    """reduceResolution, radiative_transfer.py:1326-1350 (np.int -> int)."""
+    import scipy.interpolate
+    X = np.asarray(X, dtype=float)
+    Y = np.asarray(Y, dtype=float)
+    smFactor = int(np.round(dX / np.mean(np.diff(X))))
+    sm1 = lambda y: smooth(y, window_len=smFactor, window=window)
+    sm = lambda y: 0.5 * (sm1(y) + sm1(y[::-1])[::-1])
+    interp = lambda x, y, x0: scipy.interpolate.interp1d(x, y, kind="cubic", bounds_error=False,
+                                                         fill_value="extrapolate")(x0)
+    X_ = sm(X)
+    ret_x = X_out is None
+    if ret_x:
+        nPts = int(np.ceil(N * (X_[-smFactor - 1] - X_[smFactor]) / dX)) + 1
+        X_out = np.linspace(X_[smFactor], X_[-smFactor - 1], nPts)
+    if Y.ndim > 1:
+        Y_out = np.zeros((X_out.size, Y.shape[-1]))
+        for ii in range(Y.shape[-1]):
+            Y_out[:, ii] = interp(X_, sm(Y[:, ii]), X_out)
+    else:
+        Y_out = interp(X_, sm(Y), X_out)
+    return (X_out, Y_out) if ret_x else Y_out

@@ -44,6 +44,8 @@ _SIGNATURES = {
                        c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "rtx_ils_apply": [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                       c_void_p, c_void_p],
+    "rtx_smooth_sym": [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "rtx_spline_eval": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p],
     "rtx_measure_fp64_peak": [c_void_p, POINTER(c_double)],
     "rtx_launch_count": [c_void_p, POINTER(c_uint64)],
     "rtx_weideman_coeffs": [c_void_p],

@@ -117,7 +117,98 @@ __global__ void hsi_kernel(const double* __restrict__ X, int64_t nx, const doubl
   L[i] = tau[ar] * ls + la[ar];
 }
 
+// ---- reduceResolution / smooth (radiative_transfer.py:1266-1350) ------------------------------------------
+// Symmetrised window smoothing: smFcn(y) = 0.5*(smooth(y) + smooth(y[::-1])[::-1]) with smooth() = reflect-pad,
+// convolve with the normalised window, trim (ix0 = ceil(wl/2-1)).  In index form, with xr() the reflected extension,
+//   smFcn(y)[i] = 0.5 * sum_j wn[j] * (xr(i + ix0 - j) + xr(i - ix0 + j)).
+__global__ void smooth_sym_kernel(const double* __restrict__ Y, int64_t n, int64_t m, const double* __restrict__ wn,
+                                  int wl, int ix0, int symmetric, double* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * m) return;
+  const int64_t i = idx / m, c = idx % m;
+  double acc = 0.0;
+  for (int j = 0; j < wl; ++j) {
+    int64_t q1 = i + ix0 - j, q2 = i - ix0 + j;
+    q1 = q1 < 0 ? -q1 : (q1 >= n ? 2 * (n - 1) - q1 : q1);
+    q2 = q2 < 0 ? -q2 : (q2 >= n ? 2 * (n - 1) - q2 : q2);
+    const double v = symmetric ? Y[q1 * m + c] + Y[q2 * m + c] : Y[q1 * m + c];
+    acc = fma(wn[j], v, acc);
+  }
+  out[idx] = symmetric ? 0.5 * acc : acc;
+}
+
+// Cubic-spline interpolation (scipy interp1d(kind="cubic"): C2 cubic spline through all knots).  The spline's
+// second derivatives decay like (2-sqrt(3))^k away from a knot, so each output point solves the tridiagonal system
+// only on a window of HW knots either side of its interval (truncation < 1e-20 for HW = 40); the window ends use the
+// natural condition, which is exact to rounding whenever the point is >= HW knots from the ends of the data -- always
+// the case for reduceResolution's own output axis, which starts smFactor knots inside.
+constexpr int SPL_HW = 40;
+__global__ void spline_eval_kernel(const double* __restrict__ X, const double* __restrict__ Y, int64_t n, int64_t m,
+                                   const double* __restrict__ Xo, int64_t no, double* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= no * m) return;
+  const int64_t t = idx / m, c = idx % m;
+  const double xo = Xo[t];
+  int64_t i = bisect_right_dev64(X, n, xo) - 1;          // X[i] <= xo < X[i+1]
+  i = max((int64_t)0, min(n - 2, i));                    // ends: extrapolate with the end polynomial
+  const int64_t k0 = max((int64_t)0, i - SPL_HW), k1 = min(n - 1, i + 1 + SPL_HW);
+  const int nk = (int)(k1 - k0 + 1);                     // knots in the window, <= 2*HW+2
+  double cp[2 * SPL_HW + 2], dp[2 * SPL_HW + 2];         // Thomas algorithm workspace (second derivatives)
+  cp[0] = 0.0; dp[0] = 0.0;                              // natural: M_0 = 0
+  for (int k = 1; k < nk - 1; ++k) {
+    const int64_t g = k0 + k;
+    const double h0 = X[g] - X[g - 1], h1 = X[g + 1] - X[g];
+    const double rhs = 6.0 * ((Y[(g + 1) * m + c] - Y[g * m + c]) / h1 - (Y[g * m + c] - Y[(g - 1) * m + c]) / h0);
+    const double den = 2.0 * (h0 + h1) - h0 * cp[k - 1];
+    cp[k] = h1 / den;
+    dp[k] = (rhs - h0 * dp[k - 1]) / den;
+  }
+  // back substitution down to the interval's two knots
+  double Mn = 0.0;                                        // M_{nk-1} = 0
+  const int ki = (int)(i - k0);
+  double Mi1 = 0.0, Mi = 0.0;
+  for (int k = nk - 2; k >= ki; --k) {
+    const double Mk = (k >= 1) ? dp[k] - cp[k] * Mn : 0.0;
+    if (k == ki + 1) Mi1 = Mk;
+    if (k == ki) Mi = Mk;
+    Mn = Mk;
+  }
+  if (ki + 1 == nk - 1) Mi1 = 0.0;
+  const double h = X[i + 1] - X[i];
+  const double A = (X[i + 1] - xo) / h, B = (xo - X[i]) / h;
+  out[idx] = A * Y[i * m + c] + B * Y[(i + 1) * m + c] +
+             ((A * A * A - A) * Mi + (B * B * B - B) * Mi1) * (h * h) / 6.0;
+}
+
 }  // namespace
+
+extern "C" int rtx_smooth_sym(rtx_handle* h, const double* Y_dev, int64_t n, int64_t m, const double* window_dev,
+                              int window_len, int symmetric, double* out_dev, void* stream) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  RTX_REQUIRE(n > 0 && m > 0 && window_len >= 1 && window_len <= n && Y_dev && window_dev && out_dev,
+              "rtx_smooth_sym: bad arguments");
+  DeviceGuard guard(h->device);
+  const int ix0 = (window_len + 1) / 2 - 1;               // int(ceil(window_len/2 - 1)), radiative_transfer.py:1321
+  const int64_t total = n * m;
+  smooth_sym_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      Y_dev, n, m, window_dev, window_len, ix0, symmetric, out_dev);
+  RTX_CUDA(cudaGetLastError());
+  h->launches++;
+  return RTX_OK;
+}
+
+extern "C" int rtx_spline_eval(rtx_handle* h, const double* X_dev, const double* Y_dev, int64_t n, int64_t m,
+                               const double* Xo_dev, int64_t n_out, double* out_dev, void* stream) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  RTX_REQUIRE(n >= 4 && m > 0 && n_out > 0 && X_dev && Y_dev && Xo_dev && out_dev, "rtx_spline_eval: bad arguments");
+  DeviceGuard guard(h->device);
+  const int64_t total = n_out * m;
+  spline_eval_kernel<<<(unsigned)((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      X_dev, Y_dev, n, m, Xo_dev, n_out, out_dev);
+  RTX_CUDA(cudaGetLastError());
+  h->launches++;
+  return RTX_OK;
+}
 
 extern "C" int rtx_ils_apply(rtx_handle* h, int mode, const double* X_dev, int64_t nx, const double* Y_dev, int64_t ns,
                              int n_bands, const double* centre_dev, const double* width_dev, double* out_dev,

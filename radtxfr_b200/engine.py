@@ -68,6 +68,8 @@ def to_device(x, device, dtype=None):
         return x.to(device=device, dtype=dtype).contiguous()
     npdt = {torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64}[dtype]
     a = np.ascontiguousarray(np.asarray(x, dtype=npdt))
+    if not a.flags.writeable:
+        a = a.copy()
     return torch.from_numpy(a).to(device)
 
 
@@ -347,6 +349,34 @@ def brightness(X, V, wavelength=False, inverse=False, bad_value=float("nan"), de
     if out.numel():
         _lib.call("rtx_brightness", h.h, _ptr(X), X.numel(), _ptr(V), V.shape[1], int(bool(wavelength)),
                   int(bool(inverse)), float(bad_value), _ptr(out), _stream(dev))
+    return out
+
+
+def smooth(Y, window, symmetric, device=None):
+    """rtx_smooth_sym: Y [n, m], window = normalised taps."""
+    torch = _torch()
+    dev = resolve_device(device if not (isinstance(Y, torch.Tensor) and Y.is_cuda) else Y.device)
+    h = default_handle(dev)
+    Y = to_device(Y, dev)
+    assert Y.dim() == 2
+    w = to_device(window, dev).reshape(-1)
+    out = torch.empty_like(Y)
+    _lib.call("rtx_smooth_sym", h.h, _ptr(Y), Y.shape[0], Y.shape[1], _ptr(w), w.numel(), int(bool(symmetric)), _ptr(out),
+              _stream(dev))
+    return out
+
+
+def spline_eval(X, Y, Xo, device=None):
+    """rtx_spline_eval: cubic spline through (X [n], Y [n, m]) evaluated at Xo -> [n_out, m]."""
+    torch = _torch()
+    dev = resolve_device(device if not (isinstance(Y, torch.Tensor) and Y.is_cuda) else Y.device)
+    h = default_handle(dev)
+    X = to_device(X, dev).reshape(-1)
+    Y = to_device(Y, dev)
+    Xo = to_device(Xo, dev).reshape(-1)
+    out = torch.empty((Xo.numel(), Y.shape[1]), dtype=torch.float64, device=dev)
+    _lib.call("rtx_spline_eval", h.h, _ptr(X), _ptr(Y), X.numel(), Y.shape[1], _ptr(Xo), Xo.numel(), _ptr(out),
+              _stream(dev))
     return out
 
 

@@ -341,6 +341,73 @@ def compute_LWIR_apparent_radiance(X, emis, Ts, tau, La, Ld, dT=None, return_Ls=
     return out.cpu().numpy()
 
 
+def _window_taps(window_len, window):
+    if window == "flat":
+        w = np.ones(window_len, "d")
+    else:
+        w = getattr(np, window)(window_len)                  # eval("np." + window + "(window_len)"), :1316
+    return w / w.sum()
+
+
+def smooth(x, window_len=11, window="hanning"):
+    """Window smoothing with reflected ends, radiative_transfer.py:1266-1323 (same guards and return length)."""
+    torch = engine._torch()
+    as_tensor = isinstance(x, torch.Tensor)
+    nd = x.dim() if as_tensor else np.ndim(x)
+    size = x.numel() if as_tensor else np.size(x)
+    if nd != 1:
+        print("smooth only accepts 1 dimension arrays.")
+        return x
+    if size < window_len:
+        print("Input vector needs to be bigger than window size.")
+        return x
+    if window_len < 3:
+        return x
+    if window not in ["flat", "hanning", "hamming", "bartlett", "blackman"]:
+        print("Window is on of 'flat', 'hanning', 'hamming', 'bartlett', 'blackman'")
+        return x
+    xin = x.reshape(-1, 1) if as_tensor else np.asarray(x, dtype=float)[:, None]
+    out = engine.smooth(xin, _window_taps(window_len, window), False)[:, 0]
+    return out if as_tensor else out.cpu().numpy()
+
+
+def reduceResolution(X, Y, dX, N=4, window="hanning", X_out=None):
+    """Smooth to resolution dX and resample with a cubic spline on N points per dX: radiative_transfer.py:1326-1350
+    (the step that follows compute_TUD in Generate_LWIR_TUD.py:82-85, 124-126).  Returns (X_out, Y_out), or Y_out
+    alone when X_out is given.  The reference needs np.int restored to run on numpy >= 1.24; int() is used here."""
+    torch = engine._torch()
+    as_tensor = isinstance(Y, torch.Tensor)
+    Xh = X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(X, dtype=float)
+    dX_in = np.mean(np.diff(Xh))
+    smFactor = int(np.round(dX / dX_in))
+    one_d = (Y.dim() if as_tensor else np.ndim(Y)) == 1
+    Y2 = (Y.reshape(-1, 1) if one_d else Y) if as_tensor else (np.asarray(Y, dtype=float)[:, None] if one_d
+                                                                  else np.asarray(Y, dtype=float))
+    if smFactor < 3 or Xh.size < smFactor:                  # smooth() returns its input unchanged (:1301-1306)
+        X_s = engine.to_device(Xh, None)[:, None]
+        Y_s = engine.to_device(Y2, X_s.device)
+    else:
+        taps = _window_taps(smFactor, window)
+        X_s = engine.smooth(Xh[:, None], taps, True)        # smFcn(X)
+        Y_s = engine.smooth(Y2, taps, True)                 # smFcn(Y[:, ii])
+    returnX_out = False
+    if X_out is None:
+        a = float(X_s[smFactor, 0].item())
+        b = float(X_s[-smFactor - 1, 0].item())
+        nPts = int(np.ceil(N * (b - a) / dX)) + 1
+        X_out = np.linspace(a, b, nPts)
+        returnX_out = True
+    Xo = X_out.detach().cpu().numpy() if isinstance(X_out, torch.Tensor) else np.asarray(X_out, dtype=float)
+    out = engine.spline_eval(X_s[:, 0].contiguous(), Y_s, Xo)
+    if one_d:
+        out = out[:, 0]
+    if not as_tensor:
+        out = out.cpu().numpy()
+    if returnX_out:
+        return X_out, out
+    return out
+
+
 def _mako_um():
     return engine.spectro_tables()["mako_um"]          # radiative_transfer.py:1092-1223
 

@@ -297,6 +297,27 @@ def test_brightness_temperature_golden(mods):
     assert_parity(rt.brightnessTemperature(X, rt.BT2L(X, T)), T, 1e-9, 1e-12, "BT round trip")
 
 
+def test_reduce_resolution_golden(mods):
+    """smooth / reduceResolution against the reference's outputs (np.int restored)."""
+    rt = mods["rt"]
+    g = golden("reduce.npz")
+    rng = np.random.default_rng(70)
+    X = np.linspace(690.0, 1410.0, 28800)
+    Y = np.cumsum(rng.normal(0, 1, (X.size, 3)), axis=0) * 0.01 + np.sin(X / 7.0)[:, None]
+    Xo, Yo = rt.reduceResolution(X, Y, 0.25)
+    assert Xo.shape == g["Xo"].shape and Yo.shape == g["Yo"].shape
+    assert_parity(Xo, g["Xo"], 1e-12, 0.0, "reduceResolution X_out")
+    assert_parity(Yo, g["Yo"], RTOL, FLOOR, "reduceResolution Y_out")
+    Xo5, Yo5 = rt.reduceResolution(X, Y[:, 1], 0.1, N=2, window="hamming")
+    assert Yo5.shape == g["Yo5"].shape
+    assert_parity(Yo5, g["Yo5"], RTOL, FLOOR, "reduceResolution 1-D hamming")
+    y1 = rt.reduceResolution(X, Y[:, 0], 0.25, X_out=g["Xo"])
+    assert_parity(y1, g["Yo"][:, 0], RTOL, FLOOR, "reduceResolution given X_out")
+    assert_parity(rt.smooth(Y[:, 0], 11), g["s11"], RTOL, FLOOR, "smooth hanning 11")
+    assert_parity(rt.smooth(Y[:, 2], 10, "flat"), g["s10f"], RTOL, FLOOR, "smooth flat 10")
+    assert rt.smooth(Y[:, 0], 2) is Y[:, 0] or np.array_equal(rt.smooth(Y[:, 0], 2), Y[:, 0])
+
+
 def test_hsi_pixels(mods):
     engine, port, syn = mods["engine"], mods["port"], mods["syn"]
     rng = np.random.default_rng(7)

@@ -125,3 +125,21 @@ def test_brightness_temperature():
     assert np.array_equal(np.isnan(lb), np.isnan(g["L_bad"]))
     assert np.array_equal(port.brightness_temperature(g["Xu"], g["Lu"], wavelength=True), g["bt_um"])
     assert np.array_equal(port.brightness_temperature(X, np.swapaxes(L[:, :, 0], 0, 1), spectral_dim=1), g["bt_sd"])
+
+
+def _reduce_inputs():
+    rng = np.random.default_rng(70)
+    X = np.linspace(690.0, 1410.0, 28800)
+    Y = np.cumsum(rng.normal(0, 1, (X.size, 3)), axis=0) * 0.01 + np.sin(X / 7.0)[:, None]
+    return X, Y
+
+
+def test_reduce_resolution():
+    g = golden("reduce.npz")
+    X, Y = _reduce_inputs()
+    Xo, Yo = port.reduce_resolution(X, Y, 0.25)
+    assert np.array_equal(Xo, g["Xo"]) and np.array_equal(Yo, g["Yo"])
+    Xo5, Yo5 = port.reduce_resolution(X, Y[:, 1], 0.1, N=2, window="hamming")
+    assert np.array_equal(Xo5, g["Xo5"]) and np.array_equal(Yo5, g["Yo5"])
+    assert np.array_equal(port.smooth(Y[:, 0], 11), g["s11"])
+    assert np.array_equal(port.smooth(Y[:, 2], 10, "flat"), g["s10f"])

@@ -166,8 +166,22 @@ def g_bt():
          bt_vec=bt_vec, Tb=Tb, L_bad=L_bad, Xu=Xu, Lu=Lu, bt_um=bt_um, bt_sd=bt_sd)
 
 
+def g_reduce():
+    np.int = int      # the reference needs the alias numpy >= 1.24 removed (radiative_transfer.py:1329)
+    r = R.rt()
+    rng = np.random.default_rng(70)
+    X = np.linspace(690.0, 1410.0, 28800)
+    Y = np.cumsum(rng.normal(0, 1, (X.size, 3)), axis=0) * 0.01 + np.sin(X / 7.0)[:, None]
+    Xo, Yo = r.reduceResolution(X, Y, 0.25)
+    Xo5, Yo5 = r.reduceResolution(X, Y[:, 1], 0.1, N=2, window="hamming")
+    s11 = r.smooth(Y[:, 0], 11)
+    s10f = r.smooth(Y[:, 2], 10, "flat")
+    save("reduce.npz", source="radiative_transfer.py:1266-1350 smooth, reduceResolution (with np.int = int)", seed=70,
+         Xo=Xo, Yo=Yo, Xo5=Xo5, Yo5=Yo5, s11=s11, s10f=s10f)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt"]
+    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce"]
     for w in which:
         globals()["g_" + w]()
