@@ -29,6 +29,9 @@ struct TudParams {
 };
 
 __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) {
+  __shared__ double s_exp2[64];                       // 2^(j/64), correctly rounded by exp2()
+  if (threadIdx.x < 64) s_exp2[threadIdx.x] = exp2((double)threadIdx.x * 0.015625);
+  __syncthreads();
   const int64_t x = (int64_t)blockIdx.x * TUD_THREADS + threadIdx.x;
   if (x >= P.nx) return;
   const unsigned lanes = __activemask();   // the last block of the grid may be partial
@@ -65,8 +68,8 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
   // ---- downwelling: per angle Ld <- t*Ld + (1-t)*B_j top-down, then the cos-weighted hemispheric mean
   //      (radiative_transfer.py:368-373, 387-389).  The transmittances t = exp(-OD/cos th) are >99 % of the
   //      kernel's work, so exp is evaluated for a block of angles at once with the polynomial constants shared:
-  //      n = rint(x log2 e), r = x - n ln2 (two-piece), degree-13 Taylor polynomial on |r| <= ln2/2 (truncation
-  //      4e-18), scaling by 2^n through the exponent field; 17 FP64 operations per value, 1-2 ulp.
+  //      table-driven range reduction (64 entries), degree-5 polynomial, scaling through the exponent field;
+  //      11 FP64 operations per value, 1-2 ulp.
   double ldsum = 0.0;
   for (int a0 = 0; a0 < P.n_angle; a0 += ANGLE_BLOCK) {
     double acc[ANGLE_BLOCK], sec[ANGLE_BLOCK];
@@ -95,38 +98,33 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
         }
         continue;
       }
+      // general case: exp(x) = 2^m * 2^(j/64) * exp(r),  k = rint(64 x / ln2) = 64 m + j,  r = x - k ln2/64 (two-piece),
+      // |r| <= ln2/128: degree-5 polynomial (truncation 3.5e-17), 2^(j/64) from a shared-memory table.
       double xa[ANGLE_BLOCK], tt[ANGLE_BLOCK], r[ANGLE_BLOCK], pz[ANGLE_BLOCK];
 #pragma unroll
       for (int a = 0; a < ANGLE_BLOCK; ++a) {
         xa[a] = ao * sec[a];
-        tt[a] = fma(xa[a], 1.4426950408889634, 6755399441055744.0);   // 1.5*2^52: integer part lands in the low word
+        tt[a] = fma(xa[a], 92.33248261689366, 6755399441055744.0);     // 64/ln2; 1.5*2^52 puts k in the low word
       }
 #pragma unroll
       for (int a = 0; a < ANGLE_BLOCK; ++a) {
         const double nf = tt[a] - 6755399441055744.0;
-        r[a] = fma(nf, -6.93147180369123816490e-01, xa[a]);
-        r[a] = fma(nf, -1.90821492927058770002e-10, r[a]);
-        pz[a] = fma(1.6059043836821613e-10, r[a], 2.08767569878681e-09);      // 1/13!, 1/12!
+        r[a] = fma(nf, -0.01083042469326756, xa[a]);                     // ln2/64, high part (21 trailing zero bits)
+        r[a] = fma(nf, -2.9815858269852933e-12, r[a]);                   // ln2/64, low part
+        pz[a] = fma(r[a], 8.333333333333333e-03, 4.1666666666666664e-02);
       }
 #define RTX_HORNER(c) _Pragma("unroll") for (int a = 0; a < ANGLE_BLOCK; ++a) pz[a] = fma(pz[a], r[a], c)
-      RTX_HORNER(2.505210838544172e-08);    // 1/11!
-      RTX_HORNER(2.755731922398589e-07);    // 1/10!
-      RTX_HORNER(2.7557319223985893e-06);   // 1/9!
-      RTX_HORNER(2.48015873015873e-05);     // 1/8!
-      RTX_HORNER(1.984126984126984e-04);    // 1/7!
-      RTX_HORNER(1.388888888888889e-03);    // 1/6!
-      RTX_HORNER(8.333333333333333e-03);    // 1/5!
-      RTX_HORNER(4.1666666666666664e-02);   // 1/4!
-      RTX_HORNER(1.6666666666666666e-01);   // 1/3!
+      RTX_HORNER(1.6666666666666666e-01);
       RTX_HORNER(0.5);
-      RTX_HORNER(1.0);
       RTX_HORNER(1.0);
 #undef RTX_HORNER
 #pragma unroll
       for (int a = 0; a < ANGLE_BLOCK; ++a) {
-        const int hi = __double2hiint(pz[a]) + (__double2loint(tt[a]) << 20);
-        double t = __hiloint2double(hi, __double2loint(pz[a]));
-        t = (xa[a] < -708.0) ? 0.0 : t;       // below DBL_MIN anyway
+        const int k = __double2loint(tt[a]);
+        const double tj = s_exp2[k & 63];
+        double t = fma(tj, pz[a] * r[a], tj);                            // 2^(j/64) * (1 + (exp(r)-1))
+        t = __hiloint2double(__double2hiint(t) + ((k >> 6) << 20), __double2loint(t));
+        t = (xa[a] < -708.0) ? 0.0 : t;                                  // below DBL_MIN anyway
         acc[a] = t * acc[a] + (1.0 - t) * B;
       }
     }
