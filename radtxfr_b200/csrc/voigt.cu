@@ -334,24 +334,46 @@ __device__ __forceinline__ int count_lt(const double* a, const TileScale& ts, do
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+#ifndef RTX_NPW
+#define RTX_NPW 2
+#endif
+constexpr int NPW = RTX_NPW;   // producer warps of the warp-specialised variant
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  }
+}
+
 // MODE 0: FP64, full-precision reciprocal; 1: FP64, one Newton step fewer; 2: FP32 evaluation of the asymptote branch
 // (the optional 1e-5 path of the north star): per-slot origins keep omega-nu0' accurate in single precision, partial
 // sums are kept in FP32 for at most one chunk of lines and then folded into the FP64 accumulators; the Weideman
 // cores stay in FP64.
-template <int K, int MODE>
-__global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const VoigtParams P) {
+// WS = warp-specialised variant: NPW extra producer warps run the prologue one chunk ahead (double-buffered
+// records, mbarrier full/empty handshake); the eight consumer warps never meet at a block-wide barrier.
+template <int K, int MODE, bool WS>
+__global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : RTX_MINBLOCKS) voigt_tile_kernel(const VoigtParams P) {
   constexpr bool FAST = (MODE == 1);
   constexpr bool F32 = (MODE == 2);
   constexpr int TILE = K * NT;
+  constexpr int NBUF = WS ? 2 : 1;
+  constexpr int NTH = WS ? NT + 32 * NPW : NT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* s_grid = reinterpret_cast<double*>(smem_raw);                 // TILE
   double* s_acc2 = s_grid + TILE;                                       // TILE
-  WideRec* s_wide = reinterpret_cast<WideRec*>(s_acc2 + TILE);          // LCHUNK
-  SegRec* s_seg = reinterpret_cast<SegRec*>(s_wide + LCHUNK);           // LCHUNK
+  WideRec* s_wide = reinterpret_cast<WideRec*>(s_acc2 + TILE);          // NBUF * LCHUNK
+  SegRec* s_seg = reinterpret_cast<SegRec*>(s_wide + NBUF * LCHUNK);    // NBUF * LCHUNK
   // per block of 32 lines (one warp, one prologue round) and per consumer warp: which of the 32 records that warp
   // must visit -- windows covering its whole slice, windows touching it, segments touching it
-  __shared__ unsigned s_mfull[NBLK][NT / 32], s_mtouch[NBLK][NT / 32], s_mseg[NBLK][NT / 32];
-  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ unsigned s_mfull[NBUF][NBLK][NT / 32], s_mtouch[NBUF][NBLK][NT / 32], s_mseg[NBUF][NBLK][NT / 32];
+  __shared__ __align__(8) unsigned long long s_bar, s_full[2], s_empty[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x % P.n_tiles;
@@ -375,8 +397,13 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
           : "memory");
     }
   }
-  for (int i = tma_pts + tid; i < TILE; i += NT) s_grid[i] = (i < npts) ? P.grid[p0 + i] : 1.7976931348623157e308;
-  for (int i = tid; i < TILE; i += NT) s_acc2[i] = 0.0;
+  if (WS && tid == 0) {
+    mbar_init(&s_full[0], NPW); mbar_init(&s_full[1], NPW);
+    mbar_init(&s_empty[0], NT / 32); mbar_init(&s_empty[1], NT / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tma_pts + tid; i < TILE; i += NTH) s_grid[i] = (i < npts) ? P.grid[p0 + i] : 1.7976931348623157e308;
+  for (int i = tid; i < TILE; i += NTH) s_acc2[i] = 0.0;
   __syncthreads();   // barrier init visible to all waiters; padding + acc2 written
   if (tma_pts > 0) {
     const uint32_t bar = smem_u32(&s_bar);
@@ -395,7 +422,7 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
   float w32[K], w32l[K], a32[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    w[j] = s_grid[warp * (32 * K) + j * 32 + lane];
+    w[j] = s_grid[(warp & (NT / 32 - 1)) * (32 * K) + j * 32 + lane];
     const double off = w[j] - s_grid[0];                          // offset from the tile's first point, as hi + lo
     w32[j] = (float)off;
     w32l[j] = (float)(off - (double)w32[j]);
@@ -418,11 +445,11 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
   // the tile's whole candidate range and the eight warps' slices receive equal shares of every chunk.
   const int ncand = last - first;
   const int nchunks = (ncand + LCHUNK - 1) / LCHUNK;
-  for (int c = 0; c < nchunks; ++c) {
-    // ---- prologue: one lane, one line per round; survivors compacted per warp (ballot, no atomics) -------
-#pragma unroll 1
-    for (int r = 0; r < ROUNDS; ++r) {
-      const int k = (r * (NT / 32) + warp) * 32 + lane;
+  // one block of 32 candidate lines -> records + visit masks in buffer `buf` (executed by one full warp)
+  auto produce = [&](int c, int blk, int buf) {
+      WideRec* wide_b = s_wide + buf * LCHUNK;
+      SegRec* seg_b = s_seg + buf * LCHUNK;
+      const int k = blk * 32 + lane;
       const int li = first + c + k * nchunks;
       bool is_wide = false, has_seg = false;
       WideRec wr;
@@ -506,7 +533,6 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
         }
       }
       // records live at fixed slots; the per-consumer-warp ballots below are the (deterministic) compaction
-      const int blk = r * (NT / 32) + warp;
       unsigned wm = 0, sm = 0;
       if (is_wide) {
         if (F32) {
@@ -516,14 +542,14 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
           w3.af = (float)wr.a; w3.hf = (float)h_keep; w3.mf = (float)wr.m; w3.cf = (float)wr.c;
           w3.pad0 = w3.pad1 = 0.f;
           w3.lo = wr.lo; w3.hi = wr.hi; w3.core_lo = wr.clo; w3.core_hi = wr.chi;
-          *reinterpret_cast<WideRec32*>(&s_wide[k]) = w3;
+          *reinterpret_cast<WideRec32*>(&wide_b[k]) = w3;
         } else {
-          s_wide[k] = wr;
+          wide_b[k] = wr;
         }
         wm = slice_masks(wr.lo, wr.hi, wr.clo, wr.chi, 32 * K);
       }
       if (has_seg) {
-        s_seg[k] = sr;
+        seg_b[k] = sr;
 #pragma unroll
         for (int q = 0; q < NT / 32; ++q) sm |= ((sr.e > q * 32 * K) && (sr.s < (q + 1) * 32 * K) ? 1u : 0u) << q;
       }
@@ -532,11 +558,11 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
         const unsigned bt = __ballot_sync(0xffffffffu, (wm >> q) & 1u);
         const unsigned bf = __ballot_sync(0xffffffffu, (wm >> (8 + q)) & 1u);
         const unsigned bs = __ballot_sync(0xffffffffu, (sm >> q) & 1u);
-        if (lane == q) { s_mtouch[blk][q] = bt & ~bf; s_mfull[blk][q] = bf; s_mseg[blk][q] = bs; }
+        if (lane == q) { s_mtouch[buf][blk][q] = bt & ~bf; s_mfull[buf][blk][q] = bf; s_mseg[buf][blk][q] = bs; }
       }
-    }
-    __syncthreads();
-
+  };
+  // passes 1 and 2 of one consumer warp over the records of buffer `buf`
+  auto consume = [&](int buf) {
     // ---- pass 1: wide lines, register accumulators ------------------------------------------------
 #define RTX_EVAL(j)                                                                                   \
   do {                                                                                                \
@@ -567,8 +593,8 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
     // path; only the slices holding a window end (or a Weideman core) pay for per-point predicates.
 #pragma unroll 1
     for (int blk = 0; blk < NBLK; ++blk) {
-      const WideRec* __restrict__ recs = s_wide + blk * 32;
-      unsigned m = s_mfull[blk][warp];
+      const WideRec* __restrict__ recs = s_wide + buf * LCHUNK + blk * 32;
+      unsigned m = s_mfull[buf][blk][warp];
       while (m) {
         const WideRec& rr = recs[__ffs(m) - 1];
         m &= m - 1;
@@ -577,7 +603,7 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
 #pragma unroll
         for (int j = 0; j < K; ++j) RTX_EVAL(j);
       }
-      m = s_mtouch[blk][warp];
+      m = s_mtouch[buf][blk][warp];
       while (m) {
         const WideRec& rr = recs[__ffs(m) - 1];
         m &= m - 1;
@@ -618,8 +644,8 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
     // ---- pass 2: segments, lane per point, warp-owned slice of the tile -----------------------------
 #pragma unroll 1
     for (int blk = 0; blk < NBLK; ++blk) {
-      const SegRec* __restrict__ recs = s_seg + blk * 32;
-      unsigned m = s_mseg[blk][warp];
+      const SegRec* __restrict__ recs = s_seg + buf * LCHUNK + blk * 32;
+      unsigned m = s_mseg[buf][blk][warp];
       while (m) {
         const SegRec r = recs[__ffs(m) - 1];
         m &= m - 1;
@@ -635,10 +661,40 @@ __global__ void __launch_bounds__(NT, RTX_MINBLOCKS) voigt_tile_kernel(const Voi
         __syncwarp();
       }
     }
-    __syncthreads();
+  };
+
+  if (!WS) {
+    for (int c = 0; c < nchunks; ++c) {
+#pragma unroll 1
+      for (int r = 0; r < ROUNDS; ++r) produce(c, r * (NT / 32) + warp, 0);
+      __syncthreads();
+      consume(0);
+      __syncthreads();
+    }
+  } else if (warp >= NT / 32) {
+    // ---- producer warps: derive line states one chunk ahead of the consumers (mbarrier full/empty handshake) ----
+    const int pw = warp - NT / 32;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      if (c >= 2) mbar_wait(&s_empty[buf], ((c >> 1) - 1) & 1);
+#pragma unroll 1
+      for (int blk = pw; blk < NBLK; blk += NPW) produce(c, blk, buf);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full[buf]);
+    }
+    return;
+  } else {
+    // ---- consumer warps: each runs at its own pace, at most one chunk apart from the slowest ----
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(&s_full[buf], (c >> 1) & 1);
+      consume(buf);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[buf]);
+    }
   }
 
-  double* out = P.out + (int64_t)s * P.nx + p0;
+  double* out = P.out + (int64_t)s * P.nx + p0;   // only consumer warps get here in the WS variant
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     const int i = warp * (32 * K) + j * 32 + lane;
@@ -692,18 +748,18 @@ __global__ void count_kernel(const VoigtParams P, unsigned long long* __restrict
   }
 }
 
-template <int K>
+template <int K, bool WS>
 size_t tile_smem_bytes() {
-  return (size_t)K * NT * 8 * 2 + (size_t)LCHUNK * (sizeof(WideRec) + sizeof(SegRec));
+  return (size_t)K * NT * 8 * 2 + (size_t)(WS ? 2 : 1) * LCHUNK * (sizeof(WideRec) + sizeof(SegRec));
 }
 
-template <int K, int MODE>
+template <int K, int MODE, bool WS>
 int launch_tile(const VoigtParams& P, cudaStream_t st) {
-  const size_t smem = tile_smem_bytes<K>();
-  RTX_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = tile_smem_bytes<K, WS>();
+  RTX_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<K, MODE, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t blocks = (int64_t)P.n_tiles * P.n_states;
   if (blocks > 2147483647LL) { rtx_set_error("rtx_voigt_sum: too many (tile, state) pairs for one launch"); return RTX_E_INVALID; }
-  voigt_tile_kernel<K, MODE><<<(unsigned)blocks, NT, smem, st>>>(P);
+  voigt_tile_kernel<K, MODE, WS><<<(unsigned)blocks, WS ? NT + 32 * NPW : NT, smem, st>>>(P);
   RTX_CUDA(cudaGetLastError());
   return RTX_OK;
 }
@@ -809,7 +865,10 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
   RTX_CUDA(cudaGetLastError());
   h->launches++;
   const int mode = (flags & RTX_VOIGT_FP32) ? 2 : ((flags & RTX_VOIGT_FAST_RCP) ? 1 : 0);
-#define RTX_LAUNCH(KK) (mode == 2 ? launch_tile<KK, 2>(P, st) : mode == 1 ? launch_tile<KK, 1>(P, st) : launch_tile<KK, 0>(P, st))
+  const bool ws = (flags & RTX_VOIGT_WARPSPEC) != 0;
+#define RTX_LAUNCH(KK)                                                                                        \
+  (ws ? (mode == 2 ? launch_tile<KK, 2, true>(P, st) : mode == 1 ? launch_tile<KK, 1, true>(P, st) : launch_tile<KK, 0, true>(P, st)) \
+      : (mode == 2 ? launch_tile<KK, 2, false>(P, st) : mode == 1 ? launch_tile<KK, 1, false>(P, st) : launch_tile<KK, 0, false>(P, st)))
   switch (K) {
     case 8: rc = RTX_LAUNCH(8); break;
     case 4: rc = RTX_LAUNCH(4); break;

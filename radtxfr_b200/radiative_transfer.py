@@ -121,6 +121,7 @@ def _voigt_settings(opts):
     x_self = float(sum(val for k, val in dil.items() if k.lower() == "self"))
     flags = {"fp64": 0, "fp64_fast": 1, "fp32": 2}[v.get("precision", "fp64")]
     flags |= int(v.get("tile_k", 0)) << 8          # 0 = automatic tile size
+    flags |= 4 if v.get("ws", False) else 0
     return dict(x_air=x_air, x_self=x_self, wing_abs=float(v.get("OmegaWing", 0.0)),
                 wing_hw=float(v.get("OmegaWingHW", 50.0)), s_threshold=float(v.get("IntensityThreshold", 0.0)),
                 flags=flags)

@@ -66,10 +66,10 @@ def test_xsect_golden_cases(mods):
 
 
 @pytest.mark.parametrize("K", [1, 2, 4, 8])
-@pytest.mark.parametrize("fast", [0, 1])
+@pytest.mark.parametrize("fast", [0, 1, 4, 5])
 def test_voigt_all_tile_sizes(mods, K, fast):
-    """Every tile-size instantiation of the kernel, both reciprocal variants, on a multi-state problem that
-    mixes wide (1 atm) and narrow (top of atmosphere) lines."""
+    """Every tile-size instantiation of the kernel, both reciprocal variants, plain and warp-specialised (flag 4),
+    on a multi-state problem that mixes wide (1 atm) and narrow (top of atmosphere) lines."""
     port, syn, engine = mods["port"], mods["syn"], mods["engine"]
     cols = syn.synthetic_lines(50, 400, 985.0, 1015.0, 1)
     db = engine.LineDB(cols)

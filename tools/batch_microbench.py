@@ -9,13 +9,13 @@ atm = syn.standard_atmosphere(); tabs = syn.config2_tables()
 opts = dict(rt.options); rt.set_line_database(tabs, opts=opts); db = opts["LINE_DB"]
 Ts, MF = syn.perturbed_atmospheres(2, n_atm)
 kw = dict(Zs=atm["Zs"], Ps=atm["Ps"], PLs=atm["PLs"], MFs_ID=atm["MFs_ID"], DVOUT=0.01, N_angle=30)
-for k in (8, 4, 2):
-    o = dict(opts); o["voigt"] = {"tile_k": k}
+for k in (8, 8 + 1024):
+    o = dict(opts); o["voigt"] = {"tile_k": k & 15, "ws": k > 15}
     rt.compute_TUD_batch(700.0, 1500.0, Ts[:8], MF[:8], opts=dict(o), **kw)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     rt.compute_TUD_batch(700.0, 1500.0, Ts[:32], MF[:32], opts=dict(o), **kw)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    print("K=%d: %.1f spectra/s" % (k, 32 / dt), flush=True)
+    print("K=%d ws=%d: %.1f spectra/s" % (k & 15, k > 15, 32 / dt), flush=True)
 for ils in (None, "triangle"):
     rt.compute_TUD_batch(700.0, 1500.0, Ts[:8], MF[:8], opts=dict(opts), ils=ils, **kw)
     torch.cuda.synchronize(); t0 = time.perf_counter()

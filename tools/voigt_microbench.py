@@ -42,7 +42,7 @@ def main():
         del a0, a1
     cases = []
     for K in (8,):
-        for fast in (0, 1, 2):
+        for fast in (0, 1, 2, 4):
             cases.append(("cfg2 K=%d fast=%d" % (K, fast), dict(flags=fast | (K << 8)), T, pd, wd))
     # all-wide: every line +-25 cm^-1 -> almost every visit takes the test-free path
     cases.append(("wide25 K=8 fast=0", dict(flags=8 << 8, wing_abs=25.0), T[:8], pd[:8], wd[:8]))
@@ -54,6 +54,7 @@ def main():
                      ("layers 50-65", slice(50, 66))):
         for K in (8,):
             cases.append((name + " K=%d" % K, dict(flags=K << 8), T[sl], pd[sl], wd[sl].contiguous()))
+            cases.append((name + " K=%d ws" % K, dict(flags=4 | (K << 8)), T[sl], pd[sl], wd[sl].contiguous()))
     for name, kw, Tt, pp, ww in cases:
         if only is not None and only not in name.replace(" ", "_"):
             continue
