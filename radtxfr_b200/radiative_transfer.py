@@ -66,15 +66,18 @@ _workspace = {}
 
 
 def _device_axis(Xmin, Xmax, DVOUT, device):
-    """(host axis, device copy): the device copy of a spectral axis is kept across calls (LRU of 4)."""
-    X_ = make_spectral_axis(Xmin, Xmax, DVOUT)
-    key = (float(Xmin), float(Xmax), int(X_.size), str(device))
+    """Device copy of the spectral axis, kept across calls (LRU of 4).  Returns (host axis or None, device axis):
+    on a cache hit the host axis is NOT rebuilt here -- the caller builds it while the GPU is busy."""
+    nX = int(np.ceil((Xmax - Xmin) / DVOUT))
+    key = (float(Xmin), float(Xmax), nX, str(device))
     hit = _axis_cache.get(key)
-    if hit is None:
-        if len(_axis_cache) >= 4:
-            _axis_cache.pop(next(iter(_axis_cache)))
-        hit = _axis_cache[key] = engine.to_device(X_, device)
-    return X_, hit
+    if hit is not None:
+        return None, hit
+    X_ = make_spectral_axis(Xmin, Xmax, DVOUT)
+    if len(_axis_cache) >= 4:
+        _axis_cache.pop(next(iter(_axis_cache)))
+    _axis_cache[key] = engine.to_device(X_, device)
+    return X_, _axis_cache[key]
 
 
 def _od_workspace(device, n_states, nx):
@@ -89,23 +92,46 @@ def _od_workspace(device, n_states, nx):
     return buf[:need].view(n_states, nx)
 
 
-def _to_host(*tensors):
-    """Device tensors -> fresh numpy arrays through one persistent pinned staging buffer (one sync)."""
+_copy_pool = None
+
+
+def _host_outputs(shapes):
+    """Fresh float64 numpy arrays whose pages are already touched (call this while the GPU is busy: first-touch
+    page faults of 20 MB of results would otherwise add ~1.5 ms after the kernels)."""
+    outs = [np.empty(sh, dtype=np.float64) for sh in shapes]
+    for o in outs:
+        o.fill(0.0)
+    return outs
+
+
+def _to_host(*tensors, outs=None):
+    """Device tensors -> fresh numpy arrays through one persistent pinned staging buffer: async D2H, one stream
+    sync, then the copies out of the staging buffer run on a small thread pool (numpy releases the GIL)."""
+    global _copy_pool
     torch = engine._torch()
     total = sum(t.numel() for t in tensors)
-    key = "pinned"
-    stage = _workspace.get(key)
+    stage = _workspace.get("pinned")
     if stage is None or stage.numel() < total:
-        stage = _workspace[key] = torch.empty(max(total, 1), dtype=torch.float64, pin_memory=True)
+        stage = _workspace["pinned"] = torch.empty(max(total, 1), dtype=torch.float64, pin_memory=True)
     off = 0
     views = []
     for t in tensors:
         v = stage[off:off + t.numel()]
         v.copy_(t.reshape(-1), non_blocking=True)
-        views.append((v, tuple(t.shape)))
+        views.append(v.numpy().reshape(tuple(t.shape)))
         off += t.numel()
+    if outs is None:
+        outs = [np.empty(v.shape, dtype=np.float64) for v in views]
     torch.cuda.current_stream(tensors[0].device).synchronize()
-    return [v.numpy().reshape(shape).copy() for v, shape in views]
+    if total < (1 << 18):
+        for o, v in zip(outs, views):
+            np.copyto(o, v)
+    else:
+        if _copy_pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _copy_pool = ThreadPoolExecutor(max_workers=4)
+        list(_copy_pool.map(lambda ov: np.copyto(ov[0], ov[1]), zip(outs, views)))
+    return outs
 
 
 def make_spectral_axis(Xmin, Xmax, DVOUT):
@@ -186,16 +212,24 @@ def compute_TUD(Xmin, Xmax, opts=options, **kwargs):
     returnOD = opts["returnOD"]
 
     X_, grid = _device_axis(Xmin, Xmax, opts["DVOUT"], db.device)
+    nX = grid.numel()
     db.check_temperatures(T)
     p, w = layer_weights(db, T, P, PL, MF, ID)
-    od = db.voigt_sum(T, p, w, grid, out=_od_workspace(db.device, T.size, X_.size),
+    # every host->device copy happens before the first launch (pageable copies synchronise the stream), so the
+    # host is free while the kernels run
+    Td, pd, wd = (engine.to_device(a, db.device) for a in (T, p, w))
+    od = db.voigt_sum(Td, pd, wd, grid, out=_od_workspace(db.device, T.size, nX),
                       **_voigt_settings(opts))                                  # [nL, nX], layer-major
-    tau, lu, ld = engine.tud(od, T[None, :], grid, Z, Z_s, mu_s, nA, returnOD)
+    tau, lu, ld = engine.tud(od, Td[None, :], grid, Z, Z_s, mu_s, nA, returnOD)
+    # the kernels are in flight: build the host axis and pre-touch the result arrays meanwhile
+    if X_ is None:
+        X_ = make_spectral_axis(Xmin, Xmax, opts["DVOUT"])
+    outs = _host_outputs([(nX, Z_s.size, mu_s.size), (nX, Z_s.size, mu_s.size), (nX,)])
     if opts["save"]:
         B = engine.planck(grid, T).cpu().numpy()
         np.savez("ComputeTUD.npz", OD=od.cpu().numpy().T, B=B, tau=tau[0].cpu().numpy(), Lu=lu[0].cpu().numpy(),
                  X=X_, angles=np.linspace(0, np.pi / 2.0, nA, endpoint=False), Z_s=Z_s, mu_s=mu_s)
-    tau_, Lu_, Ld_ = _to_host(tau[0], lu[0], ld[0])
+    tau_, Lu_, Ld_ = _to_host(tau[0], lu[0], ld[0], outs=outs)
     if (len(Z_s) == 1) and (len(mu_s) == 1):
         tau_, Lu_ = tau_[:, 0, 0], Lu_[:, 0, 0]
     if (len(Z_s) == 1) and not (len(mu_s) == 1):
