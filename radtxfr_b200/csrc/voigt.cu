@@ -641,23 +641,81 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : RTX_MINBLOCK
 #pragma unroll
       for (int j = 0; j < K; ++j) { acc[j] += (double)a32[j]; a32[j] = 0.f; }
     }
-    // ---- pass 2: segments, lane per point, warp-owned slice of the tile -----------------------------
+    // ---- pass 2: segments (Weideman cores, narrow windows) inside the warp's slice -------------------------
+    // When the segments of a 32-record block are short (coarse grids: a Weideman core is ~5 points), the
+    // (segment, point) pairs are flattened and dealt to the lanes, so a warp still evaluates 32 points per step.  Lanes that
+    // hit the same grid point in one step are found with match.any and summed in lane order by the lowest lane
+    // before the shared-memory update: no atomics, summation order fixed.
 #pragma unroll 1
     for (int blk = 0; blk < NBLK; ++blk) {
+      const unsigned msk = s_mseg[buf][blk][warp];
+      if (!msk) continue;
       const SegRec* __restrict__ recs = s_seg + buf * LCHUNK + blk * 32;
-      unsigned m = s_mseg[buf][blk][warp];
-      while (m) {
-        const SegRec r = recs[__ffs(m) - 1];
-        m &= m - 1;
-        const int ss = max(r.s, own_lo), ee = min(r.e, own_hi);
-        for (int i = ss + lane; i < ee; i += 32) {
-          const double om = s_grid[i];
-          const double x = __dmul_rn(om - r.sg0, r.cte);
-          double v;
-          if (__dadd_rn(fabs(x), r.y) < 15.0) v = r.cw * weideman_re(x, r.y);
-          else v = cheap_term<false>(om, r.sg0, r.a, r.ah, r.m, r.c, 0.0);
-          s_acc2[i] += v;
+      int ss = 0, n = 0;
+      if ((msk >> lane) & 1u) {
+        ss = max(recs[lane].s, own_lo);
+        n = min(recs[lane].e, own_hi) - ss;
+      }
+      int incl = n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      const int excl = incl - n;
+      if (total >= 20 * __popc(msk)) {
+        // long segments (fine grids): one segment at a time already fills the lanes
+        unsigned m2 = msk;
+        while (m2) {
+          const SegRec r = recs[__ffs(m2) - 1];
+          m2 &= m2 - 1;
+          const int s0 = max(r.s, own_lo), e0 = min(r.e, own_hi);
+          for (int i = s0 + lane; i < e0; i += 32) {
+            const double om = s_grid[i];
+            const double x = __dmul_rn(om - r.sg0, r.cte);
+            double v;
+            if (__dadd_rn(fabs(x), r.y) < 15.0) v = r.cw * weideman_re(x, r.y);
+            else v = cheap_term<false>(om, r.sg0, r.a, r.ah, r.m, r.c, 0.0);
+            s_acc2[i] += v;
+          }
+          __syncwarp();
         }
+        continue;
+      }
+#pragma unroll 1
+      for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        const bool valid = t < total;
+        int r = 0;                                   // number of records whose inclusive count is <= t
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+          const int v = __shfl_sync(0xffffffffu, incl, r + sft - 1);
+          if (v <= t) r += sft;
+        }
+        r = min(r, 31);
+        const int i = __shfl_sync(0xffffffffu, ss, r) + (t - __shfl_sync(0xffffffffu, excl, r));
+        double v = 0.0;
+        if (valid) {
+          const SegRec& rec = recs[r];
+          const double om = s_grid[i];
+          const double sg0 = rec.sg0, y = rec.y;
+          const double x = __dmul_rn(om - sg0, rec.cte);
+          if (__dadd_rn(fabs(x), y) < 15.0) v = rec.cw * weideman_re(x, y);
+          else v = cheap_term<false>(om, sg0, rec.a, rec.ah, rec.m, rec.c, 0.0);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? i : TILE + lane);
+        const int gmax = __reduce_max_sync(0xffffffffu, __popc(peers));
+        double sum = 0.0;
+        unsigned pm = peers;
+#pragma unroll 1
+        for (int k = 0; k < gmax; ++k) {
+          const int src = pm ? __ffs(pm) - 1 : lane;
+          const double val = __shfl_sync(0xffffffffu, v, src);
+          if (pm) sum += val;
+          pm &= pm - 1;
+        }
+        if (valid && lane == __ffs(peers) - 1) s_acc2[i] += sum;
         __syncwarp();
       }
     }
