@@ -318,6 +318,19 @@ def test_reduce_resolution_golden(mods):
     assert rt.smooth(Y[:, 0], 2) is Y[:, 0] or np.array_equal(rt.smooth(Y[:, 0], 2), Y[:, 0])
 
 
+def test_ils_many_spectra(mods):
+    """The coalesced many-spectra ILS kernel (ns >= 16), both line shapes, ragged ns, against the oracle."""
+    rt, ilsg, port = mods["rt"], mods["ilsg"], mods["port"]
+    rng = np.random.default_rng(8)
+    X = np.linspace(700.0, 1400.0, 3501)
+    for ns in (16, 45):
+        Y = rng.uniform(0, 10, (X.size, ns))
+        Xo, t = rt.ILS_MAKO(X, Y)
+        assert_parity(t, port.ils_mako_triangle(X, Y)[1], RTOL, FLOOR, "tri ns=%d" % ns)
+        Xg, g = ilsg.ILS_MAKO(X, Y)
+        assert_parity(g, port.ils_mako_gauss(X, Y)[1], RTOL, FLOOR, "gauss ns=%d" % ns)
+
+
 def test_hsi_pixels(mods):
     engine, port, syn = mods["engine"], mods["port"], mods["syn"]
     rng = np.random.default_rng(7)
