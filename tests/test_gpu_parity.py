@@ -161,6 +161,32 @@ def test_voigt_edge_cases(mods):
     assert xt.is_cuda and np.array_equal(xt.cpu().numpy(), xs)
 
 
+def test_voigt_window_ties_and_range_route(mods):
+    """bisect_right semantics on exact ties (grid point == nu-W is outside, == nu+W is inside, misc/hapi.py:11133-11134)
+    and the OmegaRange/OmegaStep route with the default Environment."""
+    port, hapi = mods["port"], mods["hapi"]
+    cols = {"molec_id": np.array([1, 1, 1]), "local_iso_id": np.array([1, 1, 2]), "nu": np.array([1000.0, 1002.5, 1010.0]),
+            "sw": np.array([1e-21, 3e-22, 2e-21]), "elower": np.array([100.0, 500.0, 0.0]),
+            "gamma_air": np.array([0.07, 0.05, 0.09]), "gamma_self": np.array([0.3, 0.2, 0.4]),
+            "n_air": np.array([0.7, 0.6, 0.5]), "delta_air": np.array([0.0, -0.003, 0.002])}
+    hapi.storeTable("ties", cols)
+    grid = np.arange(9900, 10200) / 10.0                       # 990.0 .. 1019.9, exact tenths where representable
+    assert 997.5 in grid and 1002.5 in grid
+    _, xs = hapi.absorptionCoefficient_Voigt(SourceTables="ties", OmegaGrid=grid, OmegaWing=2.5, OmegaWingHW=0.0)
+    _, ref = port.absorption_coefficient_voigt(cols, OmegaGrid=grid, OmegaWing=2.5, OmegaWingHW=0.0)
+    assert_parity(xs, ref, RTOL, FLOOR, "ties")
+    assert np.array_equal(xs == 0.0, ref == 0.0)               # identical window membership, point by point
+    i_lo, i_hi = int(np.where(grid == 997.5)[0][0]), int(np.where(grid == 1002.5)[0][0])
+    assert ref[i_lo] == 0.0 and ref[i_hi] > 0.0
+    om, xs2 = hapi.absorptionCoefficient_Voigt(SourceTables="ties", OmegaRange=(995.0, 1015.0), OmegaStep=0.01)
+    assert om.size == 2001 and om[0] == 995.0
+    _, ref2 = port.absorption_coefficient_voigt(cols, OmegaGrid=om)
+    assert_parity(xs2, ref2, RTOL, FLOOR, "range route")
+    _, xs3 = hapi.absorptionCoefficient_Voigt(SourceTables="ties", OmegaGrid=om, Components=[(1, 2)])
+    _, ref3 = port.absorption_coefficient_voigt(cols, OmegaGrid=om, Components=[(1, 2)])
+    assert_parity(xs3, ref3, RTOL, FLOOR, "components filter")
+
+
 def test_voigt_two_tables_and_deterministic(mods):
     port, syn, hapi = mods["port"], mods["syn"], mods["hapi"]
     a = syn.synthetic_lines(53, 150, 900.0, 1000.0, 1)
