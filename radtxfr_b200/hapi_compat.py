@@ -188,3 +188,17 @@ def absorptionCoefficient_Voigt(Components=None, SourceTables=None, partitionFun
     if as_tensor:
         return Omegas, xs
     return Omegas, xs.cpu().numpy()
+
+
+def absorptionCoefficient_SDVoigt(*args, **kwargs):
+    """Speed-dependent Voigt driver of hapi (misc/hapi.py:10657-10905) for tables WITHOUT speed-dependence columns
+    -- the situation of the reference's only hapi call site (misc/RT_gen_AbsXS_files.py:90: plain HITRAN tables).
+    With SD_<diluent> absent hapi sets Gamma2 = Shift2 = 0 (:10883-10890) and pcqsdhc takes its PART1 branch, i.e.
+    the Voigt profile centred on nu + Shift0 (the centre is formed as (nu - omega) + Shift0 instead of
+    (nu + Shift0) - omega: a last-bit difference).  Tables that do carry SD_* columns raise NotImplementedError."""
+    st = kwargs.get("SourceTables", args[1] if len(args) > 1 else None)
+    names = st if type(st) in (list, tuple) else [st]
+    for n in names:
+        if n in LOCAL_TABLE_CACHE and any(k.lower().startswith("sd_") for k in LOCAL_TABLE_CACHE[n]["data"]):
+            raise NotImplementedError("speed-dependent broadening (SD_* columns) is not on the accelerated path")
+    return absorptionCoefficient_Voigt(*args, **kwargs)

@@ -357,6 +357,34 @@ def test_ils_many_spectra(mods):
         assert_parity(g, port.ils_mako_gauss(X, Y)[1], RTOL, FLOOR, "gauss ns=%d" % ns)
 
 
+def test_sdvoigt_lut_and_afit_xs(mods, tmp_path):
+    """The reference's one hapi call site (misc/RT_gen_AbsXS_files.py:90): SDVoigt on plain HITRAN-style tables with a
+    350-halfwidth wing, batched over (T, p), and the AFIT_XS file it writes."""
+    hapi, syn = mods["hapi"], mods["syn"]
+    from radtxfr_b200 import formats
+    g = golden("lut.npz")
+    cols = syn.synthetic_lines(80, 250, 1950.0, 2400.0, 2, (1, 2, 3), (0.8, 0.1, 0.1))
+    hapi.storeTable("lut", cols)
+    grid = np.linspace(2000.0, 2350.0, 7001)
+    states = [(296.0, 1.0), (250.0, 0.1), (330.0, 0.5)]
+    for k, (T, p) in enumerate(states):
+        _, xs = hapi.absorptionCoefficient_SDVoigt(SourceTables="lut", HITRAN_units=True, Environment={"T": T, "p": p},
+                                                   OmegaGrid=grid, IntensityThreshold=0, WavenumberWingHW=350.0)
+        assert_parity(xs, g["xs%d" % k], RTOL, FLOOR, "SDVoigt state %d" % k)
+    lut = formats.cross_section_lut("lut", [296.0, 250.0, 330.0], [1.0, 0.1, 0.5], grid, WavenumberWingHW=350.0)
+    assert lut.shape == (3, 3, grid.size)
+    assert_parity(lut[0, 0], g["xs0"], RTOL, FLOOR, "lut[0,0]")
+    assert_parity(lut[1, 1], g["xs1"], RTOL, FLOOR, "lut[1,1]")
+    assert_parity(lut[2, 2], g["xs2"], RTOL, FLOOR, "lut[2,2]")
+    f = formats.AFIT_XS_write(grid, g["xs0"], 296.0, 101325 * 1.0, 2, "HITRAN2016-synthetic", File=str(tmp_path / "x.bin"))
+    assert np.array_equal(np.frombuffer(open(f, "rb").read(), dtype=np.uint8), g["afit_bytes"])
+    X, Y, T, P, ID, name = formats.AFIT_XS_read(f)
+    assert np.array_equal(Y, g["xs0"]) and (T, P, ID, name) == (296.0, 101325.0, 2, "HITRAN2016-synthetic")
+    hapi.storeTable("sd", dict(cols, SD_air=np.full(250, 0.1)))
+    with pytest.raises(NotImplementedError):
+        hapi.absorptionCoefficient_SDVoigt(SourceTables="sd", OmegaGrid=grid)
+
+
 def test_hsi_pixels(mods):
     engine, port, syn = mods["engine"], mods["port"], mods["syn"]
     rng = np.random.default_rng(7)

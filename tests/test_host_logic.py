@@ -99,3 +99,20 @@ def test_layer_weights_match_oracle_wiring():
     for p, T in ((1.0, 296.0), (0.3, 250.0)):
         assert hapi_compat.volumeConcentration(p, T) == port.volume_concentration(p, T)
     assert hapi_compat.abundance(1, 1) == 0.997317 and hapi_compat.molecularMass(2, 1) == 43.98983
+
+
+def test_afit_xs_bytes_match_reference_writer(tmp_path):
+    """AFIT_XS writer against bytes produced by the reference's own AFIT_XS_write (tests/golden/lut.npz)."""
+    from conftest import golden
+    from radtxfr_b200 import formats
+    g = golden("lut.npz")
+    grid = np.linspace(2000.0, 2350.0, 7001)
+    f = formats.AFIT_XS_write(grid, g["xs0"], 296.0, 101325 * 1.0, 2, "HITRAN2016-synthetic", File=str(tmp_path / "x.bin"))
+    assert np.array_equal(np.frombuffer(open(f, "rb").read(), dtype=np.uint8), g["afit_bytes"])
+    assert formats.AFIT_XS_write(grid[:3], g["xs0"][:3], 296.4, 101325.0, 2, "db", File=str(tmp_path / "y.bin")).endswith("y.bin")
+    import os
+    cwd = os.getcwd(); os.chdir(tmp_path)
+    try:
+        assert formats.AFIT_XS_write(grid[:3], g["xs0"][:3], 296.4, 101325.0, 2, "db") == "XS-02-0296K-101325Pa.bin"
+    finally:
+        os.chdir(cwd)

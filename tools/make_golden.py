@@ -180,8 +180,35 @@ def g_reduce():
          Xo=Xo, Yo=Yo, Xo5=Xo5, Yo5=Yo5, s11=s11, s10f=s10f)
 
 
+def g_lut():
+    """SDVoigt on a table without SD columns (the reference's own call convention, misc/RT_gen_AbsXS_files.py:90)
+    and the AFIT_XS writer, whose source is lifted out of the script with ast (the script itself fetches HITRAN
+    from the network at import)."""
+    import ast
+    import tempfile
+    h = R.hapi()
+    cols = syn.synthetic_lines(80, 250, 1950.0, 2400.0, 2, (1, 2, 3), (0.8, 0.1, 0.1))
+    R.inject_table("__lut__", cols)
+    grid = np.linspace(2000.0, 2350.0, 7001)
+    out = {}
+    import contextlib, io
+    for k, (T, p) in enumerate([(296.0, 1.0), (250.0, 0.1), (330.0, 0.5)]):
+        with contextlib.redirect_stdout(io.StringIO()):
+            _, xs = h.absorptionCoefficient_SDVoigt(SourceTables="__lut__", HITRAN_units=True, Environment={"T": T, "p": p},
+                                                    OmegaGrid=grid, IntensityThreshold=0, WavenumberWingHW=350.0)
+        out["xs%d" % k] = xs
+    src = open(os.path.join(R.REF_ROOT, "misc", "RT_gen_AbsXS_files.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "AFIT_XS_write"][0]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "AFIT_XS_write", "exec"), ns)
+    with tempfile.TemporaryDirectory() as d:
+        f = ns["AFIT_XS_write"](grid, out["xs0"], 296.0, 101325 * 1.0, 2, "HITRAN2016-synthetic", File=os.path.join(d, "x.bin"))
+        out["afit_bytes"] = np.frombuffer(open(f, "rb").read(), dtype=np.uint8)
+    save("lut.npz", source="misc/hapi.py:10657 absorptionCoefficient_SDVoigt; misc/RT_gen_AbsXS_files.py:45-83", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce"]
+    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut"]
     for w in which:
         globals()["g_" + w]()
