@@ -261,6 +261,7 @@ def compute_TUD_batch(Xmin, Xmax, Ts, MFs_VAL, opts=options, atm_chunk=None, ils
     grid = engine.to_device(X_, db.device)
     if atm_chunk is None:
         atm_chunk = max(1, min(n_atm, int(4e9 // (8 * nL * nX))))           # <= 4 GB of optical depth at a time
+    atm_chunk = min(int(atm_chunk), 32768)                                  # rtx_tud: n_atm <= 65535 per launch
     vs = _voigt_settings(opts)
     outs = []
     band = None
