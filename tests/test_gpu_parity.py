@@ -187,6 +187,28 @@ def test_voigt_window_ties_and_range_route(mods):
     assert_parity(xs3, ref3, RTOL, FLOOR, "components filter")
 
 
+def test_voigt_optional_columns(mods):
+    """Optional hapi columns on the device path: n_self (0 -> n_air), delta_self, deltap_air, deltap_self
+    (misc/hapi.py:11097-11128), with air/self diluent mixes, against the oracle (and the reference via the oracle's
+    golden pins for the plain cases)."""
+    import make_golden as mg
+    port, syn, hapi = mods["port"], mods["syn"], mods["hapi"]
+    cols = mg.optcols_table()
+    g = golden("optcols.npz")
+    hapi.storeTable("optcols", cols)
+    grid = np.linspace(1200.0, 1300.0, 20001)
+    for k, (T, p, dil) in enumerate(mg.OPT_CASES):
+        _, xs = hapi.absorptionCoefficient_Voigt(SourceTables="optcols", OmegaGrid=grid, Environment={"T": T, "p": p},
+                                                 Diluent=dil)
+        assert_parity(xs, g["xs%d" % k], RTOL, FLOOR, "optional columns %s" % dil)      # the reference's own output
+    # a table with deltap but no self columns
+    c2 = {k: v for k, v in cols.items() if k not in ("gamma_self", "n_self", "delta_self", "deltap_self")}
+    hapi.storeTable("optcols2", c2)
+    _, xs = hapi.absorptionCoefficient_Voigt(SourceTables="optcols2", OmegaGrid=grid, Environment={"T": 230.0, "p": 0.2})
+    _, ref = port.absorption_coefficient_voigt(c2, T=230.0, p=0.2, OmegaGrid=grid)
+    assert_parity(xs, ref, RTOL, FLOOR, "deltap_air only")
+
+
 def test_voigt_two_tables_and_deterministic(mods):
     port, syn, hapi = mods["port"], mods["syn"], mods["hapi"]
     a = syn.synthetic_lines(53, 150, 900.0, 1000.0, 1)

@@ -143,3 +143,13 @@ def test_reduce_resolution():
     assert np.array_equal(Xo5, g["Xo5"]) and np.array_equal(Yo5, g["Yo5"])
     assert np.array_equal(port.smooth(Y[:, 0], 11), g["s11"])
     assert np.array_equal(port.smooth(Y[:, 2], 10, "flat"), g["s10f"])
+
+
+def test_optional_columns():
+    import make_golden as mg
+    g = golden("optcols.npz")
+    cols = mg.optcols_table()
+    grid = np.linspace(1200.0, 1300.0, 20001)
+    for k, (T, p, dil) in enumerate(mg.OPT_CASES):
+        _, xs = port.absorption_coefficient_voigt(cols, T=T, p=p, OmegaGrid=grid, Diluent=dil)
+        assert_parity(xs, g["xs%d" % k], what="optional columns %d" % k, **TIGHT)

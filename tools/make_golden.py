@@ -180,6 +180,29 @@ def g_reduce():
          Xo=Xo, Yo=Yo, Xo5=Xo5, Yo5=Yo5, s11=s11, s10f=s10f)
 
 
+def optcols_table():
+    rng = np.random.default_rng(9)
+    cols = syn.synthetic_lines(56, 300, 1180.0, 1320.0, 1)
+    n = 300
+    cols["n_self"] = np.where(rng.random(n) < 0.3, 0.0, rng.uniform(0.3, 0.9, n))
+    cols["delta_self"] = rng.uniform(-0.02, 0.01, n)
+    cols["deltap_air"] = rng.uniform(-2e-5, 2e-5, n)
+    cols["deltap_self"] = rng.uniform(-5e-5, 5e-5, n)
+    return cols
+
+
+OPT_CASES = [(250.0, 0.4, {"air": 1.0}), (310.0, 0.9, {"self": 1.0}), (280.0, 0.05, {"air": 0.6, "self": 0.4})]
+
+
+def g_optcols():
+    cols = optcols_table()
+    grid = np.linspace(1200.0, 1300.0, 20001)
+    out = {}
+    for k, (T, p, dil) in enumerate(OPT_CASES):
+        _, out["xs%d" % k] = R.ref_xsect(cols, T, p, grid, Diluent=dil)
+    save("optcols.npz", source="misc/hapi.py:10906-11141 with n_self/delta_self/deltap_* columns and diluent mixes", **out)
+
+
 def g_lut():
     """SDVoigt on a table without SD columns (the reference's own call convention, misc/RT_gen_AbsXS_files.py:90)
     and the AFIT_XS writer, whose source is lifted out of the script with ast (the script itself fetches HITRAN
@@ -209,6 +232,6 @@ def g_lut():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut"]
+    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols"]
     for w in which:
         globals()["g_" + w]()
