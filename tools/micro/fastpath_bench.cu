@@ -1,0 +1,119 @@
+// Micro-benchmark of the Voigt kernel's test-free path: where do the ~21 % of idle FP64-pipe cycles come from?
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o fastpath_bench fastpath_bench.cu && ./fastpath_bench
+#include <cstdio>
+#include <cuda_runtime.h>
+
+struct __align__(16) Rec { double sg0, a, ah, m, c; short lo, hi, clo, chi; };
+
+__device__ __forceinline__ double rcp3(double x) {
+  double r0; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+  const double e = fma(-x, r0, 1.0); const double t = fma(e, e, e); return fma(r0, t, r0);
+}
+__device__ __forceinline__ double rcp2(double x) {
+  double r0; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+  const double e = fma(-x, r0, 1.0); return fma(r0, e, r0);
+}
+
+template <int V>
+__device__ __forceinline__ double term(double w, const Rec& r, double acc) {
+  const double d = w - r.sg0;
+  const double u = fma(d, d, r.m);
+  const double den = fma(u, u, r.c);
+  const double num = fma(r.a, u, r.ah);
+  if (V == 1) return fma(num, rcp2(den), acc);
+  if (V == 2) return fma(num, den, acc);            // no reciprocal at all: 5 DP ops
+  return fma(num, rcp3(den), acc);
+}
+
+template <int V, int K, int MINB>
+__global__ void __launch_bounds__(256, MINB) k(const Rec* __restrict__ g, int nrec, int reps, double* out) {
+  extern __shared__ Rec s[];
+  __shared__ unsigned masks[8];
+  if (threadIdx.x < 8) masks[threadIdx.x] = 0xffffffffu;
+  for (int i = threadIdx.x; i < nrec; i += 256) s[i] = g[i];
+  __syncthreads();
+  double w[K], acc[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) { w[j] = 1000.0 + 1e-3 * (threadIdx.x + 256 * j); acc[j] = 0.0; }
+  for (int rp = 0; rp < reps; ++rp) {
+    if (V == 5) {          // mask-driven iteration as in the product kernel
+      for (int blk = 0; blk < nrec / 32; ++blk) {
+        const Rec* recs = s + blk * 32;
+        unsigned m = masks[blk];
+        while (m) {
+          const Rec& rr = recs[__ffs(m) - 1];
+          m &= m - 1;
+          const Rec r = rr;
+#pragma unroll
+          for (int j = 0; j < K; ++j) acc[j] = term<0>(w[j], r, acc[j]);
+        }
+      }
+    } else if (V == 6) {   // mask-driven with the next record prefetched before the current one is evaluated
+      for (int blk = 0; blk < nrec / 32; ++blk) {
+        const Rec* recs = s + blk * 32;
+        unsigned m = masks[blk];
+        if (!m) continue;
+        Rec cur = recs[__ffs(m) - 1];
+        m &= m - 1;
+        while (true) {
+          const bool more = m != 0;
+          Rec nxt = cur;
+          if (more) { nxt = recs[__ffs(m) - 1]; m &= m - 1; }
+#pragma unroll
+          for (int j = 0; j < K; ++j) acc[j] = term<0>(w[j], cur, acc[j]);
+          if (!more) break;
+          cur = nxt;
+        }
+      }
+    } else if (V == 4) {
+      for (int l = 0; l + 1 < nrec; l += 2) {
+        const Rec r0 = s[l], r1 = s[l + 1];
+#pragma unroll
+        for (int j = 0; j < K; ++j) { acc[j] = term<0>(w[j], r0, acc[j]); }
+#pragma unroll
+        for (int j = 0; j < K; ++j) { acc[j] = term<0>(w[j], r1, acc[j]); }
+      }
+    } else {
+      for (int l = 0; l < nrec; ++l) {
+        const Rec r = s[l];
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] = term<V>(w[j], r, acc[j]);
+      }
+    }
+  }
+  double t = 0; for (int j = 0; j < K; ++j) t += acc[j];
+  out[blockIdx.x * 256 + threadIdx.x] = t;
+}
+
+template <int V, int K, int MINB>
+void run(const char* name, int ops, const Rec* g, double* out, int sms) {
+  const int nrec = 256, reps = 64, blocks = sms * MINB * 4;
+  cudaFuncSetAttribute(k<V, K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int it = 0; it < 4; ++it) {
+    cudaEventRecord(e0);
+    k<V, K, MINB><<<blocks, 256, 64 * 1024 / (MINB > 3 ? 2 : 1) - 1024, 0>>>(g, nrec, reps, out);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); if (it) best = ms < best ? ms : best;
+  }
+  const double evals = (double)blocks * 256 * K * nrec * reps;
+  printf("%-34s %8.3f ms  %7.3f Teval/s  %6.2f TFLOP/s (DP ops x2)\n", name, best, evals / best / 1e9, evals * ops * 2 / best / 1e9);
+}
+
+int main() {
+  int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  Rec h[256];
+  for (int i = 0; i < 256; ++i) { h[i].sg0 = 990.0 + 0.1 * i; h[i].a = 1e-3; h[i].ah = 1e-9; h[i].m = 4.9e-3; h[i].c = 1e-8; h[i].lo = 0; h[i].hi = 2048; h[i].clo = h[i].chi = 0; }
+  Rec* g; double* out; cudaMalloc(&g, sizeof(h)); cudaMalloc(&out, 8 * 256 * 4096 * 4); cudaMemcpy(g, h, sizeof(h), cudaMemcpyHostToDevice);
+  run<0, 8, 3>("cubic NR, K=8, 3 CTA/SM", 8, g, out, sms);
+  run<0, 8, 2>("cubic NR, K=8, 2 CTA/SM", 8, g, out, sms);
+  run<1, 8, 3>("one NR step, K=8, 3 CTA/SM", 7, g, out, sms);
+  run<2, 8, 3>("no reciprocal (5 ops), K=8", 5, g, out, sms);
+  run<4, 8, 3>("cubic NR, two records per iter", 8, g, out, sms);
+  run<5, 8, 3>("cubic NR, mask-driven", 8, g, out, sms);
+  run<6, 8, 3>("cubic NR, mask-driven + prefetch", 8, g, out, sms);
+  run<0, 4, 4>("cubic NR, K=4, 4 CTA/SM", 8, g, out, sms);
+  run<0, 4, 6>("cubic NR, K=4, 6 CTA/SM", 8, g, out, sms);
+  return 0;
+}
