@@ -454,3 +454,30 @@ def test_full_size_properties(mods):
     assert (tau >= 0).all() and (tau <= 1).all() and torch.isfinite(lu).all() and torch.isfinite(ld).all()
     B0 = torch.from_numpy(port.planckian(X, atm["Ts"][:1])[:, 0]).cuda()
     assert (ld <= B0 * (1 + 1e-12)).all()                               # downwelling never exceeds the warmest layer
+
+
+def test_config2_full_density_window(mods):
+    """Config 2 exactly as benchmarked (all 210 000 synthetic lines, 66 layers, 0.001 cm^-1), compared with the oracle on
+    a 2 000-point window for EVERY layer (the oracle gets only the lines that can reach the window), then through the
+    layer integration."""
+    torch, rt, syn, engine, port = (mods[k] for k in ("torch", "rt", "syn", "engine", "port"))
+    atm = syn.standard_atmosphere()
+    tabs = syn.config2_tables()
+    opts = dict(rt.options)
+    db = rt.set_line_database(tabs, opts=opts)
+    X = rt.make_spectral_axis(700.0, 1500.0, 0.001)
+    i0, i1 = 401000, 403000
+    p, w = rt.layer_weights(db, atm["Ts"], atm["Ps"], atm["PLs"], atm["MFs_VAL"], atm["MFs_ID"])
+    grid = torch.from_numpy(X).cuda()
+    od = db.voigt_sum(atm["Ts"], p, w, grid)
+    lo, hi = X[i0] - 12.0, X[i1 - 1] + 12.0          # 50 half-widths of the widest line is < 8 cm^-1
+    sub = {m: {k: v[(t["nu"] > lo) & (t["nu"] < hi)] for k, v in t.items()} for m, t in tabs.items()}
+    OD = np.zeros((i1 - i0, 66))
+    for L in range(66):
+        OD[:, L] = port.layer_od(sub, X[i0:i1], atm["Ts"][L], atm["Ps"][L], atm["PLs"][L], atm["MFs_VAL"][L], atm["MFs_ID"])
+        assert_parity(od[L, i0:i1].cpu().numpy(), OD[:, L], RTOL, FLOOR, "layer %d" % L)
+    tr, ur, dr = port.tud_from_od(X[i0:i1], OD, atm["Zs"], atm["Ts"])
+    tau, lu, ld = engine.tud(od[:, i0:i1].contiguous(), atm["Ts"][None, :], grid[i0:i1].contiguous(), atm["Zs"], [500.0], [1.0], 30)
+    assert_parity(tau[0, :, 0, 0].cpu().numpy(), tr, RTOL, FLOOR, "tau")
+    assert_parity(lu[0, :, 0, 0].cpu().numpy(), ur, RTOL, FLOOR, "Lu")
+    assert_parity(ld[0].cpu().numpy(), dr, RTOL, FLOOR, "Ld")
