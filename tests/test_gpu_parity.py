@@ -481,3 +481,34 @@ def test_config2_full_density_window(mods):
     assert_parity(tau[0, :, 0, 0].cpu().numpy(), tr, RTOL, FLOOR, "tau")
     assert_parity(lu[0, :, 0, 0].cpu().numpy(), ur, RTOL, FLOOR, "Lu")
     assert_parity(ld[0].cpu().numpy(), dr, RTOL, FLOOR, "Ld")
+
+
+def test_config2_full_size_against_c_oracle(mods):
+    """The benchmark configuration at FULL size -- 800 000 grid points x 66 layers x 210 000 lines, 3.3e10 evaluations
+    -- compared point by point with the CPU oracle (C/OpenMP restatement, oracle/voigt_c.c, pinned to the numpy port and
+    the reference's golden vectors), then through the layer integration against the numpy port."""
+    torch, rt, syn, engine, port = (mods[k] for k in ("torch", "rt", "syn", "engine", "port"))
+    from oracle import cbuild
+    atm = syn.standard_atmosphere()
+    tabs = syn.config2_tables()
+    opts = dict(rt.options)
+    db = rt.set_line_database(tabs, opts=opts)
+    X = rt.make_spectral_axis(700.0, 1500.0, 0.001)
+    p, w = rt.layer_weights(db, atm["Ts"], atm["Ps"], atm["PLs"], atm["MFs_VAL"], atm["MFs_ID"])
+    grid = torch.from_numpy(X).cuda()
+    od = db.voigt_sum(atm["Ts"], p, w, grid)
+    OD = np.zeros((X.size, 66))
+    worst = 0.0
+    for L in range(66):
+        OD[:, L] = cbuild.layer_od(tabs, X, atm["Ts"][L], atm["Ps"][L], atm["PLs"][L], atm["MFs_VAL"][L], atm["MFs_ID"])
+        got = od[L].cpu().numpy()
+        assert_parity(got, OD[:, L], RTOL, FLOOR, "full-size layer %d" % L)
+        big = OD[:, L] >= 1e-6 * OD[:, L].max()
+        worst = max(worst, float(np.max(np.abs(got - OD[:, L])[big] / OD[:, L][big])))
+    assert worst < 1e-9
+    tr, ur, dr = port.tud_from_od(X[::40], OD[::40], atm["Zs"], atm["Ts"])          # numpy recurrences on every 40th point
+    tau, lu, ld = engine.tud(od, atm["Ts"][None, :], grid, atm["Zs"], [500.0], [1.0], 30)
+    assert_parity(tau[0, ::40, 0, 0].cpu().numpy(), tr, RTOL, FLOOR, "full-size tau")
+    assert_parity(lu[0, ::40, 0, 0].cpu().numpy(), ur, RTOL, FLOOR, "full-size Lu")
+    assert_parity(ld[0, ::40].cpu().numpy(), dr, RTOL, FLOOR, "full-size Ld")
+    print("full-size config 2: max relative deviation of the optical depths %.2e" % worst)

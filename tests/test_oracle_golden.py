@@ -153,3 +153,24 @@ def test_optional_columns():
     for k, (T, p, dil) in enumerate(mg.OPT_CASES):
         _, xs = port.absorption_coefficient_voigt(cols, T=T, p=p, OmegaGrid=grid, Diluent=dil)
         assert_parity(xs, g["xs%d" % k], what="optional columns %d" % k, **TIGHT)
+
+
+def test_c_oracle_matches_numpy_port_and_golden():
+    """The C/OpenMP restatement used for full-size checks (oracle/voigt_c.c) against the numpy port and, through
+    tests/golden/xsect.npz, against the reference itself."""
+    import make_golden as mg
+    from oracle import cbuild
+    g = golden("xsect.npz")
+    for name, seed, n, (lo, hi, npts), T, p, kw in mg.XS_CASES:
+        cols = syn.synthetic_lines(seed, n, lo - 25.0, hi + 25.0, 1)
+        grid = np.linspace(lo, hi, npts)
+        _, xs, ev = cbuild.absorption_coefficient_voigt(cols, T=T, p=p, OmegaGrid=grid, **kw)
+        assert_parity(xs, g["xs_" + name], rtol=1e-11, floor=1e-14, what="C oracle " + name)
+        _, _, ev_port, _ = port.absorption_coefficient_voigt(cols, T=T, p=p, OmegaGrid=grid, return_evals=True, **kw)
+        assert ev == ev_port
+    atm, tabs = mg.tud_inputs()
+    X = port.make_spectral_axis(700.0, 750.0, 0.05)
+    for L in (0, 30, 65):
+        a = port.layer_od(tabs, X, atm["Ts"][L], atm["Ps"][L], atm["PLs"][L], atm["MFs_VAL"][L], atm["MFs_ID"])
+        b = cbuild.layer_od(tabs, X, atm["Ts"][L], atm["Ps"][L], atm["PLs"][L], atm["MFs_VAL"][L], atm["MFs_ID"])
+        assert_parity(b, a, rtol=1e-11, floor=1e-14, what="C oracle layer_od %d" % L)
