@@ -253,6 +253,21 @@ def test_tud_golden(mods):
         assert_parity(a, b, RTOL, FLOOR, w)
 
 
+def test_tud_many_layers_uncached_path(mods):
+    """More layers than the shared-memory Planck cache holds (> 72 layers): the recompute variant of the kernel."""
+    engine, port = mods["engine"], mods["port"]
+    rng = np.random.default_rng(11)
+    nL, nx = 90, 700
+    X = np.linspace(700.0, 1400.0, nx)
+    OD = rng.uniform(0, 0.3, (nx, nL)) * rng.uniform(0, 1, (nx, 1))
+    Z = np.linspace(0.0, 89.0, nL); T = rng.uniform(200.0, 300.0, nL)
+    tau, lu, ld = engine.tud(np.ascontiguousarray(OD.T), T[None, :], X, Z, [5.0, 500.0], [1.0, 1.3], 12)
+    t_ref, u_ref, d_ref = port.tud_from_od(X, OD, Z, T, N_angle=12, Altitudes=np.array([5.0, 500.0]), theta_r=0.0)
+    assert_parity(tau[0, :, :, 0].cpu().numpy(), t_ref, RTOL, FLOOR, "tau 90 layers")
+    assert_parity(lu[0, :, :, 0].cpu().numpy(), u_ref, RTOL, FLOOR, "Lu 90 layers")
+    assert_parity(ld[0].cpu().numpy(), d_ref, RTOL, FLOOR, "Ld 90 layers")
+
+
 def test_tud_sticky_options_and_compute_od(mods):
     rt, port = mods["rt"], mods["port"]
     atm, tabs, opts, kw = _tud_setup(mods)
