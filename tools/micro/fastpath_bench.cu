@@ -25,6 +25,17 @@ __device__ __forceinline__ double term(double w, const Rec& r, double acc) {
   return fma(num, rcp3(den), acc);
 }
 
+// two lines through one reciprocal:  n1/d1 + n2/d2 = (n1*d2 + n2*d1) / (d1*d2)   -> 15 FP64 ops per 2 evals
+__device__ __forceinline__ double term2(double w, const Rec& r1, const Rec& r2, double acc) {
+  const double da = w - r1.sg0, db = w - r2.sg0;
+  const double ua = fma(da, da, r1.m), ub = fma(db, db, r2.m);
+  const double dena = fma(ua, ua, r1.c), denb = fma(ub, ub, r2.c);
+  const double numa = fma(r1.a, ua, r1.ah), numb = fma(r2.a, ub, r2.ah);
+  const double P = dena * denb;
+  const double X = fma(numb, dena, numa * denb);
+  return fma(X, rcp3(P), acc);
+}
+
 template <int V, int K, int MINB>
 __global__ void __launch_bounds__(256, MINB) k(const Rec* __restrict__ g, int nrec, int reps, double* out) {
   extern __shared__ Rec s[];
@@ -36,7 +47,13 @@ __global__ void __launch_bounds__(256, MINB) k(const Rec* __restrict__ g, int nr
 #pragma unroll
   for (int j = 0; j < K; ++j) { w[j] = 1000.0 + 1e-3 * (threadIdx.x + 256 * j); acc[j] = 0.0; }
   for (int rp = 0; rp < reps; ++rp) {
-    if (V == 5) {          // mask-driven iteration as in the product kernel
+    if (V == 7) {          // paired reciprocal
+      for (int l = 0; l + 1 < nrec; l += 2) {
+        const Rec r0 = s[l], r1 = s[l + 1];
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] = term2(w[j], r0, r1, acc[j]);
+      }
+    } else if (V == 5) {          // mask-driven iteration as in the product kernel
       for (int blk = 0; blk < nrec / 32; ++blk) {
         const Rec* recs = s + blk * 32;
         unsigned m = masks[blk];
@@ -111,6 +128,8 @@ int main() {
   run<1, 8, 3>("one NR step, K=8, 3 CTA/SM", 7, g, out, sms);
   run<2, 8, 3>("no reciprocal (5 ops), K=8", 5, g, out, sms);
   run<4, 8, 3>("cubic NR, two records per iter", 8, g, out, sms);
+  run<7, 8, 3>("paired reciprocal (7.5 ops/eval)", 8, g, out, sms);
+  run<7, 8, 2>("paired reciprocal, 2 CTA/SM", 8, g, out, sms);
   run<5, 8, 3>("cubic NR, mask-driven", 8, g, out, sms);
   run<6, 8, 3>("cubic NR, mask-driven + prefetch", 8, g, out, sms);
   run<0, 4, 4>("cubic NR, K=4, 4 CTA/SM", 8, g, out, sms);
