@@ -35,6 +35,61 @@ def AFIT_XS_read(File):
     return np.linspace(xmin, xmax, int(n)), Y, float(T), float(P), int(ID), name
 
 
+def _matlab_header_blob(**kwargs):
+    """Header variables serialised as a MATLAB v5 file in memory (AFIT_MBI.py:18-28)."""
+    import io
+    import scipy.io as sio
+    H = {key: val for key, val in kwargs.items()}
+    f = io.BytesIO()
+    sio.savemat(f, {"Header": H})
+    return f.getvalue()
+
+
+def AFIT_MBI_export(fname, Data, Rows=[], Columns=[], Bands=[], Sidecar=True, BandsFirstDim=True, Verbose=True,
+                    **kwargs):
+    """BIP / BSQ multiband image export with the AFIT_MBI header, same arguments and byte layout as the reference's
+    AFIT_MBI_export (AFIT_MBI.py:45-156): uint32 dims (rows, columns, bands), 6-char dtype string, 3-char
+    interleave, uint32 offset of the pixel data, float64 rows|columns|bands, the MATLAB-v5 header blob, then the
+    pixels band-sequential ('.bsq') or band-interleaved-by-pixel ('.bip').  (The blob carries scipy's creation
+    timestamp in its 116-byte text header, so two exports differ in those bytes only.)  The output cube of
+    engine.hsi_pixels / config 4 goes through this writer."""
+    import os
+    import sys
+    Data = np.array(Data)
+    if BandsFirstDim:
+        Data = Data.transpose([1, 2, 0]).copy(order="C")
+    nR, nC, nB = Data.shape
+    if len(Bands) == 0: Bands = np.arange(nB)
+    if len(Rows) == 0: Rows = np.arange(nR)
+    if len(Columns) == 0: Columns = np.arange(nC)
+    if len(kwargs) == 0: kwargs = {"MetaData": "None"}
+    fdir, base = os.path.split(fname)
+    interleave = os.path.splitext(base)[1][1:].lower()
+    s = str(Data.dtype)
+    dtypeStr = "{0:<6}".format({"float64": "double", "float32": "single"}.get(s, s))
+    rcb = np.concatenate((Rows, Columns, Bands)).astype("float64")
+    blob = _matlab_header_blob(**kwargs)
+    offsetBytes = np.array(12 + 6 + 3 + 4 + len(blob) + rcb.nbytes)
+    if Data.dtype.byteorder == ">" or not (sys.byteorder == "little" and Data.dtype.byteorder in ("=", "|")):
+        Data = Data.byteswap()
+    with open(os.path.join(fdir, base) if fdir else base, "wb") as f:
+        np.array(Data.shape).astype("uint32").tofile(f)
+        f.write(bytes(dtypeStr, "utf-8"))
+        f.write(bytes(interleave, "utf-8"))
+        offsetBytes.astype("uint32").tofile(f)
+        rcb.tofile(f)
+        f.write(blob)
+        if interleave == "bsq":
+            np.ascontiguousarray(Data.transpose(2, 0, 1)).tofile(f)        # band by band, rows x columns each
+        elif interleave == "bip":
+            np.ascontiguousarray(Data).tofile(f)                           # pixel by pixel, all bands of a pixel
+        else:
+            print("Unknown file extension -- no data saved")
+    if Verbose:
+        print("Wrote {0} bytes ({1} header, {2} data) to {3}".format(Data.nbytes + offsetBytes, offsetBytes,
+                                                                     Data.nbytes, base))
+
+
 def cross_section_lut(SourceTables, temperatures, pressures_atm, OmegaGrid, **voigt_kwargs):
     """Cross-sections for every (T, p) pair in one launch: the loop of misc/RT_gen_AbsXS_files.py:87-93
     (`for t in T: for p in P: absorptionCoefficient_SDVoigt(...)`) batched over states.

@@ -116,3 +116,29 @@ def test_afit_xs_bytes_match_reference_writer(tmp_path):
         assert formats.AFIT_XS_write(grid[:3], g["xs0"][:3], 296.4, 101325.0, 2, "db") == "XS-02-0296K-101325Pa.bin"
     finally:
         os.chdir(cwd)
+
+
+def test_afit_mbi_export_matches_reference_bytes(tmp_path):
+    """BIP/BSQ cube writer against files written by the reference's AFIT_MBI_export (tests/golden/mbi.npz); the only
+    bytes allowed to differ are the 116-byte text header of the embedded MATLAB blob (scipy's timestamp)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_golden as mg
+    from conftest import golden
+    from radtxfr_b200 import formats
+    g = golden("mbi.npz")
+    img = mg.mbi_image()
+    cwd = os.getcwd(); os.chdir(tmp_path)
+    try:
+        formats.AFIT_MBI_export("a.bsq", img, Verbose=False, Q=np.array([1, 2, 3]), Meta1=2, myString="hello")
+        formats.AFIT_MBI_export("b.bip", img, Verbose=False)
+        formats.AFIT_MBI_export("c.bip", g["cube"], Verbose=False, Bands=np.array([7.5, 8.5, 9.5, 10.5]))
+        for name, nrcb in (("a.bsq", 40 + 32 + 3), ("b.bip", 40 + 32 + 3), ("c.bip", 6 + 5 + 4)):
+            got = np.frombuffer(open(name, "rb").read(), dtype=np.uint8).copy()
+            ref = g[name.replace(".", "_")].copy()
+            assert got.size == ref.size, name
+            blob0 = 12 + 6 + 3 + 4 + 8 * nrcb            # start of the MATLAB blob
+            got[blob0:blob0 + 116] = 0; ref[blob0:blob0 + 116] = 0
+            assert np.array_equal(got, ref), name
+    finally:
+        os.chdir(cwd)

@@ -230,8 +230,46 @@ def g_lut():
     save("lut.npz", source="misc/hapi.py:10657 absorptionCoefficient_SDVoigt; misc/RT_gen_AbsXS_files.py:45-83", **out)
 
 
+def mbi_image():
+    ii, jj = np.meshgrid(np.arange(40), np.arange(32), indexing="ij")
+    img = np.zeros((3, 40, 32), dtype=np.uint8)
+    img[0] = (ii ** 2 + jj ** 2) < 16 ** 2
+    img[1] = (abs(ii - 20) > 0) & (abs(jj - 16) > 0)
+    img[2] = (ii > 20) & (jj < 16)
+    return img
+
+
+def g_mbi():
+    """AFIT_MBI_export of the reference (AFIT_MBI.py:45-156); its functions are lifted out with ast because the
+    module runs a self-test (and imports matplotlib) at import time."""
+    import ast
+    import tempfile
+    src = open(os.path.join(R.REF_ROOT, "AFIT_MBI.py")).read()
+    tree = ast.parse(src)
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef)]
+    import pickle, sys as _sys
+    import scipy.io as sio
+    ns = {"np": np, "os": os, "sio": sio, "pickle": pickle, "tempfile": tempfile, "sys": _sys}
+    exec(compile(ast.Module(body=body, type_ignores=[]), "AFIT_MBI", "exec"), ns)
+    img = mbi_image()
+    cube = np.random.default_rng(5).uniform(0, 100, (4, 6, 5))
+    out = {}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            ns["AFIT_MBI_export"]("a.bsq", img, Verbose=False, Q=np.array([1, 2, 3]), Meta1=2, myString="hello")
+            ns["AFIT_MBI_export"]("b.bip", img, Verbose=False)
+            ns["AFIT_MBI_export"]("c.bip", cube, Verbose=False, Bands=np.array([7.5, 8.5, 9.5, 10.5]))
+            for k in ("a.bsq", "b.bip", "c.bip"):
+                out[k.replace(".", "_")] = np.frombuffer(open(k, "rb").read(), dtype=np.uint8)
+        finally:
+            os.chdir(cwd)
+    save("mbi.npz", source="AFIT_MBI.py:45-156 AFIT_MBI_export", cube=cube, **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols"]
+    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi"]
     for w in which:
         globals()["g_" + w]()
