@@ -527,3 +527,36 @@ def test_config2_full_size_against_c_oracle(mods):
     assert_parity(lu[0, ::40, 0, 0].cpu().numpy(), ur, RTOL, FLOOR, "full-size Lu")
     assert_parity(ld[0, ::40].cpu().numpy(), dr, RTOL, FLOOR, "full-size Ld")
     print("full-size config 2: max relative deviation of the optical depths %.2e" % worst)
+
+
+def test_generate_lwir_tud_driver(mods):
+    """The production sweep (Generate_LWIR_TUD.py:79-132) as one device pipeline, against a loop of oracle calls:
+    compute_TUD(returnOD=True, nine altitudes) followed by reduceResolution of OD, La and Ld, per atmosphere."""
+    rt, syn, port = mods["rt"], mods["syn"], mods["port"]
+    from radtxfr_b200 import drivers
+    import make_golden as mg
+    atm, tabs = mg.tud_inputs()
+    opts = dict(rt.options)
+    rt.set_line_database({m: tabs[m] for m in (1, 2, 3)}, opts=opts)
+    Ts, MF = syn.perturbed_atmospheres(6, 3)
+    H2O, O3 = MF[:, :, 0] * 1e-6, MF[:, :, 2] * 1e-6
+    CO2 = atm["MFs_VAL"][:, 1] * 1e-6
+    Alt = drivers.default_altitudes(float(atm["Zs"].max()))
+    X, OD, La, Ld = drivers.generate_LWIR_TUD(Ts, H2O, O3, CO2, Xmin=700.0, Xmax=750.0, DV=0.01, DV_out=0.25,
+                                              Altitudes=Alt, opts=opts, atm_chunk=2)
+    assert OD.shape == (X.size, 9, 3) and La.shape == OD.shape and Ld.shape == (X.size, 3)
+    Xr = None
+    for jj in range(3):
+        MFj = 1e6 * np.stack([H2O[jj], CO2, O3[jj]], axis=1)
+        XX, od_, la_, ld_ = port.compute_tud(tabs, 700.0, 750.0, Zs=atm["Zs"], Ts=Ts[jj], Ps=atm["Ps"], PLs=atm["PLs"],
+                                             MFs_VAL=MFj, MFs_ID=[1, 2, 3], DVOUT=0.01, Altitudes=Alt, returnOD=True)
+        if Xr is None:
+            Xr, od_r = port.reduce_resolution(XX, od_, 0.25)
+        else:
+            od_r = port.reduce_resolution(XX, od_, 0.25, X_out=Xr)
+        la_r = port.reduce_resolution(XX, la_, 0.25, X_out=Xr)
+        ld_r = port.reduce_resolution(XX, ld_, 0.25, X_out=Xr)
+        assert_parity(X, Xr, 1e-12, 0.0, "driver axis")
+        assert_parity(OD[:, :, jj], od_r, RTOL, FLOOR, "driver OD atm %d" % jj)
+        assert_parity(La[:, :, jj], la_r, RTOL, FLOOR, "driver La atm %d" % jj)
+        assert_parity(Ld[:, jj], ld_r, RTOL, FLOOR, "driver Ld atm %d" % jj)

@@ -142,3 +142,18 @@ def test_afit_mbi_export_matches_reference_bytes(tmp_path):
             assert np.array_equal(got, ref), name
     finally:
         os.chdir(cwd)
+
+
+def test_jacobian_inputs():
+    """JacIn / Jacobian sweep inputs as Generate_LWIR_TUD.py:55-71 builds them."""
+    from radtxfr_b200 import drivers
+    x = np.array([1.0, -4.0, 2.0])
+    J = drivers.JacIn(x, 0.1, rel=True)
+    assert J.shape == (3, 3) and np.allclose(np.diag(J), x + 0.4) and np.array_equal(J - np.diag(np.diag(J)), np.tile(x, (3, 1)) - np.diag(x))
+    J2 = drivers.JacIn(x, 0.5)
+    assert np.allclose(np.diag(J2), x + 0.5)
+    T, H, O = drivers.jacobian_inputs(np.array([280.0, 250.0]), np.array([1e-2, 1e-4]), np.array([1e-8, 1e-6]))
+    assert T.shape == (7, 2) and np.array_equal(T[0], [280.0, 250.0]) and T[1, 0] == 280.0 + 0.28 and T[2, 1] == 250.0 + 0.28
+    assert np.array_equal(T[3:], np.tile([280.0, 250.0], (4, 1))) and H[3, 0] == 1e-2 + 1e-5 and O[6, 1] == 1e-6 + 1e-9
+    alt = drivers.default_altitudes(70.0)
+    assert alt.size == 9 and abs(alt[0] - 0.06096) < 1e-12 and alt[-1] == 70.0
