@@ -268,6 +268,29 @@ def absorption_coefficient_voigt(cols, T=296.0, p=1.0, OmegaGrid=None, OmegaWing
     return Omegas, Xsect
 
 
+def absorption_coefficient_lorentz(cols, T=296.0, p=1.0, OmegaGrid=None, OmegaWing=0.0, OmegaWingHW=50.0,
+                                   IntensityThreshold=0.0, GammaL="gamma_air", HITRAN_units=True, Diluent=None,
+                                   Components=None):
+    """absorptionCoefficient_Lorentz, misc/hapi.py:11144-11381: wing = max(OmegaWing, HW*Gamma0) (:11375), profile
+    PROFILE_LORENTZ = Gam0/(pi*(Gam0**2+(sg-sg0)**2)) (:10142-10150) centred on nu+Shift0."""
+    Omegas = np.sort(np.asarray(OmegaGrid, dtype=float))
+    Xsect = np.zeros(Omegas.size)
+    factor = 1.0 if HITRAN_units else volume_concentration(p, T)
+    st = line_state(cols, T, p, Diluent, GammaL, Components, IntensityThreshold, OmegaWing, OmegaWingHW)
+    nu, S, Gam0, Sh, ampl, keep = (st[k] for k in ("nu", "S", "Gam0", "Shift0", "ampl", "keep"))
+    W = np.maximum(OmegaWing, OmegaWingHW * Gam0)
+    lo_all = np.searchsorted(Omegas, nu - W, side="right")
+    hi_all = np.searchsorted(Omegas, nu + W, side="right")
+    for r in np.nonzero(keep)[0]:
+        lo, hi = int(lo_all[r]), int(hi_all[r])
+        if hi <= lo:
+            continue
+        sg = Omegas[lo:hi]
+        V = Gam0[r] / (np.pi * (Gam0[r] ** 2 + (sg - (nu[r] + Sh[r])) ** 2))
+        Xsect[lo:hi] += factor * ampl[r] * S[r] * V
+    return Omegas, Xsect
+
+
 def count_evals(cols, T, p, Omegas, **kw):
     """Exact number of (line, grid-point) pairs inside hapi's window for one (T, p)."""
     st = line_state(cols, T, p, **kw)

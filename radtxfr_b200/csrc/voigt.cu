@@ -84,6 +84,7 @@ struct VoigtParams {
   const int32_t* bins;  // [n_states][n_tiles][2]
   double* out;
   int has_self, has_deltap, use_tma;
+  int lorentz;   // PROFILE_LORENTZ instead of PROFILE_VOIGT: no Doppler width, wing = max(OmegaWing, HW*Gamma0)
 };
 
 // Everything the reference derives for one line at one (T, p): misc/hapi.py:11058-11131.
@@ -123,7 +124,8 @@ __device__ __forceinline__ LineState line_state(const VoigtParams& P, int64_t li
   L.gam0 = g0;
   L.nu = nu;
   L.sg0 = nu + sh;
-  L.W = fmax(fmax(P.wing_abs, P.wing_hw * g0), P.wing_hw * L.gamD);  // :11131
+  L.W = P.lorentz ? fmax(P.wing_abs, P.wing_hw * g0)                  // misc/hapi.py:11375 (Lorentz driver)
+                  : fmax(fmax(P.wing_abs, P.wing_hw * g0), P.wing_hw * L.gamD);  // :11131
   L.amp = wgt * S;
   return L;
 }
@@ -477,9 +479,11 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : RTX_MINBLOCK
           const int lo = count_le(s_grid, ts, L.nu - L.W);                // bisect(Omegas, nu-W), misc/hapi.py:11133
           const int hi = count_le(s_grid, ts, L.nu + L.W);                // bisect(Omegas, nu+W), misc/hapi.py:11134
           if (hi > lo) {
+            // Lorentz profile Gam0/(pi*(Gam0^2+d^2)) (misc/hapi.py:10142-10150) = the closed form below with h = 0 and
+            // no Weideman region
             const double cte = RTX_SQRT_LN2 / L.gamD;                      // misc/hapi.py:9900
-            const double y = L.gam0 * cte;                                 // misc/hapi.py:9913
-            const double h = L.gamD * L.gamD / RTX_LN2;                    // 1/cte^2
+            const double y = P.lorentz ? 1e300 : L.gam0 * cte;             // misc/hapi.py:9913
+            const double h = P.lorentz ? 0.0 : L.gamD * L.gamD / RTX_LN2;  // 1/cte^2
             const double g2 = L.gam0 * L.gam0;
             const double a = L.amp * L.gam0 / RTX_PI;
             sr.sg0 = wr.sg0 = L.sg0;
@@ -804,7 +808,7 @@ __global__ void count_kernel(const VoigtParams P, unsigned long long* __restrict
       const int64_t hi = bisect_right_dev64(P.grid, P.nx, L.nu + L.W);
       if (hi > lo) {
         ev = (unsigned long long)(hi - lo);
-        const double cte = RTX_SQRT_LN2 / L.gamD, y = L.gam0 * cte;
+        const double cte = RTX_SQRT_LN2 / L.gamD, y = P.lorentz ? 1e300 : L.gam0 * cte;
         if (y < 15.0) {
           int64_t m = bisect_left_dev64(P.grid, P.nx, L.sg0);
           m = max(lo, min(hi, m));
@@ -885,6 +889,7 @@ int fill_params(rtx_handle* h, VoigtParams& P, int n_states, const double* T, co
   P.has_self = (x_self != 0.0) ? 1 : 0;
   P.has_deltap = L.has_deltap ? 1 : 0;
   P.use_tma = ((reinterpret_cast<uintptr_t>(grid) & 15u) == 0) ? 1 : 0;
+  P.lorentz = 0;
   return RTX_OK;
 }
 
@@ -930,6 +935,7 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
                        grid_dev, nx);
   if (rc) return rc;
   P.out = out_dev;
+  P.lorentz = (flags & RTX_VOIGT_LORENTZ) ? 1 : 0;
   double* st_wb = nullptr;
   rc = run_prep(h, P, st, &st_wb);
   if (rc) return rc;

@@ -115,7 +115,8 @@ def absorptionCoefficient_Voigt(Components=None, SourceTables=None, partitionFun
                                 IntensityThreshold=DefaultIntensityThreshold, OmegaWingHW=DefaultOmegaWingHW,
                                 GammaL='gamma_air', HITRAN_units=True, LineShift=True, File=None, Format=None,
                                 OmegaGrid=None, WavenumberRange=None, WavenumberStep=None, WavenumberWing=None,
-                                WavenumberWingHW=None, WavenumberGrid=None, Diluent={}, EnvDependences=None):
+                                WavenumberWingHW=None, WavenumberGrid=None, Diluent={}, EnvDependences=None,
+                                _profile_flags=0):
     """Voigt absorption cross-section / coefficient on a wavenumber grid; signature, defaults and return value
     of the reference's absorptionCoefficient_Voigt (misc/hapi.py:10906-11141)."""
     torch = engine._torch()
@@ -184,7 +185,7 @@ def absorptionCoefficient_Voigt(Components=None, SourceTables=None, partitionFun
     xs = db.voigt_sum(np.array([T]), np.array([p]), w_iso[None, :], Omegas, x_air=x_air, x_self=x_self,
                       wing_abs=float(OmegaWing), wing_hw=float(OmegaWingHW),
                       s_threshold=float(IntensityThreshold),
-                      flags={"fp64": 0, "fp64_fast": 1, "fp32": 2}[VARIABLES["precision"]])[0]
+                      flags={"fp64": 0, "fp64_fast": 1, "fp32": 2}[VARIABLES["precision"]] | int(_profile_flags))[0]
     if as_tensor:
         return Omegas, xs
     return Omegas, xs.cpu().numpy()
@@ -201,4 +202,12 @@ def absorptionCoefficient_SDVoigt(*args, **kwargs):
     for n in names:
         if n in LOCAL_TABLE_CACHE and any(k.lower().startswith("sd_") for k in LOCAL_TABLE_CACHE[n]["data"]):
             raise NotImplementedError("speed-dependent broadening (SD_* columns) is not on the accelerated path")
+    return absorptionCoefficient_Voigt(*args, **kwargs)
+
+
+def absorptionCoefficient_Lorentz(*args, **kwargs):
+    """Lorentz-profile driver of hapi (misc/hapi.py:11144-11381): same arguments as absorptionCoefficient_Voigt; the
+    profile is Gamma0/(pi*(Gamma0^2 + (omega-nu0-shift)^2)) (PROFILE_LORENTZ, :10142-10150) and the wing is
+    max(OmegaWing, OmegaWingHW*Gamma0) (:11375)."""
+    kwargs["_profile_flags"] = 16          # RTX_VOIGT_LORENTZ
     return absorptionCoefficient_Voigt(*args, **kwargs)

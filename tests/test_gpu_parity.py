@@ -560,3 +560,16 @@ def test_generate_lwir_tud_driver(mods):
         assert_parity(OD[:, :, jj], od_r, RTOL, FLOOR, "driver OD atm %d" % jj)
         assert_parity(La[:, :, jj], la_r, RTOL, FLOOR, "driver La atm %d" % jj)
         assert_parity(Ld[:, jj], ld_r, RTOL, FLOOR, "driver Ld atm %d" % jj)
+
+
+def test_lorentz_profile_golden(mods):
+    """absorptionCoefficient_Lorentz against the reference's own outputs (tests/golden/lorentz.npz)."""
+    import make_golden as mg
+    hapi, syn = mods["hapi"], mods["syn"]
+    g = golden("lorentz.npz")
+    cols = syn.synthetic_lines(90, 300, 1480.0, 1620.0, 1)
+    hapi.storeTable("lor", cols)
+    grid = np.linspace(1500.0, 1600.0, 10001)
+    for k, (T, p, kw) in enumerate(mg.LORENTZ_CASES):
+        _, xs = hapi.absorptionCoefficient_Lorentz(SourceTables="lor", Environment={"T": T, "p": p}, OmegaGrid=grid, **kw)
+        assert_parity(xs, g["xs%d" % k], RTOL, FLOOR, "Lorentz %d" % k)

@@ -174,3 +174,13 @@ def test_c_oracle_matches_numpy_port_and_golden():
         a = port.layer_od(tabs, X, atm["Ts"][L], atm["Ps"][L], atm["PLs"][L], atm["MFs_VAL"][L], atm["MFs_ID"])
         b = cbuild.layer_od(tabs, X, atm["Ts"][L], atm["Ps"][L], atm["PLs"][L], atm["MFs_VAL"][L], atm["MFs_ID"])
         assert_parity(b, a, rtol=1e-11, floor=1e-14, what="C oracle layer_od %d" % L)
+
+
+def test_lorentz():
+    import make_golden as mg
+    g = golden("lorentz.npz")
+    cols = syn.synthetic_lines(90, 300, 1480.0, 1620.0, 1)
+    grid = np.linspace(1500.0, 1600.0, 10001)
+    for k, (T, p, kw) in enumerate(mg.LORENTZ_CASES):
+        _, xs = port.absorption_coefficient_lorentz(cols, T=T, p=p, OmegaGrid=grid, **kw)
+        assert_parity(xs, g["xs%d" % k], what="Lorentz %d" % k, **TIGHT)

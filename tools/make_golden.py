@@ -230,6 +230,22 @@ def g_lut():
     save("lut.npz", source="misc/hapi.py:10657 absorptionCoefficient_SDVoigt; misc/RT_gen_AbsXS_files.py:45-83", **out)
 
 
+LORENTZ_CASES = [(296.0, 1.0, {}), (250.0, 0.2, {"OmegaWingHW": 25.0}), (310.0, 0.6, {"Diluent": {"air": 0.5, "self": 0.5}, "HITRAN_units": False})]
+
+
+def g_lorentz():
+    h = R.hapi()
+    import contextlib, io
+    cols = syn.synthetic_lines(90, 300, 1480.0, 1620.0, 1)
+    R.inject_table("__lor__", cols)
+    grid = np.linspace(1500.0, 1600.0, 10001)
+    out = {}
+    for k, (T, p, kw) in enumerate(LORENTZ_CASES):
+        with contextlib.redirect_stdout(io.StringIO()):
+            _, out["xs%d" % k] = h.absorptionCoefficient_Lorentz(SourceTables="__lor__", Environment={"T": T, "p": p}, OmegaGrid=grid, **kw)
+    save("lorentz.npz", source="misc/hapi.py:11144-11381 absorptionCoefficient_Lorentz", **out)
+
+
 def mbi_image():
     ii, jj = np.meshgrid(np.arange(40), np.arange(32), indexing="ij")
     img = np.zeros((3, 40, 32), dtype=np.uint8)
@@ -270,6 +286,6 @@ def g_mbi():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi"]
+    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi", "lorentz"]
     for w in which:
         globals()["g_" + w]()
