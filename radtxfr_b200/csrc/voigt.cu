@@ -30,6 +30,8 @@
 
 #include <algorithm>
 
+#include <type_traits>
+
 #include "rtx_common.cuh"
 
 namespace {
@@ -40,6 +42,12 @@ constexpr int NT = 256;         // threads per CTA
 #ifndef RTX_ROUNDS
 #define RTX_ROUNDS 1
 #endif
+#ifndef RTX_P2_ILP
+#define RTX_P2_ILP 2
+#endif
+#ifndef RTX_K4MAX
+#define RTX_K4MAX 0
+#endif
 #ifndef RTX_MINBLOCKS
 #define RTX_MINBLOCKS 3
 #endif
@@ -48,7 +56,7 @@ constexpr int ROUNDS = RTX_ROUNDS;  // prologue rounds per chunk (one line per t
 constexpr int LCHUNK = NT * ROUNDS;  // lines per chunk
 constexpr int NBLK = LCHUNK / 32;     // 32-line blocks per chunk
 #ifndef RTX_NARROW_MAX
-#define RTX_NARROW_MAX 64
+#define RTX_NARROW_MAX 128
 #endif
 constexpr int NARROW_MAX = RTX_NARROW_MAX;  // windows of at most this many tile points go to pass 2 entirely
 
@@ -230,9 +238,11 @@ __device__ __forceinline__ unsigned slice_masks(int lo, int hi, int clo, int chi
   }
   return m;
 }
+// pass-2 record: [s, e) is evaluated by pass 2, of which [cs, ce) is the Weideman core (empty: cs == ce == s)
 struct __align__(16) SegRec {
   double sg0, cte, y, cw, a, ah, m, c;
-  int s, e;
+  short s, e, cs, ce;
+  int pad_;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -377,7 +387,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
 // WS = warp-specialised variant: NPW extra producer warps run the prologue one chunk ahead (double-buffered
 // records, mbarrier full/empty handshake); the eight consumer warps never meet at a block-wide barrier.
 template <int K, int MODE, bool WS>
-__global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : RTX_MINBLOCKS) voigt_tile_kernel(const VoigtParams P) {
+__global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K <= RTX_K4MAX ? 4 : RTX_MINBLOCKS)) voigt_tile_kernel(const VoigtParams P) {
   constexpr bool FAST = (MODE == 1);
   constexpr bool F32 = (MODE == 2);
   constexpr int TILE = K * NT;
@@ -394,8 +404,18 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : RTX_MINBLOCK
   __shared__ __align__(8) unsigned long long s_bar, s_full[2], s_empty[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifndef RTX_BLOCK_ORDER
+#define RTX_BLOCK_ORDER 0
+#endif
+#if RTX_BLOCK_ORDER == 1
+  // tile-major: consecutive CTAs are the states (layers) of one tile, so every SM holds a mix of pipe-bound
+  // (low, pressure-broadened layers) and latency-bound (high, Doppler-dominated layers) CTAs at any time
+  const int s = blockIdx.x % P.n_states;
+  const int tile = blockIdx.x / P.n_states;
+#else
   const int tile = blockIdx.x % P.n_tiles;
   const int s = blockIdx.x / P.n_tiles;
+#endif
   const int64_t p0 = (int64_t)tile * TILE;
   const int npts = (int)min((int64_t)TILE, P.nx - p0);
 
@@ -542,12 +562,13 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : RTX_MINBLOCK
                 chi = g;
               }
             }
+            sr.cs = (short)clo; sr.ce = (short)chi;
             if (hi - lo <= NARROW_MAX) {
-              has_seg = true; sr.s = lo; sr.e = hi;
+              has_seg = true; sr.s = (short)lo; sr.e = (short)hi;
             } else {
               is_wide = true;
               wr.lo = (short)lo; wr.hi = (short)hi; wr.clo = (short)clo; wr.chi = (short)chi;
-              if (chi > clo) { has_seg = true; sr.s = clo; sr.e = chi; }
+              if (chi > clo) { has_seg = true; sr.s = (short)clo; sr.e = (short)chi; }
             }
           }
         }
@@ -615,6 +636,9 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : RTX_MINBLOCK
     for (int blk = 0; blk < NBLK; ++blk) {
       const WideRec* __restrict__ recs = s_wide + buf * LCHUNK + blk * 32;
       unsigned m = s_mfull[buf][blk][warp];
+#ifdef RTX_DBG_SKIP_FULL
+      m = 0;
+#endif
       if (MODE == 0) {
         // full-precision FP64 path: records that cover the slice are taken two at a time through one reciprocal
         while (m & (m - 1)) {
@@ -637,6 +661,9 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : RTX_MINBLOCK
         for (int j = 0; j < K; ++j) RTX_EVAL(j);
       }
       m = s_mtouch[buf][blk][warp];
+#ifdef RTX_DBG_SKIP_TOUCH
+      m = 0;
+#endif
       while (m) {
         const WideRec& rr = recs[__ffs(m) - 1];
         m &= m - 1;
@@ -675,20 +702,51 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : RTX_MINBLOCK
       for (int j = 0; j < K; ++j) { acc[j] += (double)a32[j]; a32[j] = 0.f; }
     }
     // ---- pass 2: segments (Weideman cores, narrow windows) inside the warp's slice -------------------------
-    // When the segments of a 32-record block are short (coarse grids: a Weideman core is ~5 points), the
-    // (segment, point) pairs are flattened and dealt to the lanes, so a warp still evaluates 32 points per step.  Lanes that
-    // hit the same grid point in one step are found with match.any and summed in lane order by the lowest lane
-    // before the shared-memory update: no atomics, summation order fixed.
+    // Wings and cores are taken separately so that no warp step mixes the 8-operation closed form with the
+    // 24-term series: (a) the wing points of each record (left and right of its core, concatenated) are dealt to
+    // the lanes record by record; (b) the cores of the block's records are flattened -- (record, point) pairs
+    // dealt to the lanes across record boundaries -- and lanes that hit the same grid point in one step are
+    // found with match.any and summed in lane order by the lowest lane: no atomics, summation order fixed.
 #pragma unroll 1
     for (int blk = 0; blk < NBLK; ++blk) {
-      const unsigned msk = s_mseg[buf][blk][warp];
+      unsigned msk = s_mseg[buf][blk][warp];
+#ifdef RTX_DBG_SKIP_PASS2
+      msk = 0;
+#endif
       if (!msk) continue;
       const SegRec* __restrict__ recs = s_seg + buf * LCHUNK + blk * 32;
-      int ss = 0, n = 0;
+      int cs = 0, n = 0, nw = 0;
       if ((msk >> lane) & 1u) {
-        ss = max(recs[lane].s, own_lo);
-        n = min(recs[lane].e, own_hi) - ss;
+        const SegRec& q = recs[lane];
+        cs = max((int)q.cs, own_lo);
+        n = max(min((int)q.ce, own_hi) - cs, 0);
+        nw = max(min((int)q.cs, own_hi) - max((int)q.s, own_lo), 0) + max(min((int)q.e, own_hi) - max((int)q.ce, own_lo), 0);
       }
+      // (a) wings
+      unsigned m2 = __ballot_sync(0xffffffffu, nw > 0);
+      while (m2) {
+        const SegRec& r = recs[__ffs(m2) - 1];
+        m2 &= m2 - 1;
+        const double sg0 = r.sg0, a = r.a, ah = r.ah, mm = r.m, c = r.c;
+        const int ls = max((int)r.s, own_lo), nl = max(min((int)r.cs, own_hi) - ls, 0);
+        const int rs = max((int)r.ce, own_lo), nr = max(min((int)r.e, own_hi) - rs, 0);
+        const int nt = nl + nr;
+        int t = lane;
+        for (; t + 32 < nt; t += 64) {               // two rows per step: independent chains, disjoint points
+          const int i0 = t < nl ? ls + t : rs + (t - nl);
+          const int i1 = t + 32 < nl ? ls + t + 32 : rs + (t + 32 - nl);
+          const double v0 = cheap_term<false>(s_grid[i0], sg0, a, ah, mm, c, s_acc2[i0]);
+          const double v1 = cheap_term<false>(s_grid[i1], sg0, a, ah, mm, c, s_acc2[i1]);
+          s_acc2[i0] = v0;
+          s_acc2[i1] = v1;
+        }
+        if (t < nt) {
+          const int i = t < nl ? ls + t : rs + (t - nl);
+          s_acc2[i] = cheap_term<false>(s_grid[i], sg0, a, ah, mm, c, s_acc2[i]);
+        }
+        __syncwarp();
+      }
+      // (b) cores
       int incl = n;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -697,60 +755,53 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : RTX_MINBLOCK
       }
       const int total = __shfl_sync(0xffffffffu, incl, 31);
       const int excl = incl - n;
-      if (total >= 20 * __popc(msk)) {
-        // long segments (fine grids): one segment at a time already fills the lanes
-        unsigned m2 = msk;
-        while (m2) {
-          const SegRec r = recs[__ffs(m2) - 1];
-          m2 &= m2 - 1;
-          const int s0 = max(r.s, own_lo), e0 = min(r.e, own_hi);
-          for (int i = s0 + lane; i < e0; i += 32) {
-            const double om = s_grid[i];
-            const double x = __dmul_rn(om - r.sg0, r.cte);
-            double v;
-            if (__dadd_rn(fabs(x), r.y) < 15.0) v = r.cw * weideman_re(x, r.y);
-            else v = cheap_term<false>(om, r.sg0, r.a, r.ah, r.m, r.c, 0.0);
-            s_acc2[i] += v;
+      auto core_steps = [&](int t0, auto NHc) {
+        // NH steps of 32 (record, point) pairs at once: NH independent series per lane
+        constexpr int NH = decltype(NHc)::value;
+        int ii[NH];
+        double vv[NH];
+        bool ok[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const int t = t0 + 32 * h + lane;
+          ok[h] = t < total;
+          int r = 0;                                 // number of records whose inclusive count is <= t
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, incl, r + sft - 1);
+            if (v <= t) r += sft;
           }
+          r = min(r, 31);
+          ii[h] = __shfl_sync(0xffffffffu, cs, r) + (t - __shfl_sync(0xffffffffu, excl, r));
+          const SegRec& rec = recs[r];
+          const int ic = ok[h] ? ii[h] : own_lo;
+          vv[h] = rec.cw * weideman_re(__dmul_rn(s_grid[ic] - rec.sg0, rec.cte), rec.y);
+        }
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const int i = ii[h];
+          const bool valid = ok[h];
+          const double v = valid ? vv[h] : 0.0;
+          const unsigned peers = __match_any_sync(0xffffffffu, valid ? i : TILE + lane);
+          const int gmax = __reduce_max_sync(0xffffffffu, __popc(peers));
+          double sum = 0.0;
+          unsigned pm = peers;
+#pragma unroll 1
+          for (int k = 0; k < gmax; ++k) {
+            const int src = pm ? __ffs(pm) - 1 : lane;
+            const double val = __shfl_sync(0xffffffffu, v, src);
+            if (pm) sum += val;
+            pm &= pm - 1;
+          }
+          if (valid && lane == __ffs(peers) - 1) s_acc2[i] += sum;
           __syncwarp();
         }
-        continue;
-      }
+      };
+      int t0 = 0;
 #pragma unroll 1
-      for (int t0 = 0; t0 < total; t0 += 32) {
-        const int t = t0 + lane;
-        const bool valid = t < total;
-        int r = 0;                                   // number of records whose inclusive count is <= t
-#pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) {
-          const int v = __shfl_sync(0xffffffffu, incl, r + sft - 1);
-          if (v <= t) r += sft;
-        }
-        r = min(r, 31);
-        const int i = __shfl_sync(0xffffffffu, ss, r) + (t - __shfl_sync(0xffffffffu, excl, r));
-        double v = 0.0;
-        if (valid) {
-          const SegRec& rec = recs[r];
-          const double om = s_grid[i];
-          const double sg0 = rec.sg0, y = rec.y;
-          const double x = __dmul_rn(om - sg0, rec.cte);
-          if (__dadd_rn(fabs(x), y) < 15.0) v = rec.cw * weideman_re(x, y);
-          else v = cheap_term<false>(om, sg0, rec.a, rec.ah, rec.m, rec.c, 0.0);
-        }
-        const unsigned peers = __match_any_sync(0xffffffffu, valid ? i : TILE + lane);
-        const int gmax = __reduce_max_sync(0xffffffffu, __popc(peers));
-        double sum = 0.0;
-        unsigned pm = peers;
+      for (; RTX_P2_ILP == 2 && t0 + 32 < total; t0 += 64) core_steps(t0, std::integral_constant<int, RTX_P2_ILP>{});
 #pragma unroll 1
-        for (int k = 0; k < gmax; ++k) {
-          const int src = pm ? __ffs(pm) - 1 : lane;
-          const double val = __shfl_sync(0xffffffffu, v, src);
-          if (pm) sum += val;
-          pm &= pm - 1;
-        }
-        if (valid && lane == __ffs(peers) - 1) s_acc2[i] += sum;
-        __syncwarp();
-      }
+      for (; t0 < total; t0 += 32) core_steps(t0, std::integral_constant<int, 1>{});
     }
   };
 

@@ -52,9 +52,8 @@ def main():
     # per-layer groups of config 2
     for name, sl in (("layers 0-9", slice(0, 10)), ("layers 10-29", slice(10, 30)), ("layers 30-49", slice(30, 50)),
                      ("layers 50-65", slice(50, 66))):
-        for K in (8,):
+        for K in (8, 4, 2):
             cases.append((name + " K=%d" % K, dict(flags=K << 8), T[sl], pd[sl], wd[sl].contiguous()))
-            cases.append((name + " K=%d ws" % K, dict(flags=4 | (K << 8)), T[sl], pd[sl], wd[sl].contiguous()))
     for name, kw, Tt, pp, ww in cases:
         if only is not None and only not in name.replace(" ", "_"):
             continue
