@@ -291,6 +291,33 @@ def absorption_coefficient_lorentz(cols, T=296.0, p=1.0, OmegaGrid=None, OmegaWi
     return Omegas, Xsect
 
 
+def absorption_coefficient_doppler(cols, T=296.0, p=1.0, OmegaGrid=None, OmegaWing=0.0, OmegaWingHW=50.0,
+                                   IntensityThreshold=0.0, HITRAN_units=True, LineShift=True, Components=None):
+    """absorptionCoefficient_Doppler, misc/hapi.py:11384-11550: GammaD from the driver's own SI constants
+    (:11533-11537), wing = max(OmegaWing, HW*GammaD) (:11540), Shift0 = delta_air*p/pref when LineShift (:11543),
+    PROFILE_DOPPLER (:10152-10160) with hapi's truncated cLn2 / cSqrtLn2divSqrtPi (:89-90)."""
+    Omegas = np.sort(np.asarray(OmegaGrid, dtype=float))
+    Xsect = np.zeros(Omegas.size)
+    factor = 1.0 if HITRAN_units else volume_concentration(p, T)
+    st = line_state(cols, T, p, None, "gamma_air", Components, IntensityThreshold, OmegaWing, OmegaWingHW)
+    nu, S, ampl, keep = (st[k] for k in ("nu", "S", "ampl", "keep"))
+    t = tables()
+    mass = np.array([t["iso_mass"][t["index"][(int(m), int(i))]] for m, i in zip(cols["molec_id"], cols["local_iso_id"])])
+    GammaD = (1.1774100225 / 2.99792458e8) * np.sqrt(1.3806503e-23 / 1.66053873e-27) * np.sqrt(T) * nu / np.sqrt(mass)
+    Sh = np.asarray(cols["delta_air"], dtype=float) * p / 1.0 if LineShift else np.zeros_like(nu)
+    W = np.maximum(OmegaWing, OmegaWingHW * GammaD)
+    lo_all = np.searchsorted(Omegas, nu - W, side="right")
+    hi_all = np.searchsorted(Omegas, nu + W, side="right")
+    for r in np.nonzero(keep)[0]:
+        lo, hi = int(lo_all[r]), int(hi_all[r])
+        if hi <= lo:
+            continue
+        sg = Omegas[lo:hi]
+        V = 0.469718639319144059835 * np.exp(-0.6931471805599 * ((sg - (nu[r] + Sh[r])) / GammaD[r]) ** 2) / GammaD[r]
+        Xsect[lo:hi] += factor * ampl[r] * S[r] * V
+    return Omegas, Xsect
+
+
 def count_evals(cols, T, p, Omegas, **kw):
     """Exact number of (line, grid-point) pairs inside hapi's window for one (T, p)."""
     st = line_state(cols, T, p, **kw)

@@ -93,6 +93,7 @@ struct VoigtParams {
   double* out;
   int has_self, has_deltap, use_tma;
   int lorentz;   // PROFILE_LORENTZ instead of PROFILE_VOIGT: no Doppler width, wing = max(OmegaWing, HW*Gamma0)
+  int doppler;   // PROFILE_DOPPLER (absorptionCoefficient_Doppler): 1 = with line shift, 2 = LineShift=False
 };
 
 // Everything the reference derives for one line at one (T, p): misc/hapi.py:11058-11131.
@@ -129,10 +130,15 @@ __device__ __forceinline__ LineState line_state(const VoigtParams& P, int64_t li
     if (P.has_deltap) d += P.deltap_self[li] * (T - RTX_TREF);
     sh += P.x_self * (d * p);
   }
+  if (P.doppler) {                                               // misc/hapi.py:11510-11546 (Doppler driver)
+    g0 = 0.0;
+    sh = (P.doppler == 1) ? P.delta_air[li] * p : 0.0;           // Shift0DB*p/pref, air only, no T dependence
+  }
   L.gam0 = g0;
   L.nu = nu;
   L.sg0 = nu + sh;
-  L.W = P.lorentz ? fmax(P.wing_abs, P.wing_hw * g0)                  // misc/hapi.py:11375 (Lorentz driver)
+  L.W = P.doppler ? fmax(P.wing_abs, P.wing_hw * L.gamD)         // :11540
+      : P.lorentz ? fmax(P.wing_abs, P.wing_hw * g0)                  // misc/hapi.py:11375 (Lorentz driver)
                   : fmax(fmax(P.wing_abs, P.wing_hw * g0), P.wing_hw * L.gamD);  // :11131
   L.amp = wgt * S;
   return L;
@@ -277,6 +283,7 @@ struct PrepParams {
   double *st_q, *st_d, *st_wb;
   double x_air, x_self, wing_abs, wing_hw;
   double nu_max, gair_max, gself_max, nair_min, nair_max, nself_min, nself_max;
+  int doppler;
 };
 
 __global__ void state_prep_kernel(PrepParams P) {
@@ -289,7 +296,9 @@ __global__ void state_prep_kernel(PrepParams P) {
     const double Q = ok ? tips_lagrange(T, P.tipsT, P.q + (int64_t)j * RTX_TIPS_NPT, RTX_TIPS_NPT) : nan("");
     P.st_q[(int64_t)s * P.n_iso + j] = P.qref[j] / Q;
     const double m = P.mass[j] * RTX_CMASS * 1000.0;
-    const double d = sqrt(2.0 * RTX_CBOLTZ * T * RTX_LN2 / m / (RTX_CLIGHT * RTX_CLIGHT));
+    // the Doppler driver has its own constants (SI, cSqrt2Ln2 = 1.1774100225): misc/hapi.py:11533-11537
+    const double d = P.doppler ? (1.1774100225 / 2.99792458e8) * sqrt(1.3806503e-23 / RTX_CMASS) * sqrt(T) / sqrt(P.mass[j])
+                               : sqrt(2.0 * RTX_CBOLTZ * T * RTX_LN2 / m / (RTX_CLIGHT * RTX_CLIGHT));
     P.st_d[(int64_t)s * P.n_iso + j] = d;
     dmax = fmax(dmax, d);
   }
@@ -516,7 +525,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K <= RTX_K4
             sr.y = y;
             sr.cw = L.amp * (cte / RTX_SQRT_PI);
             int clo = lo, chi = lo;                                        // empty Weideman core
-            if (y < 15.0) {
+            if (y < 15.0 && !P.doppler) {
               // the mask |x|+y<15 is a contiguous index range around sg0; find it with the exact predicate
               // (exact predicate of hum1_wei; it is monotone on either side of sg0, so each end is found by a
               // short walk from the arithmetic estimate sg0 -+ (15-y)/cte, with bisection as the fallback)
@@ -563,7 +572,13 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K <= RTX_K4
               }
             }
             sr.cs = (short)clo; sr.ce = (short)chi;
-            if (hi - lo <= NARROW_MAX) {
+            if (P.doppler) {
+              // cSqrtLn2divSqrtPi*exp(-cLn2*((sg-sg0)/GamD)**2)/GamD (misc/hapi.py:10160, hapi's truncated constants):
+              // the whole window is a "core" of pass 2, evaluated with exp instead of the rational series
+              sr.cte = 0.8325546111576705 / L.gamD;     // sqrt(cLn2), cLn2 = 0.6931471805599
+              sr.cw = L.amp * 0.469718639319144059835 / L.gamD;
+              has_seg = true; sr.s = sr.cs = (short)lo; sr.e = sr.ce = (short)hi;
+            } else if (hi - lo <= NARROW_MAX) {
               has_seg = true; sr.s = (short)lo; sr.e = (short)hi;
             } else {
               is_wide = true;
@@ -775,7 +790,8 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K <= RTX_K4
           ii[h] = __shfl_sync(0xffffffffu, cs, r) + (t - __shfl_sync(0xffffffffu, excl, r));
           const SegRec& rec = recs[r];
           const int ic = ok[h] ? ii[h] : own_lo;
-          vv[h] = rec.cw * weideman_re(__dmul_rn(s_grid[ic] - rec.sg0, rec.cte), rec.y);
+          const double x = __dmul_rn(s_grid[ic] - rec.sg0, rec.cte);
+          vv[h] = rec.cw * (P.doppler ? exp(-(x * x)) : weideman_re(x, rec.y));
         }
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
@@ -859,7 +875,7 @@ __global__ void count_kernel(const VoigtParams P, unsigned long long* __restrict
       const int64_t hi = bisect_right_dev64(P.grid, P.nx, L.nu + L.W);
       if (hi > lo) {
         ev = (unsigned long long)(hi - lo);
-        const double cte = RTX_SQRT_LN2 / L.gamD, y = P.lorentz ? 1e300 : L.gam0 * cte;
+        const double cte = RTX_SQRT_LN2 / L.gamD, y = (P.lorentz || P.doppler) ? 1e300 : L.gam0 * cte;
         if (y < 15.0) {
           int64_t m = bisect_left_dev64(P.grid, P.nx, L.sg0);
           m = max(lo, min(hi, m));
@@ -941,6 +957,7 @@ int fill_params(rtx_handle* h, VoigtParams& P, int n_states, const double* T, co
   P.has_deltap = L.has_deltap ? 1 : 0;
   P.use_tma = ((reinterpret_cast<uintptr_t>(grid) & 15u) == 0) ? 1 : 0;
   P.lorentz = 0;
+  P.doppler = 0;
   return RTX_OK;
 }
 
@@ -958,6 +975,7 @@ int run_prep(rtx_handle* h, VoigtParams& P, cudaStream_t st, double** st_wb_out)
   Q.x_air = P.x_air; Q.x_self = P.x_self; Q.wing_abs = P.wing_abs; Q.wing_hw = P.wing_hw;
   Q.nu_max = L.nu_max; Q.gair_max = L.gair_max; Q.gself_max = L.gself_max; Q.nair_min = L.nair_min;
   Q.nair_max = L.nair_max; Q.nself_min = L.nself_min; Q.nself_max = L.nself_max;
+  Q.doppler = P.doppler;
   state_prep_kernel<<<(P.n_states + 127) / 128, 128, 0, st>>>(Q);
   RTX_CUDA(cudaGetLastError());
   h->launches++;
@@ -987,6 +1005,8 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
   if (rc) return rc;
   P.out = out_dev;
   P.lorentz = (flags & RTX_VOIGT_LORENTZ) ? 1 : 0;
+  P.doppler = (flags & RTX_VOIGT_DOPPLER) ? ((flags & RTX_VOIGT_NOSHIFT) ? 2 : 1) : 0;
+  RTX_REQUIRE(!(P.lorentz && P.doppler), "RTX_VOIGT_LORENTZ and RTX_VOIGT_DOPPLER are exclusive");
   double* st_wb = nullptr;
   rc = run_prep(h, P, st, &st_wb);
   if (rc) return rc;

@@ -78,3 +78,46 @@ def generate_LWIR_TUD(T, H2O, O3, CO2, Xmin=690, Xmax=1410, DV=0.0005, DV_out=0.
         Las.append(R[:, k:2 * k].reshape(-1, na, nAlt).permute(0, 2, 1).cpu().numpy())
         Lds.append(R[:, 2 * k:].cpu().numpy())
     return X_out, np.concatenate(ODs, axis=2), np.concatenate(Las, axis=2), np.concatenate(Lds, axis=1)
+
+
+# Dataset attributes of the reference's HDF5 product (Generate_LWIR_TUD.py:157-221): units / name / info / label
+TUD_DATASET_ATTRS = {
+    "X": ("cm^{-1}", "Wavenumbers", "Spectral axis for tau, La, Ld", r"$\tilde{\nu} \,\, \left[\si{cm^{-1}} \right]$"),
+    "OD": ("none", "Optical Depth", "For nadir-viewing path. tau = np.exp(-OD)", r"$\tau(\tilde{\nu})$"),
+    "La": ("µW/(cm^2 sr cm^{-1})", "Atmospheric Path Spectral Radiance", "For nadir-viewing path, earth-to-space",
+           r"$L_a(\tilde{\nu})\,\,\left[\si{\micro W/(cm^2.sr.cm^{-1})}\right]$"),
+    "Ld": ("µW/(cm^2 sr cm^{-1})", "Atmospheric Downwelling Spectral Radiance", "Hemispherically-averaged, space-to-earth",
+           r"$L_d(\tilde{\nu})\,\,\left[\si{\micro W/(cm^2.sr.cm^{-1})}\right]$"),
+    "SensorAltitude": ("km", "Sensor Altitude", "Sensor height above surface", r"$z_s \,\, \left[ \si{km} \right]$"),
+    "StdAtmos": ("N.A.", "Standard Atmosphere Table", "1976 US Std. Atmos. with CO2 scaled to modern value", r"N.A."),
+    "z": ("km", "Altitude", "z=0 at sea level", r"$z \,\, \left[ \si{km} \right]$"),
+    "T": ("K", "Temperature profile", "", r"$T(z) \,\, \left[ \si{K} \right]$"),
+    "P": ("Pa", "Pressure profile", "", r"$P(z) \,\, \left[ \si{Pa} \right]$"),
+    "H2O": ("ppmv", "Water vapor VMR profile", "VMR - volume mixing ratio", r"$\mathrm{H_2O}(z)\,\,\left[\mathrm{ppm}_v\right]$"),
+    "O3": ("ppmv", "Ozone VMR profile", "VMR - volume mixing ratio", r"$\mathrm{O_3}(z)\,\,\left[\mathrm{ppm}_v\right]$"),
+}
+
+
+def save_LWIR_TUD_npz(fname, X, OD, La, Ld, Altitudes):
+    """The checkpoint file the reference rewrites after every batch (Generate_LWIR_TUD.py:150): same keys."""
+    np.savez(fname, X=X, OD=OD, La=La, Ld=Ld, Altitudes=Altitudes)
+
+
+def load_LWIR_TUD_npz(fname):
+    with np.load(fname) as f:
+        return {k: f[k] for k in ("X", "OD", "La", "Ld", "Altitudes")}
+
+
+def save_LWIR_TUD_h5(fname, X, OD, La, Ld, Altitudes, StdAtmos, z, T, P, H2O, O3):
+    """The reference's HDF5 product (Generate_LWIR_TUD.py:152-223): one dataset per array with units / name / info /
+    label attributes.  Needs h5py, which the reference also needs; there is no hand-written HDF5 encoder here."""
+    try:
+        import h5py
+    except ImportError as e:                                            # pragma: no cover - h5py is not in this image
+        raise ImportError("save_LWIR_TUD_h5 needs h5py (as Generate_LWIR_TUD.py does); use save_LWIR_TUD_npz") from e
+    data = dict(X=X, OD=OD, La=La, Ld=Ld, SensorAltitude=Altitudes, StdAtmos=StdAtmos, z=z, T=T, P=P, H2O=H2O, O3=O3)
+    with h5py.File(fname, "w") as hf:
+        for key, arr in data.items():
+            d = hf.create_dataset(key, data=arr)
+            for attr, val in zip(("units", "name", "info", "label"), TUD_DATASET_ATTRS[key]):
+                d.attrs[attr] = val

@@ -166,6 +166,8 @@ def absorptionCoefficient_Voigt(Components=None, SourceTables=None, partitionFun
     w_iso = db.iso_factors(comps, factor)
 
     GammaL = GammaL.lower()
+    if int(_profile_flags) & 32:
+        Diluent = {'air': 1.}        # the Doppler driver has no pressure broadening; GammaL='dummy' is ignored
     if not Diluent:
         if GammaL == 'gamma_air': Diluent = {'air': 1.}
         elif GammaL == 'gamma_self': Diluent = {'self': 1.}
@@ -211,3 +213,27 @@ def absorptionCoefficient_Lorentz(*args, **kwargs):
     max(OmegaWing, OmegaWingHW*Gamma0) (:11375)."""
     kwargs["_profile_flags"] = 16          # RTX_VOIGT_LORENTZ
     return absorptionCoefficient_Voigt(*args, **kwargs)
+
+
+def absorptionCoefficient_Doppler(Components=None, SourceTables=None, partitionFunction=PYTIPS, Environment=None,
+                                  OmegaRange=None, OmegaStep=None, OmegaWing=None,
+                                  IntensityThreshold=DefaultIntensityThreshold, OmegaWingHW=DefaultOmegaWingHW,
+                                  ParameterBindings=None, EnvironmentDependencyBindings=None, GammaL='dummy',
+                                  HITRAN_units=True, LineShift=True, File=None, Format=None, OmegaGrid=None,
+                                  WavenumberRange=None, WavenumberStep=None, WavenumberWing=None,
+                                  WavenumberWingHW=None, WavenumberGrid=None):
+    """Doppler (Gauss) profile driver of hapi (misc/hapi.py:11384-11550): profile
+    cSqrtLn2divSqrtPi*exp(-cLn2*((omega-nu0-shift)/GammaD)**2)/GammaD (:10152-10160) with the driver's own SI constants
+    for GammaD (:11533-11537), wing max(OmegaWing, OmegaWingHW*GammaD), shift delta_air*p only when LineShift."""
+    return absorptionCoefficient_Voigt(Components=Components, SourceTables=SourceTables,
+                                       partitionFunction=partitionFunction, Environment=Environment,
+                                       OmegaRange=OmegaRange, OmegaStep=OmegaStep, OmegaWing=OmegaWing,
+                                       IntensityThreshold=IntensityThreshold, OmegaWingHW=OmegaWingHW,
+                                       HITRAN_units=HITRAN_units, File=File, Format=Format, OmegaGrid=OmegaGrid,
+                                       WavenumberRange=WavenumberRange, WavenumberStep=WavenumberStep,
+                                       WavenumberWing=WavenumberWing, WavenumberWingHW=WavenumberWingHW,
+                                       WavenumberGrid=WavenumberGrid,
+                                       _profile_flags=32 | (0 if LineShift else 64))   # RTX_VOIGT_DOPPLER [| NOSHIFT]
+
+
+absorptionCoefficient_Gauss = absorptionCoefficient_Doppler       # misc/hapi.py:11557

@@ -573,3 +573,18 @@ def test_lorentz_profile_golden(mods):
     for k, (T, p, kw) in enumerate(mg.LORENTZ_CASES):
         _, xs = hapi.absorptionCoefficient_Lorentz(SourceTables="lor", Environment={"T": T, "p": p}, OmegaGrid=grid, **kw)
         assert_parity(xs, g["xs%d" % k], RTOL, FLOOR, "Lorentz %d" % k)
+
+
+def test_doppler_profile_golden(mods):
+    """absorptionCoefficient_Doppler against the reference's own outputs (tests/golden/doppler.npz)."""
+    import make_golden as mg
+    hapi, syn = mods["hapi"], mods["syn"]
+    g = golden("doppler.npz")
+    cols = syn.synthetic_lines(91, 80, 1495.0, 1525.0, 1)
+    hapi.storeTable("dop", cols)
+    grid = np.linspace(1500.0, 1520.0, 20001)
+    for k, (T, p, kw) in enumerate(mg.DOPPLER_CASES):
+        _, xs = hapi.absorptionCoefficient_Doppler(SourceTables="dop", Environment={"T": T, "p": p}, OmegaGrid=grid, **kw)
+        ref = np.zeros_like(xs); ref[g["idx%d" % k]] = g["xs%d" % k]
+        assert_parity(xs, ref, RTOL, FLOOR, "Doppler %d" % k)
+    assert hapi.absorptionCoefficient_Gauss is hapi.absorptionCoefficient_Doppler

@@ -157,3 +157,23 @@ def test_jacobian_inputs():
     assert np.array_equal(T[3:], np.tile([280.0, 250.0], (4, 1))) and H[3, 0] == 1e-2 + 1e-5 and O[6, 1] == 1e-6 + 1e-9
     alt = drivers.default_altitudes(70.0)
     assert alt.size == 9 and abs(alt[0] - 0.06096) < 1e-12 and alt[-1] == 70.0
+
+
+def test_lwir_tud_products(tmp_path):
+    """npz checkpoint of the production sweep keeps the reference's keys (Generate_LWIR_TUD.py:150); the HDF5 writer
+    carries the reference's attribute table and refuses loudly without h5py."""
+    from radtxfr_b200 import drivers
+    rng = np.random.default_rng(3)
+    X = np.linspace(700, 1400, 50); OD = rng.random((4, 9, 50)); La = rng.random((4, 9, 50)); Ld = rng.random((4, 50))
+    alt = drivers.default_altitudes(100.0)
+    f = str(tmp_path / "LWIR_TUD.npz")
+    drivers.save_LWIR_TUD_npz(f, X, OD, La, Ld, alt)
+    back = drivers.load_LWIR_TUD_npz(f)
+    assert sorted(back) == ["Altitudes", "La", "Ld", "OD", "X"]
+    assert np.array_equal(back["OD"], OD) and np.array_equal(back["Altitudes"], alt)
+    assert set(drivers.TUD_DATASET_ATTRS) == {"X", "OD", "La", "Ld", "SensorAltitude", "StdAtmos", "z", "T", "P", "H2O", "O3"}
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            drivers.save_LWIR_TUD_h5(str(tmp_path / "x.h5"), X, OD, La, Ld, alt, OD, X, X, X, X, X)

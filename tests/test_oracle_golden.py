@@ -184,3 +184,14 @@ def test_lorentz():
     for k, (T, p, kw) in enumerate(mg.LORENTZ_CASES):
         _, xs = port.absorption_coefficient_lorentz(cols, T=T, p=p, OmegaGrid=grid, **kw)
         assert_parity(xs, g["xs%d" % k], what="Lorentz %d" % k, **TIGHT)
+
+
+def test_doppler():
+    import make_golden as mg
+    g = golden("doppler.npz")
+    cols = syn.synthetic_lines(91, 80, 1495.0, 1525.0, 1)
+    grid = np.linspace(1500.0, 1520.0, 20001)
+    for k, (T, p, kw) in enumerate(mg.DOPPLER_CASES):
+        _, xs = port.absorption_coefficient_doppler(cols, T=T, p=p, OmegaGrid=grid, **kw)
+        ref = np.zeros_like(xs); ref[g["idx%d" % k]] = g["xs%d" % k]
+        assert_parity(xs, ref, what="Doppler %d" % k, **TIGHT)

@@ -246,6 +246,26 @@ def g_lorentz():
     save("lorentz.npz", source="misc/hapi.py:11144-11381 absorptionCoefficient_Lorentz", **out)
 
 
+DOPPLER_CASES = [(296.0, 1.0, {}), (220.0, 0.05, {"OmegaWingHW": 30.0, "LineShift": False}),
+                 (310.0, 0.6, {"HITRAN_units": False, "OmegaWing": 0.02})]
+
+
+def g_doppler():
+    h = R.hapi()
+    import contextlib, io
+    cols = syn.synthetic_lines(91, 80, 1495.0, 1525.0, 1)
+    R.inject_table("__dop__", cols)
+    grid = np.linspace(1500.0, 1520.0, 20001)
+    out = {}
+    for k, (T, p, kw) in enumerate(DOPPLER_CASES):
+        with contextlib.redirect_stdout(io.StringIO()):
+            _, xs = h.absorptionCoefficient_Doppler(SourceTables="__dop__", Environment={"T": T, "p": p}, OmegaGrid=grid, **kw)
+        nz = np.nonzero(xs)[0]
+        out["idx%d" % k] = nz.astype(np.int32)
+        out["xs%d" % k] = xs[nz]
+    save("doppler.npz", source="misc/hapi.py:11384-11550 absorptionCoefficient_Doppler (non-zero samples of a 20001-point grid)", **out)
+
+
 def mbi_image():
     ii, jj = np.meshgrid(np.arange(40), np.arange(32), indexing="ij")
     img = np.zeros((3, 40, 32), dtype=np.uint8)
@@ -286,6 +306,6 @@ def g_mbi():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi", "lorentz"]
+    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi", "lorentz", "doppler"]
     for w in which:
         globals()["g_" + w]()
