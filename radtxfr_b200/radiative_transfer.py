@@ -42,6 +42,7 @@ options = {
     "Altitudes": np.asarray([500]),
     "save": False,
     "returnOD": False,
+    "continuum_od": None,          # optional additive layer optical depth (array or callable), see _add_continuum
     # --- additions of this implementation -----------------------------------------------------
     "LINE_DB": None,        # engine.LineDB, set through set_line_database()
     "voigt": {},            # extra Voigt settings: OmegaWing, OmegaWingHW, IntensityThreshold, Diluent, and
@@ -172,6 +173,24 @@ def layer_weights(db, T, P_pa, PL_km, MF_VAL, MF_ID):
     return p, w
 
 
+def _add_continuum(od, opts, X, T, P, PL, MF, ID):
+    """Optional continuum hook (the reference gets its continuum, MT_CKD, from inside LBLRTM and only passes
+    `continuum_factors` through, radiative_transfer.py:162-163, 530, 590-672; there is no continuum model here):
+    opts["continuum_od"] is an array broadcastable to the layer optical depths [nL, nX], or a callable
+    (X, Ts, Ps, PLs, MFs_VAL, MFs_ID) -> such an array (numpy or a torch tensor on the device); it is added to the
+    line-by-line optical depth on the device before the layer integration."""
+    c = opts.get("continuum_od")
+    if c is None:
+        return od
+    if callable(c):
+        c = c(X, T, P, PL, MF, ID)
+    c = engine.to_device(c, od.device)
+    if c.dim() == 1 and c.numel() == od.shape[0] and od.shape[0] != od.shape[-1]:
+        c = c[:, None]                                   # one value per layer
+    od += c                                              # broadcasts [nL, nX], [nX], [nL, 1] or a scalar
+    return od
+
+
 def _require_db(opts):
     db = opts.get("LINE_DB")
     if db is None:
@@ -220,6 +239,8 @@ def compute_TUD(Xmin, Xmax, opts=options, **kwargs):
     Td, pd, wd = (engine.to_device(a, db.device) for a in (T, p, w))
     od = db.voigt_sum(Td, pd, wd, grid, out=_od_workspace(db.device, T.size, nX),
                       **_voigt_settings(opts))                                  # [nL, nX], layer-major
+    if opts.get("continuum_od") is not None:
+        od = _add_continuum(od, opts, X_ if X_ is not None else grid, T, P, PL, MF, ID)
     tau, lu, ld = engine.tud(od, Td[None, :], grid, Z, Z_s, mu_s, nA, returnOD)
     # the kernels are in flight: build the host axis and pre-touch the result arrays meanwhile
     if X_ is None:

@@ -588,3 +588,28 @@ def test_doppler_profile_golden(mods):
         ref = np.zeros_like(xs); ref[g["idx%d" % k]] = g["xs%d" % k]
         assert_parity(xs, ref, RTOL, FLOOR, "Doppler %d" % k)
     assert hapi.absorptionCoefficient_Gauss is hapi.absorptionCoefficient_Doppler
+
+
+def test_continuum_hook(mods):
+    """opts['continuum_od'] (array or callable) is added to the layer optical depths before the layer integration:
+    a per-layer constant c_l scales the transmittance by exp(-sum of c_l below the sensor), and the result equals the
+    oracle's layer integration of OD + continuum."""
+    rt, port = mods["rt"], mods["port"]
+    atm, tabs, opts, kw = _tud_setup(mods)
+    nL = atm["Ts"].size
+    X, OD0, _, _ = rt.compute_TUD(700.0, 720.0, opts=dict(opts), returnOD=True, Altitudes=np.array([500.0]), **kw)
+    c_layer = 1e-3 * (1.0 + np.arange(nL))
+    Xc, ODc, Luc, Ldc = rt.compute_TUD(700.0, 720.0, opts=dict(opts), returnOD=True, Altitudes=np.array([500.0]),
+                                       continuum_od=c_layer, **kw)
+    assert_parity(ODc, OD0 + c_layer.sum(), RTOL, FLOOR, "OD with per-layer continuum")
+    ramp = np.linspace(0.0, 0.01, X.size)
+    calls = []
+
+    def cont(Xg, Ts, Ps, PLs, MF, ID):
+        calls.append(np.asarray(Ts).size)
+        return np.outer(np.ones(nL), ramp)
+
+    Xf, ODf, _, _ = rt.compute_TUD(700.0, 720.0, opts=dict(opts), returnOD=True, Altitudes=np.array([500.0]),
+                                   continuum_od=cont, **kw)
+    assert calls == [nL]
+    assert_parity(ODf, OD0 + nL * ramp, RTOL, FLOOR, "OD with callable continuum")
