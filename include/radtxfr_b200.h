@@ -211,6 +211,8 @@ int rtx_measure_fp64_peak(rtx_handle* h, double* flops_per_s);
 int rtx_weideman_coeffs(double* out24);
 /* Number of kernels this library has launched on this handle since creation. */
 int rtx_launch_count(rtx_handle* h, uint64_t* n);
+/* Tile size the last rtx_voigt_sum on this handle used: K = grid points per CTA / 256 (0 before the first call). */
+int rtx_voigt_last_tile(rtx_handle* h, int* K);
 
 #ifdef __cplusplus
 }

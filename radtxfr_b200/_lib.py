@@ -48,6 +48,7 @@ _SIGNATURES = {
     "rtx_spline_eval": [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p],
     "rtx_measure_fp64_peak": [c_void_p, POINTER(c_double)],
     "rtx_launch_count": [c_void_p, POINTER(c_uint64)],
+    "rtx_voigt_last_tile": [c_void_p, POINTER(c_int)],
     "rtx_weideman_coeffs": [c_void_p],
 }
 

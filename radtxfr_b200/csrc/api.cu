@@ -57,6 +57,7 @@ extern "C" int rtx_destroy(rtx_handle* h) {
   free_lines(h->lines);
   for (double* p : {h->d_mass, h->d_tipsT, h->d_q, h->d_qref, h->d_state}) if (p) cudaFree(p);
   if (h->d_bins) cudaFree(h->d_bins);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
   delete h;
   return RTX_OK;
 }
@@ -98,6 +99,12 @@ extern "C" int rtx_stream_sync(rtx_handle* h, void* stream) {
   RTX_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   return RTX_OK;
 }
+extern "C" int rtx_voigt_last_tile(rtx_handle* h, int* K) {
+  RTX_REQUIRE(h && K, "rtx_voigt_last_tile: null pointer");
+  *K = h->last_K;
+  return RTX_OK;
+}
+
 extern "C" int rtx_launch_count(rtx_handle* h, uint64_t* n) {
   RTX_REQUIRE(h && n, "rtx_launch_count: null pointer");
   *n = h->launches;

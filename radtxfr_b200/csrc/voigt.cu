@@ -45,8 +45,15 @@ constexpr int NT = 256;         // threads per CTA
 #ifndef RTX_P2_ILP
 #define RTX_P2_ILP 2
 #endif
-#ifndef RTX_K4MAX
-#define RTX_K4MAX 0
+// K = 4 (1024-point tiles, 46 KB of shared memory) is compiled for four CTAs per SM (64 registers): the regime it is
+// chosen for -- windows of a few hundred grid points -- is latency- and issue-bound, not register-bound.
+#ifndef RTX_MINBLOCKS_K4
+#define RTX_MINBLOCKS_K4 4
+#endif
+// eval-weighted mean window half-width (in grid points) below which K = 4 beats K = 8 (measured: coarse-grid batch
+// of config 3, ~350 points: K = 4 is 9 % faster; config 2, ~3000 points: K = 8 is 9 % faster)
+#ifndef RTX_K4_WINDOW
+#define RTX_K4_WINDOW 1200.0
 #endif
 #ifndef RTX_MINBLOCKS
 #define RTX_MINBLOCKS 3
@@ -310,6 +317,24 @@ __global__ void state_prep_kernel(PrepParams P) {
   P.st_wb[s] = wb * (1.0 + 1e-6) + 1e-9;
 }
 
+// eval-weighted mean of the per-state wing bound in grid points: sum(wb^2)/sum(wb) / mean grid spacing
+__global__ void window_stats_kernel(int n_states, const double* __restrict__ st_wb, const double* __restrict__ grid,
+                                    int64_t nx, double* __restrict__ out) {
+  __shared__ double s1[256], s2[256];
+  double a = 0.0, b = 0.0;
+  for (int s = threadIdx.x; s < n_states; s += 256) { const double w = st_wb[s]; a += w * w; b += w; }
+  s1[threadIdx.x] = a; s2[threadIdx.x] = b;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if (threadIdx.x < d) { s1[threadIdx.x] += s1[threadIdx.x + d]; s2[threadIdx.x] += s2[threadIdx.x + d]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double dv = nx > 1 ? (grid[nx - 1] - grid[0]) / (double)(nx - 1) : 0.0;
+    out[0] = (s2[0] > 0.0 && dv > 0.0) ? (s1[0] / s2[0]) / dv : 1e300;
+  }
+}
+
 __global__ void tips_kernel(int n, int n_iso, const double* __restrict__ T, const double* __restrict__ tipsT,
                             const double* __restrict__ q, double* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -396,7 +421,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
 // WS = warp-specialised variant: NPW extra producer warps run the prologue one chunk ahead (double-buffered
 // records, mbarrier full/empty handshake); the eight consumer warps never meet at a block-wide barrier.
 template <int K, int MODE, bool WS>
-__global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K <= RTX_K4MAX ? 4 : RTX_MINBLOCKS)) voigt_tile_kernel(const VoigtParams P) {
+__global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RTX_MINBLOCKS_K4 : RTX_MINBLOCKS)) voigt_tile_kernel(const VoigtParams P) {
   constexpr bool FAST = (MODE == 1);
   constexpr bool F32 = (MODE == 2);
   constexpr int TILE = K * NT;
@@ -963,7 +988,7 @@ int fill_params(rtx_handle* h, VoigtParams& P, int n_states, const double* T, co
 
 int run_prep(rtx_handle* h, VoigtParams& P, cudaStream_t st, double** st_wb_out) {
   const size_t per = (size_t)P.n_states * P.n_iso;
-  int rc = ensure_scratch(h, 2 * per + P.n_states, h->bins_cap);
+  int rc = ensure_scratch(h, 2 * per + P.n_states + 2, h->bins_cap);
   if (rc) return rc;
   double* st_q = h->d_state;
   double* st_d = st_q + per;
@@ -1017,7 +1042,21 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
     if (tiles * n_states >= 4LL * h->sm_count) { K = k; break; }
   }
   const int forced = (flags >> RTX_VOIGT_TILE_SHIFT) & 0xF;   // test hook: force the tile size
-  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) K = forced;
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) {
+    K = forced;
+  } else if (K == 8) {
+    // narrow windows (coarse grids, low pressures): smaller slices turn partial visits into test-free ones and
+    // four CTAs per SM hide the per-visit latency.  One 8-byte read-back decides; it waits only for state_prep.
+    if (!h->h_pin) RTX_CUDA(cudaMallocHost(&h->h_pin, 2 * sizeof(double)));
+    double* stat = st_wb + n_states;
+    window_stats_kernel<<<1, 256, 0, st>>>(n_states, st_wb, grid_dev, nx, stat);
+    RTX_CUDA(cudaGetLastError());
+    h->launches++;
+    RTX_CUDA(cudaMemcpyAsync(h->h_pin, stat, sizeof(double), cudaMemcpyDeviceToHost, st));
+    RTX_CUDA(cudaStreamSynchronize(st));
+    if (h->h_pin[0] < RTX_K4_WINDOW) K = 4;
+  }
+  h->last_K = K;
   const int tile_pts = K * NT;
   P.n_tiles = (int)((nx + tile_pts - 1) / tile_pts);
   const size_t nb = (size_t)P.n_tiles * n_states;

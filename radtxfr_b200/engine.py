@@ -102,6 +102,12 @@ class Handle:
         _lib.call("rtx_launch_count", self._h, ctypes.byref(n))
         return int(n.value)
 
+    def last_tile(self):
+        """K (grid points per CTA / 256) of the last voigt_sum on this handle."""
+        k = ctypes.c_int()
+        _lib.call("rtx_voigt_last_tile", self._h, ctypes.byref(k))
+        return int(k.value)
+
     def device_info(self):
         sm = ctypes.c_int()
         buf = ctypes.create_string_buffer(256)

@@ -613,3 +613,23 @@ def test_continuum_hook(mods):
                                    continuum_od=cont, **kw)
     assert calls == [nL]
     assert_parity(ODf, OD0 + nL * ramp, RTOL, FLOOR, "OD with callable continuum")
+
+
+def test_voigt_automatic_tile_size(mods):
+    """Automatic tile size: 2048-point tiles when the windows are thousands of grid points wide (fine grid, low
+    layers), 1024-point tiles at four CTAs per SM when they are a few hundred (coarse grid) -- decided from the
+    eval-weighted mean wing bound in grid points (rtx_voigt_last_tile reports the choice).  Either way parity holds."""
+    port, syn, engine = mods["port"], mods["syn"], mods["engine"]
+    cols = syn.synthetic_lines(57, 300, 940.0, 1060.0, 1)
+    db = engine.LineDB(cols)
+    nS = 80                                      # enough (tile, state) pairs for 2048-point tiles on both grids
+    T = np.linspace(296.0, 220.0, nS); p = np.geomspace(1.0, 0.05, nS)
+    w = np.tile(db.iso_factors(None, 1.0), (nS, 1))
+    picked = {}
+    for name, grid in (("fine", np.linspace(950.0, 1050.0, 100001)), ("coarse", np.linspace(950.0, 1050.0, 20001))):
+        out = db.voigt_sum(T, p, w, grid).cpu().numpy()
+        picked[name] = db.handle.last_tile()
+        for k in (0, nS - 1):
+            _, ref = port.absorption_coefficient_voigt(cols, T=T[k], p=p[k], OmegaGrid=grid)
+            assert_parity(out[k], ref, RTOL, FLOOR, "%s grid state %d" % (name, k))
+    assert picked == {"fine": 8, "coarse": 4}, picked
