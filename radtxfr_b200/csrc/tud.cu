@@ -13,7 +13,36 @@
 namespace {
 
 constexpr int TUD_THREADS = 128;
-constexpr int ANGLE_BLOCK = 8;
+constexpr int ANGLE_BLOCK = 10;
+// exp constants: 256/ln2, 1.5*2^52, -(ln2/256) high and low parts, 1/24, 1/6
+__constant__ double c_exp[6] = {369.3299304675746, 6755399441055744.0, -0.00270760617331689, -7.453964567463233e-13,
+                                4.1666666666666664e-02, 1.6666666666666666e-01};
+
+// exp(x) for |x| < 700 by the same table-driven scheme as the angle loop below (1-2 ulp): k = rint(256 x/ln2),
+// r = x - k ln2/256, degree-4 polynomial, 2^(j/256) from the shared table, 2^m through the exponent field.
+__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
+  const double tt = fma(x, c_exp[0], c_exp[1]);
+  const double nf = tt - c_exp[1];
+  double r = fma(nf, c_exp[2], x);
+  r = fma(nf, c_exp[3], r);
+  double pz = fma(r, c_exp[4], c_exp[5]);
+  pz = fma(pz, r, 0.5);
+  pz = fma(pz, r, 1.0);
+  const int k = __double2loint(tt);
+  const double tj = tab[k & 255];
+  const double t = fma(tj, pz * r, tj);
+  return __hiloint2double(__double2hiint(t) + ((k >> 8) << 20), __double2loint(t));
+}
+// Planck radiance (radiative_transfer.py:841-843) from per-point and per-layer factors: c1X3 = c1*X^3, c2X = c2*X
+// (X = 100 nu), invT = 1/T; the quotient is a Newton-refined reciprocal (full double precision).
+__device__ __forceinline__ double planck_fast(double c1X3, double c2X, double invT, const double* __restrict__ tab) {
+  const double d = exp_tab(fmin(c2X * invT, 700.0), tab) - 1.0;
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+  const double e = fma(-d, r0, 1.0);
+  const double q = fma(r0, fma(e, e, e), r0);
+  return c1X3 * q * 1e4;
+}
 
 struct TudParams {
   int n_atm, n_layers, n_alt, n_mu, n_angle, n_down, return_od, max_cnt;
@@ -29,8 +58,10 @@ struct TudParams {
 };
 
 __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) {
-  __shared__ double s_exp2[64];                       // 2^(j/64), correctly rounded by exp2()
-  if (threadIdx.x < 64) s_exp2[threadIdx.x] = exp2((double)threadIdx.x * 0.015625);
+  __shared__ double s_exp2[256];                      // 2^(j/256), correctly rounded by exp2()
+  __shared__ double s_invT[RTX_MAX_LAYERS];           // 1/T of this block's atmosphere
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_exp2[i] = exp2((double)i * 0.00390625);
+  for (int i = threadIdx.x; i < P.n_layers; i += blockDim.x) s_invT[i] = 1.0 / P.T[(int64_t)blockIdx.y * P.n_layers + i];
   __syncthreads();
   const int64_t x = (int64_t)blockIdx.x * TUD_THREADS + threadIdx.x;
   if (x >= P.nx) return;
@@ -38,7 +69,8 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
   const int atm = blockIdx.y;
   const double nu = P.grid[x];
   const double* __restrict__ od = P.od + ((int64_t)atm * P.n_layers) * P.nx + x;
-  const double* __restrict__ T = P.T + (int64_t)atm * P.n_layers;
+  const double X100 = nu * 100.0;
+  const double c1X3 = RTX_RT_C1 * (X100 * X100 * X100), c2X = RTX_RT_C2 * X100;
   const int64_t obase = ((int64_t)atm * P.nx + x) * P.n_alt * P.n_mu;
 
   // ---- upwelling: Lu <- t*Lu + (1-t)*B_k bottom-up, snapshot at every altitude's layer count
@@ -50,9 +82,9 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
       if (P.cnt[a] == 0) P.lu[obase + (int64_t)a * P.n_mu + m] = 0.0;
     for (int k = 0; k < P.max_cnt; ++k) {
       const double o = od[(int64_t)k * P.nx];
-      const double B = planck_wn(nu, T[k]);
-      const double t = exp(-o * mu);
-      lu = t * lu + (1.0 - t) * B;
+      const double B = planck_fast(c1X3, c2X, s_invT[k], s_exp2);
+      const double t = exp_tab(fmax(-o * mu, -708.0), s_exp2);
+      lu = fma(t, lu - B, B);                                  // t*Lu + (1-t)*B
       for (int a = 0; a < P.n_alt; ++a)
         if (P.cnt[a] == k + 1) P.lu[obase + (int64_t)a * P.n_mu + m] = lu;
     }
@@ -68,8 +100,8 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
   // ---- downwelling: per angle Ld <- t*Ld + (1-t)*B_j top-down, then the cos-weighted hemispheric mean
   //      (radiative_transfer.py:368-373, 387-389).  The transmittances t = exp(-OD/cos th) are >99 % of the
   //      kernel's work, so exp is evaluated for a block of angles at once with the polynomial constants shared:
-  //      table-driven range reduction (64 entries), degree-5 polynomial, scaling through the exponent field;
-  //      11 FP64 operations per value, 1-2 ulp.
+  //      table-driven range reduction (256 entries), degree-4 polynomial, scaling through the exponent field;
+  //      10 FP64 operations per value, 1-2 ulp.
   double ldsum = 0.0;
   for (int a0 = 0; a0 < P.n_angle; a0 += ANGLE_BLOCK) {
     double acc[ANGLE_BLOCK], sec[ANGLE_BLOCK];
@@ -82,7 +114,7 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
     }
     for (int j = P.n_down - 1; j >= 0; --j) {
       const double ao = -fabs(od[(int64_t)j * P.nx]);     // optical depths are non-negative
-      const double B = planck_wn(nu, T[j]);
+      const double B = planck_fast(c1X3, c2X, s_invT[j], s_exp2);
       // optically thin layer for every lane of the warp and every angle of the block (|x| <= 2^-9): the degree-5
       // Taylor polynomial is exact to < 1e-19 and needs no range reduction
       if (__all_sync(lanes, ao * secmax >= -1.953125e-3)) {
@@ -94,38 +126,37 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
           t = fma(t, x, 0.5);
           t = fma(t, x, 1.0);
           t = fma(t, x, 1.0);
-          acc[a] = t * acc[a] + (1.0 - t) * B;
+          acc[a] = fma(t, acc[a] - B, B);
         }
         continue;
       }
-      // general case: exp(x) = 2^m * 2^(j/64) * exp(r),  k = rint(64 x / ln2) = 64 m + j,  r = x - k ln2/64 (two-piece),
-      // |r| <= ln2/128: degree-5 polynomial (truncation 3.5e-17), 2^(j/64) from a shared-memory table.
+      // general case: exp(x) = 2^m * 2^(j/256) * exp(r),  k = rint(256 x / ln2) = 256 m + j,  r = x - k ln2/256
+      // (two-piece), |r| <= ln2/512: degree-4 polynomial (truncation 3.8e-17), 2^(j/256) from a shared-memory table.
+      // The constants sit in constant memory so the FP64 instructions read them as operands.
       double xa[ANGLE_BLOCK], tt[ANGLE_BLOCK], r[ANGLE_BLOCK], pz[ANGLE_BLOCK];
 #pragma unroll
       for (int a = 0; a < ANGLE_BLOCK; ++a) {
-        xa[a] = ao * sec[a];
-        tt[a] = fma(xa[a], 92.33248261689366, 6755399441055744.0);     // 64/ln2; 1.5*2^52 puts k in the low word
+        xa[a] = fmax(ao * sec[a], -708.0);                               // exp(-708) = 3e-308: nothing below matters
+        tt[a] = fma(xa[a], c_exp[0], c_exp[1]);                          // 256/ln2; 1.5*2^52 puts k in the low word
       }
 #pragma unroll
       for (int a = 0; a < ANGLE_BLOCK; ++a) {
-        const double nf = tt[a] - 6755399441055744.0;
-        r[a] = fma(nf, -0.01083042469326756, xa[a]);                     // ln2/64, high part (21 trailing zero bits)
-        r[a] = fma(nf, -2.9815858269852933e-12, r[a]);                   // ln2/64, low part
-        pz[a] = fma(r[a], 8.333333333333333e-03, 4.1666666666666664e-02);
+        const double nf = tt[a] - c_exp[1];
+        r[a] = fma(nf, c_exp[2], xa[a]);                                 // -ln2/256, high part (21 trailing zero bits)
+        r[a] = fma(nf, c_exp[3], r[a]);                                  // -ln2/256, low part
+        pz[a] = fma(r[a], c_exp[4], c_exp[5]);                           // 1/24, 1/6
       }
-#define RTX_HORNER(c) _Pragma("unroll") for (int a = 0; a < ANGLE_BLOCK; ++a) pz[a] = fma(pz[a], r[a], c)
-      RTX_HORNER(1.6666666666666666e-01);
-      RTX_HORNER(0.5);
-      RTX_HORNER(1.0);
-#undef RTX_HORNER
+#pragma unroll
+      for (int a = 0; a < ANGLE_BLOCK; ++a) pz[a] = fma(pz[a], r[a], 0.5);
+#pragma unroll
+      for (int a = 0; a < ANGLE_BLOCK; ++a) pz[a] = fma(pz[a], r[a], 1.0);
 #pragma unroll
       for (int a = 0; a < ANGLE_BLOCK; ++a) {
         const int k = __double2loint(tt[a]);
-        const double tj = s_exp2[k & 63];
-        double t = fma(tj, pz[a] * r[a], tj);                            // 2^(j/64) * (1 + (exp(r)-1))
-        t = __hiloint2double(__double2hiint(t) + ((k >> 6) << 20), __double2loint(t));
-        t = (xa[a] < -708.0) ? 0.0 : t;                                  // below DBL_MIN anyway
-        acc[a] = t * acc[a] + (1.0 - t) * B;
+        const double tj = s_exp2[k & 255];
+        double t = fma(tj, pz[a] * r[a], tj);                            // 2^(j/256) * (1 + (exp(r)-1))
+        t = __hiloint2double(__double2hiint(t) + ((k >> 8) << 20), __double2loint(t));
+        acc[a] = fma(t, acc[a] - B, B);                                  // t*Ld + (1-t)*B
       }
     }
 #pragma unroll
