@@ -115,23 +115,36 @@ def _to_host(*tensors, outs=None):
     if stage is None or stage.numel() < total:
         stage = _workspace["pinned"] = torch.empty(max(total, 1), dtype=torch.float64, pin_memory=True)
     off = 0
-    views = []
+    views, events = [], []
     for t in tensors:
         v = stage[off:off + t.numel()]
         v.copy_(t.reshape(-1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()                                   # this tensor's bytes have landed once the event completes
+        events.append(ev)
         views.append(v.numpy().reshape(tuple(t.shape)))
         off += t.numel()
     if outs is None:
         outs = [np.empty(v.shape, dtype=np.float64) for v in views]
-    torch.cuda.current_stream(tensors[0].device).synchronize()
     if total < (1 << 18):
+        torch.cuda.current_stream(tensors[0].device).synchronize()
         for o, v in zip(outs, views):
             np.copyto(o, v)
     else:
+        # copy each array out of the staging buffer as soon as its own transfer is done, while the next one is
+        # still on the bus
         if _copy_pool is None:
             from concurrent.futures import ThreadPoolExecutor
-            _copy_pool = ThreadPoolExecutor(max_workers=4)
-        list(_copy_pool.map(lambda ov: np.copyto(ov[0], ov[1]), zip(outs, views)))
+            _copy_pool = ThreadPoolExecutor(max_workers=6)
+        futs = []
+        for o, v, ev in zip(outs, views, events):
+            ev.synchronize()
+            of, vf = o.reshape(-1), v.reshape(-1)
+            h = of.size // 2
+            futs.append(_copy_pool.submit(np.copyto, of[:h], vf[:h]))
+            futs.append(_copy_pool.submit(np.copyto, of[h:], vf[h:]))
+        for f in futs:
+            f.result()
     return outs
 
 
