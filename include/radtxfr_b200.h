@@ -141,7 +141,9 @@ int rtx_tips(rtx_handle* h, int n, const double* T_dev, double* q_dev, void* str
  *   tau_dev, lu_dev [n_atm][nx][n_alt][n_mu];  ld_dev [n_atm][nx]
  * Quirks of the reference are kept: layer mask Z<=alt (:348), upwelling over the first count(mask)
  * layers (:353-356), downwelling over the layer count of the LAST altitude (:353,:370);
- * return_od!=0 stores the optical-depth sum instead of the transmittance (:349-350). */
+ * return_od!=0 stores the optical-depth sum instead of the transmittance (:349-350).
+ * The two halves can be launched separately: ld_dev == NULL computes only tau and lu, tau_dev == lu_dev == NULL
+ * only ld (a caller can then start moving tau / lu off the device while the downwelling half still runs). */
 int rtx_tud(rtx_handle* h, int n_atm, int n_layers, const double* od_dev, const double* T_dev,
             const double* grid_dev, int64_t nx, const double* Z_host, const double* alt_host, int n_alt,
             const double* mu_host, int n_mu, int n_angle, int return_od, double* tau_dev, double* lu_dev,

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
 
   // ---- upwelling: Lu <- t*Lu + (1-t)*B_k bottom-up, snapshot at every altitude's layer count
   //      (radiative_transfer.py:353-356)
-  for (int m = 0; m < P.n_mu; ++m) {
+  for (int m = 0; P.tau != nullptr && m < P.n_mu; ++m) {
     const double mu = P.mu[m];
     double lu = 0.0;
     for (int a = 0; a < P.n_alt; ++a)
@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
   //      kernel's work, so exp is evaluated for a block of angles at once with the polynomial constants shared:
   //      table-driven range reduction (256 entries), degree-4 polynomial, scaling through the exponent field;
   //      10 FP64 operations per value, 1-2 ulp.
+  if (P.ld == nullptr) return;              // upwelling / transmittance half only
   double ldsum = 0.0;
   for (int a0 = 0; a0 < P.n_angle; a0 += ANGLE_BLOCK) {
     double acc[ANGLE_BLOCK], sec[ANGLE_BLOCK];
@@ -223,8 +224,9 @@ extern "C" int rtx_tud(rtx_handle* h, int n_atm, int n_layers, const double* od_
   RTX_REQUIRE(n_alt > 0 && n_alt <= RTX_MAX_ALT, "rtx_tud: n_alt out of range");
   RTX_REQUIRE(n_mu > 0 && n_mu <= RTX_MAX_MU, "rtx_tud: n_mu out of range");
   RTX_REQUIRE(n_angle > 0 && n_angle <= RTX_MAX_ANGLES, "rtx_tud: N_angle out of range");
-  RTX_REQUIRE(od_dev && T_dev && grid_dev && Z_host && alt_host && mu_host && tau_dev && lu_dev && ld_dev,
-              "rtx_tud: null pointer");
+  RTX_REQUIRE(od_dev && T_dev && grid_dev && Z_host && alt_host && mu_host, "rtx_tud: null pointer");
+  RTX_REQUIRE((tau_dev != nullptr) == (lu_dev != nullptr) && (tau_dev || ld_dev),
+              "rtx_tud: pass tau and lu together, or ld, or all three");
   DeviceGuard guard(h->device);
   TudParams P{};
   P.n_atm = n_atm; P.n_layers = n_layers; P.n_alt = n_alt; P.n_mu = n_mu; P.return_od = return_od ? 1 : 0;

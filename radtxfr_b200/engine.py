@@ -306,7 +306,7 @@ class LineDB:
 
 
 # --------------------------------------------------------------------------------------------- line-less ops
-def tud(od, T_layers, grid, Z, altitudes, mu, n_angle, return_od=False, device=None):
+def tud(od, T_layers, grid, Z, altitudes, mu, n_angle, return_od=False, device=None, split=False):
     """rtx_tud.  od [n_atm, nL, nx] (or [nL, nx]), T_layers [n_atm, nL]; returns (tau, lu, ld) CUDA tensors of
     shapes [n_atm, nx, n_alt, n_mu], same, [n_atm, nx]."""
     torch = _torch()
@@ -326,9 +326,17 @@ def tud(od, T_layers, grid, Z, altitudes, mu, n_angle, return_od=False, device=N
     tau = torch.empty((n_atm, nx, alt.size, mu.size), dtype=torch.float64, device=dev)
     lu = torch.empty_like(tau)
     ld = torch.empty((n_atm, nx), dtype=torch.float64, device=dev)
-    _lib.call("rtx_tud", h.h, n_atm, nL, _ptr(od), _ptr(T_layers), _ptr(grid), nx, _hptr(Z), _hptr(alt), alt.size,
-              _hptr(mu), mu.size, int(n_angle), int(bool(return_od)), _ptr(tau), _ptr(lu), _ptr(ld), _stream(dev))
-    return tau, lu, ld
+    args = (h.h, n_atm, nL, _ptr(od), _ptr(T_layers), _ptr(grid), nx, _hptr(Z), _hptr(alt), alt.size, _hptr(mu), mu.size,
+            int(n_angle), int(bool(return_od)))
+    if not split:
+        _lib.call("rtx_tud", *args, _ptr(tau), _ptr(lu), _ptr(ld), _stream(dev))
+        return tau, lu, ld
+    # two launches: tau and lu are complete at `ready` while the (longer) downwelling half still runs
+    _lib.call("rtx_tud", *args, _ptr(tau), _ptr(lu), None, _stream(dev))
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream(dev))
+    _lib.call("rtx_tud", *args, None, None, _ptr(ld), _stream(dev))
+    return tau, lu, ld, ready
 
 
 def planck(X, T, wavelength=False, device=None):

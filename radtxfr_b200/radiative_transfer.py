@@ -105,22 +105,37 @@ def _host_outputs(shapes):
     return outs
 
 
-def _to_host(*tensors, outs=None):
-    """Device tensors -> fresh numpy arrays through one persistent pinned staging buffer: async D2H, one stream
-    sync, then the copies out of the staging buffer run on a small thread pool (numpy releases the GIL)."""
+def _to_host(*tensors, outs=None, early=None):
+    """Device tensors -> fresh numpy arrays through one persistent pinned staging buffer: async D2H, then the copies
+    out of the staging buffer run on a small thread pool (numpy releases the GIL).  early = (event, n): the first n
+    tensors are complete at `event` (recorded on the current stream while later kernels are still queued); their
+    transfers go on a side stream so that they overlap those kernels."""
     global _copy_pool
     torch = engine._torch()
+    dev = tensors[0].device
+    side = None
+    if early is not None:
+        side = _workspace.get("side_stream")
+        if side is None:
+            side = _workspace["side_stream"] = torch.cuda.Stream(device=dev)
+        side.wait_event(early[0])
     total = sum(t.numel() for t in tensors)
     stage = _workspace.get("pinned")
     if stage is None or stage.numel() < total:
         stage = _workspace["pinned"] = torch.empty(max(total, 1), dtype=torch.float64, pin_memory=True)
     off = 0
     views, events = [], []
-    for t in tensors:
+    for i, t in enumerate(tensors):
         v = stage[off:off + t.numel()]
-        v.copy_(t.reshape(-1), non_blocking=True)
         ev = torch.cuda.Event()
-        ev.record()                                   # this tensor's bytes have landed once the event completes
+        if side is not None and i < early[1]:
+            with torch.cuda.stream(side):
+                v.copy_(t.reshape(-1), non_blocking=True)
+                ev.record(side)
+            t.record_stream(side)
+        else:
+            v.copy_(t.reshape(-1), non_blocking=True)
+            ev.record()                               # this tensor's bytes have landed once the event completes
         events.append(ev)
         views.append(v.numpy().reshape(tuple(t.shape)))
         off += t.numel()
@@ -254,7 +269,7 @@ def compute_TUD(Xmin, Xmax, opts=options, **kwargs):
                       **_voigt_settings(opts))                                  # [nL, nX], layer-major
     if opts.get("continuum_od") is not None:
         od = _add_continuum(od, opts, X_ if X_ is not None else grid, T, P, PL, MF, ID)
-    tau, lu, ld = engine.tud(od, Td[None, :], grid, Z, Z_s, mu_s, nA, returnOD)
+    tau, lu, ld, up_ready = engine.tud(od, Td[None, :], grid, Z, Z_s, mu_s, nA, returnOD, split=True)
     # the kernels are in flight: build the host axis and pre-touch the result arrays meanwhile
     if X_ is None:
         X_ = make_spectral_axis(Xmin, Xmax, opts["DVOUT"])
@@ -263,7 +278,7 @@ def compute_TUD(Xmin, Xmax, opts=options, **kwargs):
         B = engine.planck(grid, T).cpu().numpy()
         np.savez("ComputeTUD.npz", OD=od.cpu().numpy().T, B=B, tau=tau[0].cpu().numpy(), Lu=lu[0].cpu().numpy(),
                  X=X_, angles=np.linspace(0, np.pi / 2.0, nA, endpoint=False), Z_s=Z_s, mu_s=mu_s)
-    tau_, Lu_, Ld_ = _to_host(tau[0], lu[0], ld[0], outs=outs)
+    tau_, Lu_, Ld_ = _to_host(tau[0], lu[0], ld[0], outs=outs, early=(up_ready, 2))
     if (len(Z_s) == 1) and (len(mu_s) == 1):
         tau_, Lu_ = tau_[:, 0, 0], Lu_[:, 0, 0]
     if (len(Z_s) == 1) and not (len(mu_s) == 1):

@@ -633,3 +633,27 @@ def test_voigt_automatic_tile_size(mods):
             _, ref = port.absorption_coefficient_voigt(cols, T=T[k], p=p[k], OmegaGrid=grid)
             assert_parity(out[k], ref, RTOL, FLOOR, "%s grid state %d" % (name, k))
     assert picked == {"fine": 8, "coarse": 4}, picked
+
+
+def test_tud_split_halves(mods):
+    """rtx_tud launched as two halves (tau+Lu, then Ld: NULL output pointers select the half) gives bit-identical
+    results to the single launch; asking for tau without lu is refused."""
+    import torch
+    engine = mods["engine"]
+    rng = np.random.default_rng(5)
+    nL, nx = 12, 3000
+    od = rng.uniform(0, 2.0, (nL, nx)) * rng.uniform(0, 1, (1, nx))
+    T = np.linspace(290.0, 215.0, nL)[None, :]
+    Z = np.linspace(0.5, 30.0, nL)
+    X = np.linspace(700.0, 1400.0, nx)
+    one = engine.tud(od, T, X, Z, [3.0, 500.0], [1.0, 1.3], 9)
+    two = engine.tud(od, T, X, Z, [3.0, 500.0], [1.0, 1.3], 9, split=True)
+    two[3].synchronize()
+    for a, b in zip(one, two[:3]):
+        assert torch.equal(a, b)
+    from radtxfr_b200 import _lib
+    with pytest.raises(RuntimeError):
+        h = engine.default_handle(one[0].device)
+        _lib.call("rtx_tud", h.h, 1, nL, engine._ptr(engine.to_device(od, one[0].device)), engine._ptr(engine.to_device(T, one[0].device)),
+                  engine._ptr(engine.to_device(X, one[0].device)), nx, engine._hptr(Z), engine._hptr(np.array([3.0])), 1,
+                  engine._hptr(np.array([1.0])), 1, 9, 0, engine._ptr(one[0]), None, None, engine._stream(one[0].device))
