@@ -59,9 +59,17 @@ constexpr int NT = 256;         // threads per CTA
 #define RTX_MINBLOCKS 3
 #endif
 
-constexpr int ROUNDS = RTX_ROUNDS;  // prologue rounds per chunk (one line per thread per round)
-constexpr int LCHUNK = NT * ROUNDS;  // lines per chunk
-constexpr int NBLK = LCHUNK / 32;     // 32-line blocks per chunk
+// Lines per chunk (one line per thread per prologue round).  The FP64 kernels keep ONE 80-byte record per line, so
+// the 2048-point tile affords 512-line chunks at three CTAs per SM: half as many block-wide barriers and prologue
+// phases per tile as 256-line chunks (measured gain 0.3 %; the single record itself 0.5 %).  The FP32 mode carries
+// an extra single-precision record per line and the warp-specialised variant double-buffers, so they stay at 256.
+#ifndef RTX_LCH_BIG
+#define RTX_LCH_BIG 512
+#endif
+template <int K, int MODE, bool WS>
+struct ChunkCfg {
+  static constexpr int LCH = (K == 8 && MODE != 2 && !WS) ? RTX_LCH_BIG : NT * RTX_ROUNDS;
+};
 #ifndef RTX_NARROW_MAX
 #define RTX_NARROW_MAX 128
 #endif
@@ -251,12 +259,14 @@ __device__ __forceinline__ unsigned slice_masks(int lo, int hi, int clo, int chi
   }
   return m;
 }
-// pass-2 record: [s, e) is evaluated by pass 2, of which [cs, ce) is the Weideman core (empty: cs == ce == s)
+// per-line record: [s, e) is evaluated by pass 2, of which [clo, chi) is the Weideman core (empty: clo == chi)
+// It is also the pass-1 record of the FP64 kernels: [lo, hi) is the line's window, [clo, chi) its Weideman core.
 struct __align__(16) SegRec {
-  double sg0, cte, y, cw, a, ah, m, c;
-  short s, e, cs, ce;
+  double sg0, a, ah, m, c, cte, y, cw;
+  short lo, hi, clo, chi, s, e;
   int pad_;
 };
+static_assert(sizeof(SegRec) == 80, "one 80-byte record per line");
 
 // ---------------------------------------------------------------------------------------------
 // per-state tables: Q(Tref)/Q(T) by TIPS-2011 Lagrange interpolation (misc/hapi.py:5311-5388, 9568-9582),
@@ -427,11 +437,15 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
   constexpr int TILE = K * NT;
   constexpr int NBUF = WS ? 2 : 1;
   constexpr int NTH = WS ? NT + 32 * NPW : NT;
+  constexpr int LCHUNK = ChunkCfg<K, MODE, WS>::LCH;   // lines per chunk
+  constexpr int NBLK = LCHUNK / 32;                    // 32-line blocks per chunk
+  constexpr int ROUNDS = LCHUNK / NT;                  // prologue rounds per chunk
+  using P1Rec = typename std::conditional<F32, WideRec, SegRec>::type;   // what pass 1 reads
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* s_grid = reinterpret_cast<double*>(smem_raw);                 // TILE
   double* s_acc2 = s_grid + TILE;                                       // TILE
-  WideRec* s_wide = reinterpret_cast<WideRec*>(s_acc2 + TILE);          // NBUF * LCHUNK
-  SegRec* s_seg = reinterpret_cast<SegRec*>(s_wide + NBUF * LCHUNK);    // NBUF * LCHUNK
+  WideRec* s_wide = reinterpret_cast<WideRec*>(s_acc2 + TILE);          // NBUF * LCHUNK, FP32 mode only
+  SegRec* s_seg = reinterpret_cast<SegRec*>(s_wide + (F32 ? NBUF * LCHUNK : 0));   // NBUF * LCHUNK
   // per block of 32 lines (one warp, one prologue round) and per consumer warp: which of the 32 records that warp
   // must visit -- windows covering its whole slice, windows touching it, segments touching it
   __shared__ unsigned s_mfull[NBUF][NBLK][NT / 32], s_mtouch[NBUF][NBLK][NT / 32], s_mseg[NBUF][NBLK][NT / 32];
@@ -524,7 +538,6 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       const int k = blk * 32 + lane;
       const int li = first + c + k * nchunks;
       bool is_wide = false, has_seg = false;
-      WideRec wr;
       SegRec sr;
       double h_keep = 0.0;
       if (li < last) {
@@ -540,11 +553,11 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
             const double h = P.lorentz ? 0.0 : L.gamD * L.gamD / RTX_LN2;  // 1/cte^2
             const double g2 = L.gam0 * L.gam0;
             const double a = L.amp * L.gam0 / RTX_PI;
-            sr.sg0 = wr.sg0 = L.sg0;
-            sr.a = wr.a = a;
-            sr.ah = wr.ah = a * h;
-            sr.m = wr.m = g2 - 0.5 * h;
-            sr.c = wr.c = 2.0 * h * g2;
+            sr.sg0 = L.sg0;
+            sr.a = a;
+            sr.ah = a * h;
+            sr.m = g2 - 0.5 * h;
+            sr.c = 2.0 * h * g2;
             h_keep = h;
             sr.cte = cte;
             sr.y = y;
@@ -596,19 +609,19 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
                 chi = g;
               }
             }
-            sr.cs = (short)clo; sr.ce = (short)chi;
+            sr.lo = (short)lo; sr.hi = (short)hi; sr.clo = (short)clo; sr.chi = (short)chi;
             if (P.doppler) {
               // cSqrtLn2divSqrtPi*exp(-cLn2*((sg-sg0)/GamD)**2)/GamD (misc/hapi.py:10160, hapi's truncated constants):
               // the whole window is a "core" of pass 2, evaluated with exp instead of the rational series
               sr.cte = 0.8325546111576705 / L.gamD;     // sqrt(cLn2), cLn2 = 0.6931471805599
               sr.cw = L.amp * 0.469718639319144059835 / L.gamD;
-              has_seg = true; sr.s = sr.cs = (short)lo; sr.e = sr.ce = (short)hi;
+              has_seg = true; sr.s = sr.clo = (short)lo; sr.e = sr.chi = (short)hi;
             } else if (hi - lo <= NARROW_MAX) {
               has_seg = true; sr.s = (short)lo; sr.e = (short)hi;
             } else {
               is_wide = true;
-              wr.lo = (short)lo; wr.hi = (short)hi; wr.clo = (short)clo; wr.chi = (short)chi;
-              if (chi > clo) { has_seg = true; sr.s = (short)clo; sr.e = (short)chi; }
+              sr.s = (short)clo; sr.e = (short)chi;                          // pass 2 takes the core only
+              has_seg = chi > clo;
             }
           }
         }
@@ -618,19 +631,17 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       if (is_wide) {
         if (F32) {
           WideRec32 w3;
-          const double c = wr.sg0 - s_grid[0];
+          const double c = sr.sg0 - s_grid[0];
           w3.chi = (float)c; w3.clo = (float)(c - (double)w3.chi);
-          w3.af = (float)wr.a; w3.hf = (float)h_keep; w3.mf = (float)wr.m; w3.cf = (float)wr.c;
+          w3.af = (float)sr.a; w3.hf = (float)h_keep; w3.mf = (float)sr.m; w3.cf = (float)sr.c;
           w3.pad0 = w3.pad1 = 0.f;
-          w3.lo = wr.lo; w3.hi = wr.hi; w3.core_lo = wr.clo; w3.core_hi = wr.chi;
+          w3.lo = sr.lo; w3.hi = sr.hi; w3.core_lo = sr.clo; w3.core_hi = sr.chi;
           *reinterpret_cast<WideRec32*>(&wide_b[k]) = w3;
-        } else {
-          wide_b[k] = wr;
         }
-        wm = slice_masks(wr.lo, wr.hi, wr.clo, wr.chi, 32 * K);
+        wm = slice_masks(sr.lo, sr.hi, sr.clo, sr.chi, 32 * K);
       }
+      if (is_wide || has_seg) seg_b[k] = sr;
       if (has_seg) {
-        seg_b[k] = sr;
 #pragma unroll
         for (int q = 0; q < NT / 32; ++q) sm |= ((sr.e > q * 32 * K) && (sr.s < (q + 1) * 32 * K) ? 1u : 0u) << q;
       }
@@ -674,7 +685,8 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
     // path; only the slices holding a window end (or a Weideman core) pay for per-point predicates.
 #pragma unroll 1
     for (int blk = 0; blk < NBLK; ++blk) {
-      const WideRec* __restrict__ recs = s_wide + buf * LCHUNK + blk * 32;
+      const P1Rec* __restrict__ recs = (F32 ? reinterpret_cast<const P1Rec*>(s_wide) : reinterpret_cast<const P1Rec*>(s_seg)) +
+                                       buf * LCHUNK + blk * 32;
       unsigned m = s_mfull[buf][blk][warp];
 #ifdef RTX_DBG_SKIP_FULL
       m = 0;
@@ -682,9 +694,9 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       if (MODE == 0) {
         // full-precision FP64 path: records that cover the slice are taken two at a time through one reciprocal
         while (m & (m - 1)) {
-          const WideRec& ra = recs[__ffs(m) - 1];
+          const P1Rec& ra = recs[__ffs(m) - 1];
           m &= m - 1;
-          const WideRec& rb = recs[__ffs(m) - 1];
+          const P1Rec& rb = recs[__ffs(m) - 1];
           m &= m - 1;
           const double sg1 = ra.sg0, a1 = ra.a, ah1 = ra.ah, m1 = ra.m, c1 = ra.c;
           const double sg2 = rb.sg0, a2 = rb.a, ah2 = rb.ah, m2 = rb.m, c2 = rb.c;
@@ -693,7 +705,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
         }
       }
       while (m) {
-        const WideRec& rr = recs[__ffs(m) - 1];
+        const P1Rec& rr = recs[__ffs(m) - 1];
         m &= m - 1;
         RTX_VISIT_SETUP();
         (void)wlo; (void)whi; (void)wclo; (void)wchi;
@@ -705,7 +717,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       m = 0;
 #endif
       while (m) {
-        const WideRec& rr = recs[__ffs(m) - 1];
+        const P1Rec& rr = recs[__ffs(m) - 1];
         m &= m - 1;
         RTX_VISIT_SETUP();
         const int lo = wlo - own_lo, hi = whi - own_lo;              // window in slice coordinates
@@ -758,9 +770,9 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       int cs = 0, n = 0, nw = 0;
       if ((msk >> lane) & 1u) {
         const SegRec& q = recs[lane];
-        cs = max((int)q.cs, own_lo);
-        n = max(min((int)q.ce, own_hi) - cs, 0);
-        nw = max(min((int)q.cs, own_hi) - max((int)q.s, own_lo), 0) + max(min((int)q.e, own_hi) - max((int)q.ce, own_lo), 0);
+        cs = max((int)q.clo, own_lo);
+        n = max(min((int)q.chi, own_hi) - cs, 0);
+        nw = max(min((int)q.clo, own_hi) - max((int)q.s, own_lo), 0) + max(min((int)q.e, own_hi) - max((int)q.chi, own_lo), 0);
       }
       // (a) wings
       unsigned m2 = __ballot_sync(0xffffffffu, nw > 0);
@@ -768,8 +780,8 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
         const SegRec& r = recs[__ffs(m2) - 1];
         m2 &= m2 - 1;
         const double sg0 = r.sg0, a = r.a, ah = r.ah, mm = r.m, c = r.c;
-        const int ls = max((int)r.s, own_lo), nl = max(min((int)r.cs, own_hi) - ls, 0);
-        const int rs = max((int)r.ce, own_lo), nr = max(min((int)r.e, own_hi) - rs, 0);
+        const int ls = max((int)r.s, own_lo), nl = max(min((int)r.clo, own_hi) - ls, 0);
+        const int rs = max((int)r.chi, own_lo), nr = max(min((int)r.e, own_hi) - rs, 0);
         const int nt = nl + nr;
         int t = lane;
         for (; t + 32 < nt; t += 64) {               // two rows per step: independent chains, disjoint points
@@ -931,14 +943,15 @@ __global__ void count_kernel(const VoigtParams P, unsigned long long* __restrict
   }
 }
 
-template <int K, bool WS>
+template <int K, int MODE, bool WS>
 size_t tile_smem_bytes() {
-  return (size_t)K * NT * 8 * 2 + (size_t)(WS ? 2 : 1) * LCHUNK * (sizeof(WideRec) + sizeof(SegRec));
+  return (size_t)K * NT * 8 * 2 + (size_t)(WS ? 2 : 1) * ChunkCfg<K, MODE, WS>::LCH *
+                                      (sizeof(SegRec) + (MODE == 2 ? sizeof(WideRec) : 0));
 }
 
 template <int K, int MODE, bool WS>
 int launch_tile(const VoigtParams& P, cudaStream_t st) {
-  const size_t smem = tile_smem_bytes<K, WS>();
+  const size_t smem = tile_smem_bytes<K, MODE, WS>();
   RTX_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<K, MODE, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t blocks = (int64_t)P.n_tiles * P.n_states;
   if (blocks > 2147483647LL) { rtx_set_error("rtx_voigt_sum: too many (tile, state) pairs for one launch"); return RTX_E_INVALID; }
