@@ -63,6 +63,9 @@ constexpr int NT = 256;         // threads per CTA
 // the 2048-point tile affords 512-line chunks at three CTAs per SM: half as many block-wide barriers and prologue
 // phases per tile as 256-line chunks (measured gain 0.3 %; the single record itself 0.5 %).  The FP32 mode carries
 // an extra single-precision record per line and the warp-specialised variant double-buffers, so they stay at 256.
+#ifndef RTX_CORE_SUB
+#define RTX_CORE_SUB 1
+#endif
 #ifndef RTX_LCH_BIG
 #define RTX_LCH_BIG 512
 #endif
@@ -247,13 +250,15 @@ struct __align__(16) WideRec32 {
 static_assert(sizeof(WideRec32) <= sizeof(WideRec), "WideRec32 must fit a WideRec slot");
 // per wide line: bit q = the window touches warp q's slice, bit 8+q = it covers the slice with no Weideman point
 // inside (test-free path)
-__device__ __forceinline__ unsigned slice_masks(int lo, int hi, int clo, int chi, int slice) {
+// With core_ok a covered slice is test-free even when the core lies inside it: pass 1 then evaluates the closed form
+// on the core points too and pass 2 adds (series - closed form) there.
+__device__ __forceinline__ unsigned slice_masks(int lo, int hi, int clo, int chi, int slice, bool core_ok) {
   unsigned m = 0;
 #pragma unroll
   for (int q = 0; q < NT / 32; ++q) {
     const int a = q * slice, b = a + slice;
     const bool touch = (hi > a) && (lo < b);
-    const bool full = (lo <= a) && (hi >= b) && ((chi <= clo) || (chi <= a) || (clo >= b));
+    const bool full = (lo <= a) && (hi >= b) && (core_ok || (chi <= clo) || (chi <= a) || (clo >= b));
     m |= (touch ? 1u : 0u) << q;
     m |= (full ? 1u : 0u) << (8 + q);
   }
@@ -264,7 +269,7 @@ __device__ __forceinline__ unsigned slice_masks(int lo, int hi, int clo, int chi
 struct __align__(16) SegRec {
   double sg0, a, ah, m, c, cte, y, cw;
   short lo, hi, clo, chi, s, e;
-  int pad_;
+  int sub;   // slices the window covers were evaluated with the closed form on the core points too (pass 2 subtracts)
 };
 static_assert(sizeof(SegRec) == 80, "one 80-byte record per line");
 
@@ -539,6 +544,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       const int li = first + c + k * nchunks;
       bool is_wide = false, has_seg = false;
       SegRec sr;
+      sr.sub = 0;
       double h_keep = 0.0;
       if (li < last) {
         const LineState L = line_state(P, li, s, T, p, lnr);
@@ -621,6 +627,12 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
             } else {
               is_wide = true;
               sr.s = (short)clo; sr.e = (short)chi;                          // pass 2 takes the core only
+              // The slice that holds the core of a wide line would need per-point tests in pass 1.  Instead pass 1
+              // treats it like any covered slice (closed form on every point, finite for Gamma0 > 0) and pass 2 adds
+              // series - closed form on the core points.  The closed form peaks at amp/(2 pi Gamma0), 1/(2 sqrt(pi) y)
+              // times the true peak, so the cancellation costs < 3e-13 relative for y >= 1e-4; below that (and in
+              // the FP32 mode) the slice keeps the tested path.
+              sr.sub = (!F32 && RTX_CORE_SUB && y >= 1e-4 && y < 15.0) ? 1 : 0;
               has_seg = chi > clo;
             }
           }
@@ -638,7 +650,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
           w3.lo = sr.lo; w3.hi = sr.hi; w3.core_lo = sr.clo; w3.core_hi = sr.chi;
           *reinterpret_cast<WideRec32*>(&wide_b[k]) = w3;
         }
-        wm = slice_masks(sr.lo, sr.hi, sr.clo, sr.chi, 32 * K);
+        wm = slice_masks(sr.lo, sr.hi, sr.clo, sr.chi, 32 * K, sr.sub != 0);
       }
       if (is_wide || has_seg) seg_b[k] = sr;
       if (has_seg) {
@@ -827,8 +839,11 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
           ii[h] = __shfl_sync(0xffffffffu, cs, r) + (t - __shfl_sync(0xffffffffu, excl, r));
           const SegRec& rec = recs[r];
           const int ic = ok[h] ? ii[h] : own_lo;
-          const double x = __dmul_rn(s_grid[ic] - rec.sg0, rec.cte);
+          const double om = s_grid[ic];
+          const double x = __dmul_rn(om - rec.sg0, rec.cte);
           vv[h] = rec.cw * (P.doppler ? exp(-(x * x)) : weideman_re(x, rec.y));
+          if (rec.sub && rec.lo <= own_lo && rec.hi >= own_hi)        // pass 1 took this slice test-free
+            vv[h] = cheap_term<FAST>(om, rec.sg0, -rec.a, -rec.ah, rec.m, rec.c, vv[h]);   // same reciprocal as pass 1
         }
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
