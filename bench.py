@@ -18,6 +18,8 @@ reference itself is pure Python and cannot travel to the GPU box) on all host co
 same workload.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -371,4 +373,17 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout
+    # when NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the whole run and the JSON line is
+    # written to the real stdout at the end.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _buf = io.StringIO()
+    with contextlib.redirect_stdout(_buf):
+        main()
+    sys.stdout.flush()
+    os.dup2(_real_stdout, 1)
+    os.close(_real_stdout)
+    sys.stdout.write(_buf.getvalue())
+    sys.stdout.flush()
