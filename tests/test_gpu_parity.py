@@ -657,3 +657,22 @@ def test_tud_split_halves(mods):
         _lib.call("rtx_tud", h.h, 1, nL, engine._ptr(engine.to_device(od, one[0].device)), engine._ptr(engine.to_device(T, one[0].device)),
                   engine._ptr(engine.to_device(X, one[0].device)), nx, engine._hptr(Z), engine._hptr(np.array([3.0])), 1,
                   engine._hptr(np.array([1.0])), 1, 9, 0, engine._ptr(one[0]), None, None, engine._stream(one[0].device))
+
+
+def test_voigt_core_slice_cancellation(mods):
+    """Wide windows at very low pressure (OmegaWing forces +-1 cm^-1 windows while y = Gamma0*cte is 1e-2 ... 1e-5):
+    the slice holding the Weideman core takes the test-free path and pass 2 adds series - closed form there.  The
+    closed form is up to 1/(2 sqrt(pi) y) times the true core value, so this is the worst case for the cancellation;
+    below y = 1e-4 the kernel keeps the tested path.  Parity must hold throughout."""
+    port, syn, engine = mods["port"], mods["syn"], mods["engine"]
+    cols = syn.synthetic_lines(61, 120, 995.0, 1005.0, 1)
+    db = engine.LineDB(cols)
+    grid = np.linspace(996.0, 1004.0, 8001)
+    states = [(250.0, 1e-2), (240.0, 1e-3), (230.0, 2e-4), (220.0, 5e-5), (220.0, 1e-6)]
+    T = np.array([s[0] for s in states]); p = np.array([s[1] for s in states])
+    w = np.tile(db.iso_factors(None, 1.0), (len(states), 1))
+    for K in (8, 4):
+        out = db.voigt_sum(T, p, w, grid, wing_abs=1.0, flags=K << 8).cpu().numpy()
+        for k, (Tk, pk) in enumerate(states):
+            _, ref = port.absorption_coefficient_voigt(cols, T=Tk, p=pk, OmegaGrid=grid, OmegaWing=1.0)
+            assert_parity(out[k], ref, RTOL, FLOOR, "K=%d p=%g atm" % (K, pk))
