@@ -457,18 +457,8 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
   __shared__ __align__(8) unsigned long long s_bar, s_full[2], s_empty[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#ifndef RTX_BLOCK_ORDER
-#define RTX_BLOCK_ORDER 0
-#endif
-#if RTX_BLOCK_ORDER == 1
-  // tile-major: consecutive CTAs are the states (layers) of one tile, so every SM holds a mix of pipe-bound
-  // (low, pressure-broadened layers) and latency-bound (high, Doppler-dominated layers) CTAs at any time
-  const int s = blockIdx.x % P.n_states;
-  const int tile = blockIdx.x / P.n_states;
-#else
   const int tile = blockIdx.x % P.n_tiles;
   const int s = blockIdx.x / P.n_tiles;
-#endif
   const int64_t p0 = (int64_t)tile * TILE;
   const int npts = (int)min((int64_t)TILE, P.nx - p0);
 
