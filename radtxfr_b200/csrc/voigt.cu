@@ -5,31 +5,35 @@
 // 9833-9844) for many homogeneous (T, p) states at once.
 //
 // Design (B200-first, not a translation):
-//   * one CTA (256 threads, 80 registers, 64 KB shared memory: three CTAs per SM) per (wavenumber tile, state).
-//     The tile of the spectral grid is staged in shared memory by one TMA bulk copy (cp.async.bulk + mbarrier)
-//     and kept there: the prologue searches it with exact comparisons, so window membership is decided on the
-//     same doubles the reference bisects, and the evaluation passes read it back.
+//   * one CTA (256 threads) per (wavenumber tile, state): 2048-point tiles at 80 registers and 72 KB of shared memory
+//     (three CTAs per SM) when the windows are thousands of grid points wide, 1024-point tiles at 64 registers
+//     (four CTAs per SM) when they are a few hundred (window_stats_kernel decides).  The tile of the spectral grid is
+//     staged in shared memory by one TMA bulk copy (cp.async.bulk + mbarrier) and kept there: the prologue searches
+//     it with exact comparisons, so window membership is decided on the same doubles the reference bisects, and the
+//     evaluation passes read it back.
 //   * the CTA streams only the lines that can reach its tile (device-side binning on the sorted line centres
-//     with a conservative per-state wing bound), 256 lines per chunk, dealt round-robin so that every chunk spans
-//     the whole candidate range.  One thread derives one line's state (S(T), Gamma_D, Gamma_0, shift, wing, window
-//     indices, Weideman core indices); records stay at fixed slots and per-consumer-warp ballot masks say which
-//     records a warp must visit (no atomics, fixed summation order).
+//     with a conservative per-state wing bound), 512 (256) lines per chunk, dealt round-robin so that every chunk
+//     spans the whole candidate range.  One thread derives one line's state (S(T), Gamma_D, Gamma_0, shift, wing,
+//     window indices, Weideman core indices) into ONE 80-byte record; records stay at fixed slots and
+//     per-consumer-warp ballot masks say which records a warp must visit (no atomics, fixed summation order).
 //   * pass 1 ("wide" lines): each warp owns 32*K contiguous grid points (K per lane, lane-strided), accumulators
 //     in registers.  Outside the Weideman core the reference's w(z) is the one-term Humlicek asymptote, for which
 //       S*V = a*(u+h)/(u^2+c),  u=(omega-nu0')^2+Gamma0^2-h/2, h=GammaD^2/ln2, c=2*h*Gamma0^2, a=amp*Gamma0/pi
 //     (closed form of SURVEY.md App. A.3 with the square completed) = 8 FP64 pipe operations per (line, grid
 //     point) incl. a Newton-refined MUFU.RCP64H reciprocal; on slices a window covers completely two lines share
-//     one reciprocal (7.5 operations per evaluation).  Slices holding a window end use edge-specialised code.
-//   * pass 2 ("segments"): the Weideman cores of wide lines and the whole window of narrow lines are evaluated
-//     lane-per-point by the warp that owns that part of the tile (shared-memory accumulator, no atomics; short
-//     segments of several lines are flattened across the lanes), so the 24-term rational series never diverges
-//     against the cheap branch inside a warp.
+//     one reciprocal (7.5 operations per evaluation) -- including the slice that holds the line's core, where pass 2
+//     adds (series - closed form) on the core points.  Slices holding a window end use edge-specialised code.
+//   * pass 2: the Weideman cores of wide lines and the whole window of narrow lines (<= 128 points) are evaluated
+//     lane-per-point by the warp that owns that part of the tile (shared-memory accumulator, no atomics): wings
+//     record by record, two rows at a time; cores flattened across record boundaries, two steps at a time, so the
+//     24-term rational series never diverges against the cheap branch inside a warp.
+//   * flags select the Lorentz and Doppler drivers of hapi (same skeleton, different wing rule and profile).
 //   * FP64 throughout (an optional FP32 mode exists for the asymptote branch); summation order is fixed, so
-//     results are bit-reproducible run to run and independent of how the grid is sharded across GPUs.
+//     results are bit-reproducible run to run and, with the tile size pinned, independent of how the grid is
+//     sharded across GPUs.
 #include <math.h>
 
 #include <algorithm>
-
 #include <type_traits>
 
 #include "rtx_common.cuh"
