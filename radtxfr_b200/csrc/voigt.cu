@@ -41,7 +41,7 @@
 namespace {
 
 constexpr int NT = 256;         // threads per CTA
-// 3 CTAs (24 warps) per SM: 80 registers per thread and 64 KB of shared memory per CTA; measured 7 % faster on
+// 3 CTAs (24 warps) per SM: 80 registers per thread and 72 KB of shared memory per CTA; measured 7 % faster on
 // config 2 than 2 CTAs with 126 registers and 512-line chunks.
 #ifndef RTX_ROUNDS
 #define RTX_ROUNDS 1
@@ -49,7 +49,7 @@ constexpr int NT = 256;         // threads per CTA
 #ifndef RTX_P2_ILP
 #define RTX_P2_ILP 2
 #endif
-// K = 4 (1024-point tiles, 46 KB of shared memory) is compiled for four CTAs per SM (64 registers): the regime it is
+// K = 4 (1024-point tiles, 36 KB of shared memory) is compiled for four CTAs per SM (64 registers): the regime it is
 // chosen for -- windows of a few hundred grid points -- is latency- and issue-bound, not register-bound.
 #ifndef RTX_MINBLOCKS_K4
 #define RTX_MINBLOCKS_K4 4
