@@ -237,3 +237,41 @@ def absorptionCoefficient_Doppler(Components=None, SourceTables=None, partitionF
 
 
 absorptionCoefficient_Gauss = absorptionCoefficient_Doppler       # misc/hapi.py:11557
+
+
+hh = 6.626196e-27                 # erg*s, misc/hapi.py:86
+
+
+def _xp(a):
+    """numpy for host arrays, torch for tensors (these helpers are element-wise post-processing, not the hot path)."""
+    torch = engine._torch()
+    return torch if isinstance(a, torch.Tensor) else np
+
+
+def transmittanceSpectrum(Omegas, AbsorptionCoefficient, Environment={'l': 100.}, File=None, Format='%e %e',
+                          Wavenumber=None):
+    """exp(-k*l) on the grid (misc/hapi.py:11582-11610)."""
+    if Wavenumber is not None: Omegas = Wavenumber
+    if File: raise NotImplementedError("File output: write (Omegas, Xsect) on the host after the call")
+    return Omegas, _xp(AbsorptionCoefficient).exp(-AbsorptionCoefficient * Environment['l'])
+
+
+def absorptionSpectrum(Omegas, AbsorptionCoefficient, Environment={'l': 100.}, File=None, Format='%e %e',
+                       Wavenumber=None):
+    """1 - exp(-k*l) on the grid (misc/hapi.py:11613-11641)."""
+    if Wavenumber is not None: Omegas = Wavenumber
+    if File: raise NotImplementedError("File output: write (Omegas, Xsect) on the host after the call")
+    return Omegas, 1 - _xp(AbsorptionCoefficient).exp(-AbsorptionCoefficient * Environment['l'])
+
+
+def radianceSpectrum(Omegas, AbsorptionCoefficient, Environment={'l': 100., 'T': 296.}, File=None, Format='%e %e',
+                     Wavenumber=None):
+    """(1 - exp(-k*l)) * Planck(Omegas, T) in W/sr/cm^2/cm^-1 (misc/hapi.py:11644-11681)."""
+    if Wavenumber is not None: Omegas = Wavenumber
+    if File: raise NotImplementedError("File output: write (Omegas, Xsect) on the host after the call")
+    xp = _xp(AbsorptionCoefficient)
+    l, T = Environment['l'], Environment['T']
+    Alw = 1 - xp.exp(-AbsorptionCoefficient * l)
+    Om = Omegas if xp is np or not isinstance(Omegas, np.ndarray) else xp.as_tensor(Omegas, device=AbsorptionCoefficient.device)
+    LBBTw = 2 * hh * cc ** 2 * Om ** 3 / (xp.exp(hh * cc * Om / (cBolts * T)) - 1) * 1.0E-7
+    return Omegas, Alw * LBBTw

@@ -177,3 +177,14 @@ def test_lwir_tud_products(tmp_path):
     except ImportError:
         with pytest.raises(ImportError):
             drivers.save_LWIR_TUD_h5(str(tmp_path / "x.h5"), X, OD, La, Ld, alt, OD, X, X, X, X, X)
+
+
+def test_hapi_spectrum_helpers_golden():
+    """transmittanceSpectrum / absorptionSpectrum / radianceSpectrum against the reference's outputs."""
+    from radtxfr_b200 import hapi_compat as hapi
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "spectra.npz"))
+    env = {"l": 250.0, "T": 283.0}
+    for fn, key in ((hapi.transmittanceSpectrum, "trans"), (hapi.absorptionSpectrum, "absorp"), (hapi.radianceSpectrum, "radi")):
+        nu, y = fn(g["nu"], g["coef"], Environment=env)
+        assert np.array_equal(nu, g["nu"])
+        np.testing.assert_allclose(y, g[key], rtol=1e-14, atol=0)

@@ -266,6 +266,19 @@ def g_doppler():
     save("doppler.npz", source="misc/hapi.py:11384-11550 absorptionCoefficient_Doppler (non-zero samples of a 20001-point grid)", **out)
 
 
+def g_spectra():
+    """transmittanceSpectrum / absorptionSpectrum / radianceSpectrum of hapi on a fixed coefficient vector."""
+    h = R.hapi()
+    nu = np.linspace(900.0, 1100.0, 41)
+    coef = 1e-3 * (1.0 + np.sin(nu / 7.0) ** 2)
+    env = {"l": 250.0, "T": 283.0}
+    out = {"nu": nu, "coef": coef}
+    out["trans"] = h.transmittanceSpectrum(nu, coef, Environment=env)[1]
+    out["absorp"] = h.absorptionSpectrum(nu, coef, Environment=env)[1]
+    out["radi"] = h.radianceSpectrum(nu, coef, Environment=env)[1]
+    save("spectra.npz", source="misc/hapi.py:11582-11681", **out)
+
+
 def mbi_image():
     ii, jj = np.meshgrid(np.arange(40), np.arange(32), indexing="ij")
     img = np.zeros((3, 40, 32), dtype=np.uint8)
@@ -306,6 +319,6 @@ def g_mbi():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi", "lorentz", "doppler"]
+    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi", "lorentz", "doppler", "spectra"]
     for w in which:
         globals()["g_" + w]()
