@@ -114,7 +114,10 @@ int rtx_tape3_read(const char* path, double vmin, double vmax, int64_t capacity,
 #define RTX_VOIGT_LORENTZ 16 /* Lorentz profile and wing rule of absorptionCoefficient_Lorentz (misc/hapi.py:11144-11381) */
 #define RTX_VOIGT_DOPPLER 32    /* PROFILE_DOPPLER, absorptionCoefficient_Doppler (misc/hapi.py:11384-11550) */
 #define RTX_VOIGT_NOSHIFT 64    /* with RTX_VOIGT_DOPPLER: LineShift=False */
-#define RTX_VOIGT_TILE_SHIFT 8 /* bits 8..11: force 256*K grid points per CTA, K in {1,2,4,8} (0 = automatic) */
+#define RTX_VOIGT_TILE_SHIFT 8 /* bits 8..11: force 256*K grid points per CTA, K in {1,2,4,8} (0 = automatic).
+                                * The automatic choice between K = 8 and K = 4 reads 8 bytes back from the device
+                                * (one stream synchronisation after a tiny kernel); force K to keep the call fully
+                                * asynchronous, e.g. under CUDA-graph capture, or to pin the summation order. */
 int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, const double* p_dev,
                   const double* weight_dev, double x_air, double x_self, double wing_abs, double wing_hw,
                   double s_threshold, const double* grid_dev, int64_t nx, double* out_dev, int flags,
