@@ -383,7 +383,5 @@ if __name__ == "__main__":
     with contextlib.redirect_stdout(_buf):
         main()
     sys.stdout.flush()
-    os.dup2(_real_stdout, 1)
+    os.write(_real_stdout, _buf.getvalue().encode())     # fd 1 stays on stderr: libraries also print at exit
     os.close(_real_stdout)
-    sys.stdout.write(_buf.getvalue())
-    sys.stdout.flush()
