@@ -210,13 +210,26 @@ def gpu_arm(args):
     gathered = torch.empty((world, 3, nX), dtype=torch.float64, device=dev) if world > 1 else None
     h0 = engine.default_handle(dev)
 
+    # The one collective of the path: every rank's three spectra to every rank.  It runs on a side
+    # stream so that step k's gather overlaps step k+1's Voigt kernel; the timed region ends after the last gather.
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+
+    def gather(tau, lu, ld):
+        done = torch.cuda.Event()
+        done.record()
+        with torch.cuda.stream(side):
+            side.wait_event(done)
+            mine = torch.stack([tau.reshape(-1), lu.reshape(-1), ld.reshape(-1)])
+            for t in (tau, lu, ld):
+                t.record_stream(side)
+            dist.all_gather_into_tensor(gathered, mine)
+
     def step(i):
         T, p, w = states[i]
         db.voigt_sum(T, p, w, grid, out=od, flags=args.flags)
         tau, lu, ld = engine.tud(od, T[None, :], grid, atm["Zs"], [500.0], [1.0], N_ANGLE)
         if world > 1:
-            mine = torch.stack([tau.reshape(-1), lu.reshape(-1), ld.reshape(-1)])
-            dist.all_gather_into_tensor(gathered, mine)
+            gather(tau, lu, ld)
         return tau, lu, ld
 
     for i in range(args.warmup):
@@ -245,15 +258,18 @@ def gpu_arm(args):
         db.voigt_sum(T, p, w, grid, out=od, flags=args.flags)
         ev[2 * k + 1].record()
         tau, lu, ld = engine.tud(od, T[None, :], grid, atm["Zs"], [500.0], [1.0], N_ANGLE)
-        if world > 1:
-            mine = torch.stack([tau.reshape(-1), lu.reshape(-1), ld.reshape(-1)])
-            dist.all_gather_into_tensor(gathered, mine)
         ev[2 * k + 2].record()
+        if world > 1:
+            gather(tau, lu, ld)
+    if world > 1:
+        torch.cuda.current_stream(dev).wait_stream(side)      # the last gather is inside the timed region
+    ev_end = torch.cuda.Event(enable_timing=True)
+    ev_end.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t1 = time.perf_counter()
-    ms_total = ev[0].elapsed_time(ev[-1])
+    ms_total = ev[0].elapsed_time(ev_end)
     ms_voigt = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps))
     ms_tud = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps))
     launches = db.handle.launches() + h0.launches() - launches0
