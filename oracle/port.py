@@ -13,7 +13,6 @@ evaluated in the same order).
 Every function cites the reference lines it follows (paths relative to /root/reference).
 """
 import os
-from bisect import bisect_right
 
 import numpy as np
 

@@ -4,8 +4,7 @@ There is no CPU fallback: if the shared library is missing or no B200 is visible
 """
 import ctypes
 import os
-from ctypes import (POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_uint64, c_void_p,
-                    create_string_buffer)
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_uint64, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RADTXFR_LIB", os.path.join(_PKG, "libradtxfr_b200.so"))

@@ -2,7 +2,6 @@
     python tools/voigt_microbench.py [reps]"""
 import os
 import sys
-import time
 
 import numpy as np
 import torch
