@@ -188,3 +188,27 @@ def test_hapi_spectrum_helpers_golden():
         nu, y = fn(g["nu"], g["coef"], Environment=env)
         assert np.array_equal(nu, g["nu"])
         np.testing.assert_allclose(y, g[key], rtol=1e-14, atol=0)
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "radtxfr_b200")
+    exe = str(tmp_path / "voigt_from_c")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "voigt_from_c.c"), "-L", libdir, "-lradtxfr_b200",
+                    "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    return exe
+
+
+def test_c_abi_from_plain_c_without_gpu(tmp_path):
+    """The header compiles as C11 and the library links from plain C; without a CUDA device rtx_create fails loudly
+    (exit status 77 of the example, with the library's own error text) -- no CPU fallback."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("covered by the GPU test")
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 77, (r.returncode, r.stdout, r.stderr)
+    assert "no CPU fallback" in r.stdout
