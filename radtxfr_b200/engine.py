@@ -308,7 +308,9 @@ class LineDB:
 # --------------------------------------------------------------------------------------------- line-less ops
 def tud(od, T_layers, grid, Z, altitudes, mu, n_angle, return_od=False, device=None, split=False):
     """rtx_tud.  od [n_atm, nL, nx] (or [nL, nx]), T_layers [n_atm, nL]; returns (tau, lu, ld) CUDA tensors of
-    shapes [n_atm, nx, n_alt, n_mu], same, [n_atm, nx]."""
+    shapes [n_atm, nx, n_alt, n_mu], same, [n_atm, nx].  split=True launches the two halves separately and returns
+    (tau, lu, ld, ready): tau and lu are complete once the CUDA event `ready` has fired, while the downwelling half
+    is still running."""
     torch = _torch()
     dev = od.device if isinstance(od, torch.Tensor) and od.is_cuda else resolve_device(device)
     h = default_handle(dev)

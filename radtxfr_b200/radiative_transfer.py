@@ -109,15 +109,17 @@ def _to_host(*tensors, outs=None, early=None):
     """Device tensors -> fresh numpy arrays through one persistent pinned staging buffer: async D2H, then the copies
     out of the staging buffer run on a small thread pool (numpy releases the GIL).  early = (event, n): the first n
     tensors are complete at `event` (recorded on the current stream while later kernels are still queued); their
-    transfers go on a side stream so that they overlap those kernels."""
+    transfers go on a side stream so that they overlap those kernels.  The staging buffer and the side stream are
+    module-level state: like the reference's module-level `options`, this is not meant for concurrent calls from
+    several host threads."""
     global _copy_pool
     torch = engine._torch()
     dev = tensors[0].device
     side = None
     if early is not None:
-        side = _workspace.get("side_stream")
+        side = _workspace.get(("side_stream", str(dev)))
         if side is None:
-            side = _workspace["side_stream"] = torch.cuda.Stream(device=dev)
+            side = _workspace[("side_stream", str(dev))] = torch.cuda.Stream(device=dev)
         side.wait_event(early[0])
     total = sum(t.numel() for t in tensors)
     stage = _workspace.get("pinned")
