@@ -212,3 +212,18 @@ def test_c_abi_from_plain_c_without_gpu(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 77, (r.returncode, r.stdout, r.stderr)
     assert "no CPU fallback" in r.stdout
+
+
+def test_flag_literals_match_header():
+    """The shim passes the RTX_VOIGT_* bits as literals; they must equal the header's values."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "radtxfr_b200.h")).read()
+    val = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define (RTX_VOIGT_[A-Z0-9_]+) (\d+)", hdr)}
+    assert val["RTX_VOIGT_FAST_RCP"] == 1 and val["RTX_VOIGT_FP32"] == 2 and val["RTX_VOIGT_WARPSPEC"] == 4
+    assert val["RTX_VOIGT_LORENTZ"] == 16 and val["RTX_VOIGT_DOPPLER"] == 32 and val["RTX_VOIGT_NOSHIFT"] == 64
+    assert val["RTX_VOIGT_TILE_SHIFT"] == 8
+    shim = open(os.path.join(root, "radtxfr_b200", "hapi_compat.py")).read()
+    assert 'kwargs["_profile_flags"] = 16' in shim and "_profile_flags=32 | (0 if LineShift else 64)" in shim
+    assert '{"fp64": 0, "fp64_fast": 1, "fp32": 2}' in shim
+    rtm = open(os.path.join(root, "radtxfr_b200", "radiative_transfer.py")).read()
+    assert "<< 8" in rtm and "flags |= 4 if" in rtm
