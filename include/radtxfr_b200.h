@@ -108,12 +108,17 @@ int rtx_tape3_read(const char* path, double vmin, double vmax, int64_t capacity,
  *   grid_dev         [nx] sorted ascending (any spacing);   out_dev [n_states][nx], overwritten
  *   flags            RTX_VOIGT_* bits */
 #define RTX_VOIGT_DEFAULT 0
-#define RTX_VOIGT_FAST_RCP 1 /* one Newton step fewer in the reciprocal (rel. err ~1e-12 per term) */
+#define RTX_VOIGT_FAST_RCP 1 /* accepted for compatibility: the one-Newton-step reciprocal is the default now */
 #define RTX_VOIGT_FP32 2 /* optional FP32 evaluation of the asymptote branch (tolerance 1e-5 instead of 1e-9) */
 #define RTX_VOIGT_WARPSPEC 4 /* warp-specialised kernel variant: producer warps run the line prologue one chunk ahead */
 #define RTX_VOIGT_LORENTZ 16 /* Lorentz profile and wing rule of absorptionCoefficient_Lorentz (misc/hapi.py:11144-11381) */
 #define RTX_VOIGT_DOPPLER 32    /* PROFILE_DOPPLER, absorptionCoefficient_Doppler (misc/hapi.py:11384-11550) */
 #define RTX_VOIGT_NOSHIFT 64    /* with RTX_VOIGT_DOPPLER: LineShift=False */
+#define RTX_VOIGT_EXACT_RCP 128 /* second Newton step in the reciprocal: every asymptote-branch term to full double
+                                 * precision (default: one step, relative error <= 2^-40 ~ 9e-13 per term) */
+#define RTX_VOIGT_NOFAR 4096    /* disable the far-field blocks: evaluate every (line, grid point) pair at the grid point
+                                 * itself (default: slices a window covers from >= 0.375 slice widths away are summed
+                                 * at 32 Chebyshev nodes and interpolated, relative error < 1e-13) */
 #define RTX_VOIGT_TILE_SHIFT 8 /* bits 8..11: force 256*K grid points per CTA, K in {1,2,4,8} (0 = automatic).
                                 * The automatic choice between K = 8 and K = 4 reads 8 bytes back from the device
                                 * (one stream synchronisation after a tiny kernel); force K to keep the call fully

@@ -57,6 +57,7 @@ extern "C" int rtx_destroy(rtx_handle* h) {
   free_lines(h->lines);
   for (double* p : {h->d_mass, h->d_tipsT, h->d_q, h->d_qref, h->d_state}) if (p) cudaFree(p);
   if (h->d_bins) cudaFree(h->d_bins);
+  if (h->d_cheb) cudaFree(h->d_cheb);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   delete h;
   return RTX_OK;

@@ -47,6 +47,7 @@ struct rtx_handle {
   double* d_state = nullptr;  size_t state_cap = 0;   // per-state tables
   int32_t* d_bins = nullptr;  size_t bins_cap = 0;    // [n_states][n_tiles][2]
   double* h_pin = nullptr;                             // 2 pinned doubles for small read-backs
+  double* d_cheb = nullptr;                            // Chebyshev tables of the Voigt far-field blocks
   uint64_t launches = 0;
   int last_K = 0;                                      // tile size of the last rtx_voigt_sum
 };

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
     for (int k = 0; k < P.max_cnt; ++k) {
       const double o = od[(int64_t)k * P.nx];
       const double B = planck_fast(c1X3, c2X, s_invT[k], s_exp2);
-      const double t = exp_tab(fmax(-o * mu, -708.0), s_exp2);
+      const double t = exp_tab(fmin(fmax(-o * mu, -708.0), 708.0), s_exp2);
       lu = fma(t, lu - B, B);                                  // t*Lu + (1-t)*B
       for (int a = 0; a < P.n_alt; ++a)
         if (P.cnt[a] == k + 1) P.lu[obase + (int64_t)a * P.n_mu + m] = lu;
@@ -114,11 +114,12 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
       secmax = fmax(secmax, sec[a]);
     }
     for (int j = P.n_down - 1; j >= 0; --j) {
-      const double ao = -fabs(od[(int64_t)j * P.nx]);     // optical depths are non-negative
+      const double ao = -od[(int64_t)j * P.nx];           // signed, like the reference's exp(-OD/cos th) (a continuum
+                                                          // hook may hand in negative optical depths)
       const double B = planck_fast(c1X3, c2X, s_invT[j], s_exp2);
       // optically thin layer for every lane of the warp and every angle of the block (|x| <= 2^-9): the degree-5
       // Taylor polynomial is exact to < 1e-19 and needs no range reduction
-      if (__all_sync(lanes, ao * secmax >= -1.953125e-3)) {
+      if (__all_sync(lanes, fabs(ao) * secmax <= 1.953125e-3)) {
 #pragma unroll
         for (int a = 0; a < ANGLE_BLOCK; ++a) {
           const double x = ao * sec[a];
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
       double xa[ANGLE_BLOCK], tt[ANGLE_BLOCK], r[ANGLE_BLOCK], pz[ANGLE_BLOCK];
 #pragma unroll
       for (int a = 0; a < ANGLE_BLOCK; ++a) {
-        xa[a] = fmax(ao * sec[a], -708.0);                               // exp(-708) = 3e-308: nothing below matters
+        xa[a] = fmin(fmax(ao * sec[a], -708.0), 708.0);                  // exp(-708) = 3e-308: nothing below matters
         tt[a] = fma(xa[a], c_exp[0], c_exp[1]);                          // 256/ln2; 1.5*2^52 puts k in the low word
       }
 #pragma unroll

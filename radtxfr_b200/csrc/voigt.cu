@@ -114,6 +114,8 @@ struct VoigtParams {
   const int32_t* bins;  // [n_states][n_tiles][2]
   double* out;
   int has_self, has_deltap, use_tma;
+  const double* cheb;   // [32] Chebyshev nodes cos(theta_k), then [32][32] node-values -> coefficients matrix [k][m]
+  int far_ok;    // far-field blocks enabled
   int lorentz;   // PROFILE_LORENTZ instead of PROFILE_VOIGT: no Doppler width, wing = max(OmegaWing, HW*Gamma0)
   int doppler;   // PROFILE_DOPPLER (absorptionCoefficient_Doppler): 1 = with line shift, 2 = LineShift=False
 };
@@ -189,27 +191,35 @@ __device__ __forceinline__ double rcp_nr(double x) {
 // -> 8 FP64-pipe operations: DADD, 3 DFMA, MUFU.RCP64H + 3 DFMA (cubic Newton), DFMA.  In the branch's domain
 // (|x|+y >= 15) u is positive and free of cancellation; c is formed from its closed form, not by subtraction.
 template <bool FAST>
-__device__ __forceinline__ double cheap_term(double omega, double sg0, double a, double ah, double m, double c,
-                                             double acc) {
-  const double d = omega - sg0;
+__device__ __forceinline__ double cheap_d(double d, double a, double ah, double m, double c, double acc) {
   const double u = fma(d, d, m);
   const double den = fma(u, u, c);
   const double num = fma(a, u, ah);
   return fma(num, rcp_nr<FAST>(den), acc);
 }
+template <bool FAST>
+__device__ __forceinline__ double cheap_term(double omega, double sg0, double a, double ah, double m, double c,
+                                             double acc) {
+  return cheap_d<FAST>(omega - sg0, a, ah, m, c, acc);
+}
 
 // Two lines through ONE reciprocal:  n1/d1 + n2/d2 = (n1*d2 + n2*d1)/(d1*d2)  -- 15 FP64 operations for two
 // evaluations instead of 16, and half the MUFU traffic (micro-benchmark: +8 % on the test-free path).  All factors
 // are positive and of moderate magnitude in the asymptote branch's domain, so nothing cancels or overflows.
-__device__ __forceinline__ double cheap_pair(double omega, double sg1, double a1, double ah1, double m1, double c1,
-                                             double sg2, double a2, double ah2, double m2, double c2, double acc) {
-  const double d1 = omega - sg1, d2 = omega - sg2;
+template <bool FAST>
+__device__ __forceinline__ double cheap_pair_d(double d1, double a1, double ah1, double m1, double c1, double d2,
+                                               double a2, double ah2, double m2, double c2, double acc) {
   const double u1 = fma(d1, d1, m1), u2 = fma(d2, d2, m2);
   const double den1 = fma(u1, u1, c1), den2 = fma(u2, u2, c2);
   const double n1 = fma(a1, u1, ah1), n2 = fma(a2, u2, ah2);
   const double P = den1 * den2;
   const double X = fma(n2, den1, n1 * den2);
-  return fma(X, rcp_nr<false>(P), acc);
+  return fma(X, rcp_nr<FAST>(P), acc);
+}
+template <bool FAST>
+__device__ __forceinline__ double cheap_pair(double omega, double sg1, double a1, double ah1, double m1, double c1,
+                                             double sg2, double a2, double ah2, double m2, double c2, double acc) {
+  return cheap_pair_d<FAST>(omega - sg1, a1, ah1, m1, c1, omega - sg2, a2, ah2, m2, c2, acc);
 }
 
 // Re w(x+iy) by Weideman's 24-term rational series, misc/hapi.py:9812-9827 (cef):
@@ -252,19 +262,41 @@ struct __align__(16) WideRec32 {
   short lo, hi, core_lo, core_hi;
 };
 static_assert(sizeof(WideRec32) <= sizeof(WideRec), "WideRec32 must fit a WideRec slot");
+// Far-field blocks.  Away from its core a line's contribution is the closed form a*(u+h)/(u^2+c): analytic in omega with
+// poles only at |omega-nu0'| ~ Gamma0, GammaD.  On a warp's slice of 32*K grid points whose nearest point is at least
+// FAR_FRAC slice widths away from the line centre, the degree-31 Chebyshev interpolant through 32 nodes reproduces it
+// to < 1e-13 relative (scale-free in the distance/width ratio: 0.25 -> 7e-12, 0.3 -> 4e-13, 0.375 -> 2e-14, measured
+// for Gamma0 from 1e-4 to 100 grid spacings; tools/farfield_error.py).  So a line that covers such a slice is evaluated
+// at the slice's 32 nodes only -- one node per lane, K times fewer evaluations -- into per-lane node accumulators, and
+// once per (tile, state) the node sums are turned into Chebyshev coefficients and evaluated at the slice's own grid
+// points (Clenshaw at the actual grid values, so nothing assumes a uniform grid).  Window membership stays exact:
+// a slice is far only if the reference's window covers all of it (misc/hapi.py:11133-11134).
+#ifndef RTX_FAR_FRAC
+#define RTX_FAR_FRAC 0.375
+#endif
 // per wide line: bit q = the window touches warp q's slice, bit 8+q = it covers the slice with no Weideman point
-// inside (test-free path)
+// inside (test-free path), bit 16+q = it covers the slice from far away (far-field nodes)
 // With core_ok a covered slice is test-free even when the core lies inside it: pass 1 then evaluates the closed form
 // on the core points too and pass 2 adds (series - closed form) there.
-__device__ __forceinline__ unsigned slice_masks(int lo, int hi, int clo, int chi, int slice, bool core_ok) {
+__device__ __forceinline__ unsigned slice_masks(int lo, int hi, int clo, int chi, int slice, bool core_ok, bool far_ok,
+                                                double sg0, const double* __restrict__ s_grid) {
   unsigned m = 0;
 #pragma unroll
   for (int q = 0; q < NT / 32; ++q) {
     const int a = q * slice, b = a + slice;
     const bool touch = (hi > a) && (lo < b);
-    const bool full = (lo <= a) && (hi >= b) && (core_ok || (chi <= clo) || (chi <= a) || (clo >= b));
+    const bool cover = (lo <= a) && (hi >= b);
+    const bool nocore = (chi <= clo) || (chi <= a) || (clo >= b);
+    bool far = false;
+    if (far_ok && cover && nocore) {
+      const double gf = s_grid[a], gl = s_grid[b - 1];
+      const double D = RTX_FAR_FRAC * (gl - gf);
+      far = (sg0 <= gf - D) || (sg0 >= gl + D);
+    }
+    const bool full = cover && !far && (core_ok || nocore);
     m |= (touch ? 1u : 0u) << q;
     m |= (full ? 1u : 0u) << (8 + q);
+    m |= (far ? 1u : 0u) << (16 + q);
   }
   return m;
 }
@@ -457,7 +489,8 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
   SegRec* s_seg = reinterpret_cast<SegRec*>(s_wide + (F32 ? NBUF * LCHUNK : 0));   // NBUF * LCHUNK
   // per block of 32 lines (one warp, one prologue round) and per consumer warp: which of the 32 records that warp
   // must visit -- windows covering its whole slice, windows touching it, segments touching it
-  __shared__ unsigned s_mfull[NBUF][NBLK][NT / 32], s_mtouch[NBUF][NBLK][NT / 32], s_mseg[NBUF][NBLK][NT / 32];
+  __shared__ unsigned s_mfull[NBUF][NBLK][NT / 32], s_mtouch[NBUF][NBLK][NT / 32], s_mseg[NBUF][NBLK][NT / 32],
+      s_mfar[NBUF][NBLK][NT / 32];
   __shared__ __align__(8) unsigned long long s_bar, s_full[2], s_empty[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -515,6 +548,20 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
   }
 #pragma unroll
   for (int j = 0; j < K; ++j) acc[j] = 0.0;
+
+  // far-field nodes of this warp's slice: omega_k = centre + halfwidth*cos(theta_k), one per lane
+  // The node offset from the slice centre and the centre's offset from the line are formed separately: a node
+  // position rounded to a double near 1000 cm^-1 would be off by ~1e-13, i.e. 2*1e-13/d ~ 1e-11 relative in a term
+  // that varies like 1/d^2, while (centre - nu0') + offset carries only the relative rounding of d itself.
+  const int own_w = warp & (NT / 32 - 1);
+  double xoff, sl_c;
+  {
+    const double sl_first = s_grid[own_w * (32 * K)], sl_last = s_grid[own_w * (32 * K) + 32 * K - 1];
+    sl_c = 0.5 * (sl_first + sl_last);
+    xoff = (0.5 * (sl_last - sl_first) * ((double)(32 * K) / (double)(32 * K - 1))) * P.cheb[lane];
+  }
+  double accn = 0.0;
+  bool far_used = false;
 
   TileScale ts;
   ts.g0 = s_grid[0];
@@ -626,7 +673,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
               // series - closed form on the core points.  The closed form peaks at amp/(2 pi Gamma0), 1/(2 sqrt(pi) y)
               // times the true peak, so the cancellation costs < 3e-13 relative for y >= 1e-4; below that (and in
               // the FP32 mode) the slice keeps the tested path.
-              sr.sub = (!F32 && RTX_CORE_SUB && y >= 1e-4 && y < 15.0) ? 1 : 0;
+              sr.sub = (!F32 && RTX_CORE_SUB && y >= (FAST ? 1e-2 : 1e-4) && y < 15.0) ? 1 : 0;
               has_seg = chi > clo;
             }
           }
@@ -644,7 +691,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
           w3.lo = sr.lo; w3.hi = sr.hi; w3.core_lo = sr.clo; w3.core_hi = sr.chi;
           *reinterpret_cast<WideRec32*>(&wide_b[k]) = w3;
         }
-        wm = slice_masks(sr.lo, sr.hi, sr.clo, sr.chi, 32 * K, sr.sub != 0);
+        wm = slice_masks(sr.lo, sr.hi, sr.clo, sr.chi, 32 * K, sr.sub != 0, K >= 4 && P.far_ok != 0, sr.sg0, s_grid);   // K < 4: too few points per node to pay
       }
       if (is_wide || has_seg) seg_b[k] = sr;
       if (has_seg) {
@@ -656,7 +703,11 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
         const unsigned bt = __ballot_sync(0xffffffffu, (wm >> q) & 1u);
         const unsigned bf = __ballot_sync(0xffffffffu, (wm >> (8 + q)) & 1u);
         const unsigned bs = __ballot_sync(0xffffffffu, (sm >> q) & 1u);
-        if (lane == q) { s_mtouch[buf][blk][q] = bt & ~bf; s_mfull[buf][blk][q] = bf; s_mseg[buf][blk][q] = bs; }
+        const unsigned bn = __ballot_sync(0xffffffffu, (wm >> (16 + q)) & 1u);
+        if (lane == q) {
+          s_mtouch[buf][blk][q] = bt & ~bf & ~bn; s_mfull[buf][blk][q] = bf; s_mseg[buf][blk][q] = bs;
+          s_mfar[buf][blk][q] = bn;
+        }
       }
   };
   // passes 1 and 2 of one consumer warp over the records of buffer `buf`
@@ -693,12 +744,30 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
     for (int blk = 0; blk < NBLK; ++blk) {
       const P1Rec* __restrict__ recs = (F32 ? reinterpret_cast<const P1Rec*>(s_wide) : reinterpret_cast<const P1Rec*>(s_seg)) +
                                        buf * LCHUNK + blk * 32;
+      {
+        // far-field visits: the line is evaluated at this slice's 32 Chebyshev nodes only (one per lane)
+        const SegRec* __restrict__ frecs = s_seg + buf * LCHUNK + blk * 32;
+        unsigned mf = s_mfar[buf][blk][warp];
+        if (mf) far_used = true;
+        while (mf & (mf - 1)) {
+          const SegRec& ra = frecs[__ffs(mf) - 1];
+          mf &= mf - 1;
+          const SegRec& rb = frecs[__ffs(mf) - 1];
+          mf &= mf - 1;
+          accn = cheap_pair_d<FAST>((sl_c - ra.sg0) + xoff, ra.a, ra.ah, ra.m, ra.c, (sl_c - rb.sg0) + xoff, rb.a, rb.ah, rb.m,
+                                    rb.c, accn);
+        }
+        if (mf) {
+          const SegRec& ra = frecs[__ffs(mf) - 1];
+          accn = cheap_d<FAST>((sl_c - ra.sg0) + xoff, ra.a, ra.ah, ra.m, ra.c, accn);
+        }
+      }
       unsigned m = s_mfull[buf][blk][warp];
 #ifdef RTX_DBG_SKIP_FULL
       m = 0;
 #endif
-      if (MODE == 0) {
-        // full-precision FP64 path: records that cover the slice are taken two at a time through one reciprocal
+      if (!F32) {
+        // FP64 paths: records that cover the slice are taken two at a time through one reciprocal
         while (m & (m - 1)) {
           const P1Rec& ra = recs[__ffs(m) - 1];
           m &= m - 1;
@@ -707,7 +776,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
           const double sg1 = ra.sg0, a1 = ra.a, ah1 = ra.ah, m1 = ra.m, c1 = ra.c;
           const double sg2 = rb.sg0, a2 = rb.a, ah2 = rb.ah, m2 = rb.m, c2 = rb.c;
 #pragma unroll
-          for (int j = 0; j < K; ++j) acc[j] = cheap_pair(w[j], sg1, a1, ah1, m1, c1, sg2, a2, ah2, m2, c2, acc[j]);
+          for (int j = 0; j < K; ++j) acc[j] = cheap_pair<FAST>(w[j], sg1, a1, ah1, m1, c1, sg2, a2, ah2, m2, c2, acc[j]);
         }
       }
       while (m) {
@@ -895,6 +964,36 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       consume(buf);
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[buf]);
+    }
+  }
+
+  // ---- far-field epilogue: node sums -> Chebyshev coefficients (lane m holds c_m) -> Clenshaw at the slice's points
+  if (far_used) {                                  // warp-uniform
+    const double* __restrict__ dct = P.cheb + 32;  // [k][m] = (2 - [m==0])/32 * cos(m*theta_k)
+    double cm = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) cm = fma(__shfl_sync(0xffffffffu, accn, k), dct[k * 32 + lane], cm);
+    const double sl_first = s_grid[own_w * (32 * K)], sl_last = s_grid[own_w * (32 * K) + 32 * K - 1];
+    const double inv_hw = 1.0 / (0.5 * (sl_last - sl_first) * ((double)(32 * K) / (double)(32 * K - 1)));
+    const double c0 = __shfl_sync(0xffffffffu, cm, 0);
+    constexpr int G = K < 4 ? K : 4;               // rows per Clenshaw sweep (register budget)
+#pragma unroll
+    for (int j0 = 0; j0 < K; j0 += G) {
+      double x2[G], b1[G], b2[G];
+#pragma unroll
+      for (int j = 0; j < G; ++j) { x2[j] = 2.0 * ((w[j0 + j] - sl_c) * inv_hw); b1[j] = 0.0; b2[j] = 0.0; }
+#pragma unroll 1
+      for (int mm = 31; mm >= 1; --mm) {
+        const double cc = __shfl_sync(0xffffffffu, cm, mm);
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const double b0 = fma(x2[j], b1[j], cc - b2[j]);
+          b2[j] = b1[j];
+          b1[j] = b0;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < G; ++j) acc[j0 + j] += fma(0.5 * x2[j], b1[j], c0 - b2[j]);
     }
   }
 
@@ -1089,7 +1188,24 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
                                                           st_wb, h->d_bins);
   RTX_CUDA(cudaGetLastError());
   h->launches++;
-  const int mode = (flags & RTX_VOIGT_FP32) ? 2 : ((flags & RTX_VOIGT_FAST_RCP) ? 1 : 0);
+  // Chebyshev tables of the far-field blocks (once per handle): cos(theta_k) and the node-values -> coefficients matrix
+  if (!h->d_cheb) {
+    std::vector<double> tab(32 + 32 * 32);
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (int k = 0; k < 32; ++k) {
+      tab[k] = (double)cosl(pi * (2 * k + 1) / 64.0L);
+      for (int m = 0; m < 32; ++m)
+        tab[32 + k * 32 + m] = (double)((m == 0 ? 1.0L : 2.0L) / 32.0L * cosl(pi * m * (2 * k + 1) / 64.0L));
+    }
+    RTX_CUDA(cudaMalloc(&h->d_cheb, tab.size() * sizeof(double)));
+    RTX_CUDA(cudaMemcpyAsync(h->d_cheb, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    RTX_CUDA(cudaStreamSynchronize(st));   // tab is a local
+  }
+  P.cheb = h->d_cheb;
+  P.far_ok = (flags & RTX_VOIGT_NOFAR) ? 0 : 1;
+  // default: paired evaluations through a reciprocal with ONE Newton step (relative error <= 2^-40 ~ 9e-13 per term);
+  // RTX_VOIGT_EXACT_RCP adds the second step (full double precision)
+  const int mode = (flags & RTX_VOIGT_FP32) ? 2 : ((flags & RTX_VOIGT_EXACT_RCP) ? 0 : 1);
   const bool ws = (flags & RTX_VOIGT_WARPSPEC) != 0;
 #define RTX_LAUNCH(KK)                                                                                        \
   (ws ? (mode == 2 ? launch_tile<KK, 2, true>(P, st) : mode == 1 ? launch_tile<KK, 1, true>(P, st) : launch_tile<KK, 0, true>(P, st)) \

@@ -34,6 +34,16 @@ def _torch():
     return torch
 
 
+# RTX_VOIGT_* flag bits (include/radtxfr_b200.h)
+VOIGT_FP32, VOIGT_WARPSPEC, VOIGT_LORENTZ, VOIGT_DOPPLER, VOIGT_NOSHIFT = 2, 4, 16, 32, 64
+VOIGT_EXACT_RCP, VOIGT_NOFAR, VOIGT_TILE_SHIFT = 128, 4096, 8
+# precision names of the shims -> flags.  "fp64" (default): FP64 with the one-Newton-step reciprocal (<= 9e-13 per
+# term) and far-field blocks (< 1e-13); "fp64_fast" is the same thing (kept for round-1 callers); "fp64_exact":
+# every (line, grid point) pair evaluated at the grid point with the fully refined reciprocal; "fp32": optional
+# single-precision asymptote branch (1e-5 parity).
+PRECISION_FLAGS = {"fp64": 0, "fp64_fast": 0, "fp64_exact": VOIGT_EXACT_RCP | VOIGT_NOFAR, "fp32": VOIGT_FP32}
+
+
 def resolve_device(device=None):
     torch = _torch()
     if not torch.cuda.is_available():

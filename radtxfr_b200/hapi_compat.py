@@ -28,8 +28,9 @@ DefaultOmegaWingHW = 50.0         # misc/hapi.py:10218
 cBolts = 1.380648813e-16          # misc/hapi.py:84-92
 cc = 2.99792458e10
 
-# Arithmetic of the Voigt sum: "fp64" (default; 1e-9 parity), "fp64_fast" (one Newton step fewer in the
-# reciprocal, ~1e-12 per term) or "fp32" (optional single-precision asymptote branch, 1e-5 parity).
+# Arithmetic of the Voigt sum: "fp64" (default; 1e-9 parity: one-Newton-step reciprocal ~1e-12 per term, far-field
+# blocks < 1e-13), "fp64_exact" (every pair at its own grid point, fully refined reciprocal) or "fp32" (optional
+# single-precision asymptote branch, 1e-5 parity); engine.PRECISION_FLAGS.
 VARIABLES = {"precision": "fp64"}
 
 _linedb_cache = {}
@@ -187,7 +188,7 @@ def absorptionCoefficient_Voigt(Components=None, SourceTables=None, partitionFun
     xs = db.voigt_sum(np.array([T]), np.array([p]), w_iso[None, :], Omegas, x_air=x_air, x_self=x_self,
                       wing_abs=float(OmegaWing), wing_hw=float(OmegaWingHW),
                       s_threshold=float(IntensityThreshold),
-                      flags={"fp64": 0, "fp64_fast": 1, "fp32": 2}[VARIABLES["precision"]] | int(_profile_flags))[0]
+                      flags=engine.PRECISION_FLAGS[VARIABLES["precision"]] | int(_profile_flags))[0]
     if as_tensor:
         return Omegas, xs
     return Omegas, xs.cpu().numpy()

@@ -46,7 +46,8 @@ options = {
     # --- additions of this implementation -----------------------------------------------------
     "LINE_DB": None,        # engine.LineDB, set through set_line_database()
     "voigt": {},            # extra Voigt settings: OmegaWing, OmegaWingHW, IntensityThreshold, Diluent, and
-                            # precision: "fp64" (default, 1e-9), "fp64_fast" (one Newton step fewer), "fp32" (1e-5)
+                            # precision: "fp64" (default, 1e-9), "fp64_exact" (no far-field blocks, fully refined
+                            # reciprocal), "fp32" (1e-5) -- see engine.PRECISION_FLAGS
 }
 
 
@@ -144,7 +145,8 @@ def _to_host(*tensors, outs=None, early=None):
     if outs is None:
         outs = [np.empty(v.shape, dtype=np.float64) for v in views]
     if total < (1 << 18):
-        torch.cuda.current_stream(tensors[0].device).synchronize()
+        for ev in events:                             # some transfers ran on the side stream: wait for each one
+            ev.synchronize()
         for o, v in zip(outs, views):
             np.copyto(o, v)
     else:
@@ -176,7 +178,7 @@ def _voigt_settings(opts):
     dil = v.get("Diluent") or {"air": 1.0}
     x_air = float(sum(val for k, val in dil.items() if k.lower() == "air"))
     x_self = float(sum(val for k, val in dil.items() if k.lower() == "self"))
-    flags = {"fp64": 0, "fp64_fast": 1, "fp32": 2}[v.get("precision", "fp64")]
+    flags = engine.PRECISION_FLAGS[v.get("precision", "fp64")]
     flags |= int(v.get("tile_k", 0)) << 8          # 0 = automatic tile size
     flags |= 4 if v.get("ws", False) else 0
     return dict(x_air=x_air, x_self=x_self, wing_abs=float(v.get("OmegaWing", 0.0)),
@@ -270,6 +272,8 @@ def compute_TUD(Xmin, Xmax, opts=options, **kwargs):
     od = db.voigt_sum(Td, pd, wd, grid, out=_od_workspace(db.device, T.size, nX),
                       **_voigt_settings(opts))                                  # [nL, nX], layer-major
     if opts.get("continuum_od") is not None:
+        if X_ is None and callable(opts["continuum_od"]):
+            X_ = make_spectral_axis(Xmin, Xmax, opts["DVOUT"])     # a callable always receives the numpy axis
         od = _add_continuum(od, opts, X_ if X_ is not None else grid, T, P, PL, MF, ID)
     tau, lu, ld, up_ready = engine.tud(od, Td[None, :], grid, Z, Z_s, mu_s, nA, returnOD, split=True)
     # the kernels are in flight: build the host axis and pre-touch the result arrays meanwhile

@@ -66,10 +66,11 @@ def test_xsect_golden_cases(mods):
 
 
 @pytest.mark.parametrize("K", [1, 2, 4, 8])
-@pytest.mark.parametrize("fast", [0, 1, 4, 5])
-def test_voigt_all_tile_sizes(mods, K, fast):
-    """Every tile-size instantiation of the kernel, both reciprocal variants, plain and warp-specialised (flag 4),
-    on a multi-state problem that mixes wide (1 atm) and narrow (top of atmosphere) lines."""
+@pytest.mark.parametrize("variant", [0, 128, 4096, 128 | 4096, 4, 4 | 128 | 4096])
+def test_voigt_all_tile_sizes(mods, K, variant):
+    """Every tile-size instantiation of the kernel; default arithmetic (one-Newton-step reciprocal + far-field blocks),
+    RTX_VOIGT_EXACT_RCP (128), RTX_VOIGT_NOFAR (4096), both, plain and warp-specialised (flag 4), on a multi-state
+    problem that mixes wide (1 atm) and narrow (top of atmosphere) lines."""
     port, syn, engine = mods["port"], mods["syn"], mods["engine"]
     cols = syn.synthetic_lines(50, 400, 985.0, 1015.0, 1)
     db = engine.LineDB(cols)
@@ -77,10 +78,40 @@ def test_voigt_all_tile_sizes(mods, K, fast):
     states = [(296.0, 1.0), (250.0, 0.2), (225.53, 7.3 / 101325.0), (216.7, 0.02)]
     T = np.array([s[0] for s in states]); p = np.array([s[1] for s in states])
     w = np.tile(db.iso_factors(None, 1.0), (len(states), 1))
-    out = db.voigt_sum(T, p, w, grid, flags=fast | (K << 8)).cpu().numpy()
+    out = db.voigt_sum(T, p, w, grid, flags=variant | (K << 8)).cpu().numpy()
     for k, (Tk, pk) in enumerate(states):
         _, ref = port.absorption_coefficient_voigt(cols, T=Tk, p=pk, OmegaGrid=grid)
-        assert_parity(out[k], ref, RTOL, FLOOR, "K=%d fast=%d state %d" % (K, fast, k))
+        assert_parity(out[k], ref, RTOL, FLOOR, "K=%d variant=%d state %d" % (K, variant, k))
+
+
+@pytest.mark.parametrize("K", [4, 8])
+def test_voigt_far_field_blocks(mods, K):
+    """Far-field blocks (slices a window covers from >= 0.375 slice widths away are summed at 32 Chebyshev nodes and
+    interpolated): on a fine grid where most evaluations take that path, the result agrees with the node-free
+    evaluation (RTX_VOIGT_NOFAR | RTX_VOIGT_EXACT_RCP) to 5e-12 and with the oracle to the parity tolerance; worst
+    cases: a strong isolated line next to weak ones (the window cut of the strong line must stay exact), a grid whose
+    spacing changes by a factor of 3 half way (Clenshaw runs on the actual grid values), and a jittered grid."""
+    port, syn, engine = mods["port"], mods["syn"], mods["engine"]
+    cols = syn.synthetic_lines(52, 300, 992.0, 1008.0, 1)
+    cols["sw"][::37] *= 1e6                                   # a few lines 10^6 times stronger than their neighbours
+    db = engine.LineDB(cols)
+    states = [(296.0, 1.0), (260.0, 0.5), (230.0, 0.1)]
+    T = np.array([s[0] for s in states]); p = np.array([s[1] for s in states])
+    w = np.tile(db.iso_factors(None, 1.0), (len(states), 1))
+    rng = np.random.default_rng(5)
+    uniform = np.linspace(995.0, 1005.0, 20001)
+    two_step = np.concatenate([np.linspace(995.0, 1000.0, 15001)[:-1], np.linspace(1000.0, 1005.0, 5001)])
+    jitter = np.sort(uniform + rng.uniform(-2e-4, 2e-4, uniform.size))
+    for name, grid in (("uniform", uniform), ("two_step", two_step), ("jitter", jitter)):
+        far = db.voigt_sum(T, p, w, grid, flags=(K << 8)).cpu().numpy()
+        fx = db.voigt_sum(T, p, w, grid, flags=128 | (K << 8)).cpu().numpy()
+        exact = db.voigt_sum(T, p, w, grid, flags=128 | 4096 | (K << 8)).cpu().numpy()
+        assert np.max(np.abs(fx - exact) / np.maximum(exact, 1e-300)) < 2e-13, name        # the interpolation alone
+        assert np.max(np.abs(far - exact) / np.maximum(exact, 1e-300)) < 5e-12, name       # plus the one-step reciprocal
+        assert not np.array_equal(far, db.voigt_sum(T, p, w, grid, flags=4096 | (K << 8)).cpu().numpy())  # path taken
+        for k, (Tk, pk) in enumerate(states[:2]):
+            _, ref = port.absorption_coefficient_voigt(cols, T=Tk, p=pk, OmegaGrid=grid)
+            assert_parity(far[k], ref, RTOL, FLOOR, "far K=%d %s state %d" % (K, name, k))
 
 
 def test_voigt_fp32_option(mods):
@@ -455,9 +486,16 @@ def test_full_size_properties(mods):
     od2 = db.voigt_sum(atm["Ts"], p, 2.0 * w, grid)
     assert torch.equal(od2, 2.0 * od)                                   # exact: power-of-two scaling
     assert torch.equal(od, db.voigt_sum(atm["Ts"], p, w, grid))         # bit-reproducible
+    # tile-size independence: K=2 has no far-field blocks and pairs lines differently -> default arithmetic agrees
+    # to its own bound (one-step reciprocal 9e-13 per term), the exact arithmetic to rounding
     od_k2 = db.voigt_sum(atm["Ts"], p, w, grid, flags=2 << 8)
-    err = (od_k2 - od).abs().max().item() / od.abs().max().item()
-    assert err < 1e-13
+    err = ((od_k2 - od).abs() / od.abs().clamp_min(1e-300)).max().item()
+    assert err < 5e-12, err
+    ex8 = db.voigt_sum(atm["Ts"], p, w, grid, flags=128 | 4096 | (8 << 8))
+    ex2 = db.voigt_sum(atm["Ts"], p, w, grid, flags=128 | 4096 | (2 << 8))
+    assert ((ex8 - ex2).abs().max() / ex8.abs().max()).item() < 1e-13
+    assert ((od - ex8).abs() / ex8.abs().clamp_min(1e-300)).max().item() < 5e-12
+    del od_k2, ex8, ex2
     sub = slice(0, 2000)
     for layer in (0, 30, 65):
         ref = port.layer_od(tabs, X[sub], atm["Ts"][layer], atm["Ps"][layer], atm["PLs"][layer],
@@ -633,6 +671,43 @@ def test_voigt_automatic_tile_size(mods):
             _, ref = port.absorption_coefficient_voigt(cols, T=T[k], p=p[k], OmegaGrid=grid)
             assert_parity(out[k], ref, RTOL, FLOOR, "%s grid state %d" % (name, k))
     assert picked == {"fine": 8, "coarse": 4}, picked
+
+
+def test_tud_negative_optical_depth(mods):
+    """A continuum hook may hand in negative layer optical depths: every exp(-OD...) of the layer integration uses the
+    signed value, like the reference (radiative_transfer.py:349-355, :371), in the upwelling, transmittance AND
+    downwelling halves -- including the thin-layer fast path (|OD|/cos(th) <= 2^-9) and large negative values."""
+    engine, port = mods["engine"], mods["port"]
+    rng = np.random.default_rng(21)
+    nL, nx = 20, 2100
+    X = np.linspace(700.0, 1400.0, nx)
+    OD = rng.uniform(-0.4, 1.0, (nx, nL)) * rng.uniform(0, 1, (nx, 1))
+    OD[:700] *= 1e-3                                  # thin layers of both signs
+    OD[700:710, 3] = -30.0                            # strongly negative: exp(+30/cos th)
+    Z = np.linspace(0.0, 60.0, nL); T = rng.uniform(200.0, 300.0, nL)
+    tau, lu, ld = engine.tud(np.ascontiguousarray(OD.T), T[None, :], X, Z, [7.0, 500.0], [1.0, 1.2], 30)
+    t_ref, u_ref, d_ref = port.tud_from_od(X, OD, Z, T, N_angle=30, Altitudes=np.array([7.0, 500.0]), theta_r=0.0)
+    assert_parity(tau[0, :, :, 0].cpu().numpy(), t_ref, RTOL, FLOOR, "tau negative OD")
+    assert_parity(lu[0, :, :, 0].cpu().numpy(), u_ref, RTOL, FLOOR, "Lu negative OD")
+    for sl in (slice(0, 700), slice(710, nx)):        # row-wise: the exp(+30) rows would swamp the floor term
+        assert_parity(ld[0, sl].cpu().numpy(), d_ref[sl], RTOL, FLOOR, "Ld negative OD")
+    assert_parity(ld[0, 700:710].cpu().numpy(), d_ref[700:710], RTOL, FLOOR, "Ld strongly negative OD")
+
+
+def test_small_compute_tud_alternating(mods):
+    """Small outputs take the single-staging-buffer path of _to_host with tau/Lu copied on a side stream: alternate two
+    different atmospheres many times and require every call to return its own result (a missing wait on the side
+    stream would hand back stale bytes of the previous call)."""
+    rt, syn = mods["rt"], mods["syn"]
+    atm, tabs, opts, kw = _tud_setup(mods)
+    Ts, MF = syn.perturbed_atmospheres(7, 2)
+    want = [rt.compute_TUD(700.0, 730.0, opts=dict(opts), **dict(kw, Ts=Ts[j], MFs_VAL=MF[j])) for j in (0, 1)]
+    assert not np.array_equal(want[0][1], want[1][1])
+    for it in range(40):
+        j = it & 1
+        got = rt.compute_TUD(700.0, 730.0, opts=dict(opts), **dict(kw, Ts=Ts[j], MFs_VAL=MF[j]))
+        for a, b in zip(got, want[j]):
+            assert np.array_equal(a, b), (it, j)
 
 
 def test_tud_split_halves(mods):

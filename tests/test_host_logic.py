@@ -224,6 +224,16 @@ def test_flag_literals_match_header():
     assert val["RTX_VOIGT_TILE_SHIFT"] == 8
     shim = open(os.path.join(root, "radtxfr_b200", "hapi_compat.py")).read()
     assert 'kwargs["_profile_flags"] = 16' in shim and "_profile_flags=32 | (0 if LineShift else 64)" in shim
-    assert '{"fp64": 0, "fp64_fast": 1, "fp32": 2}' in shim
+    assert val["RTX_VOIGT_EXACT_RCP"] == 128 and val["RTX_VOIGT_NOFAR"] == 4096
+    import types
+    eng_src = open(os.path.join(root, "radtxfr_b200", "engine.py")).read()
+    consts = dict(re.findall(r"^(VOIGT_[A-Z0-9_]+(?:, VOIGT_[A-Z0-9_]+)*) = (.+)$", eng_src, flags=re.M))
+    ns = types.SimpleNamespace()
+    for names, vals in consts.items():
+        for n, v in zip(names.split(", "), vals.split(", ")):
+            setattr(ns, n, int(v))
+    for n in ("FP32", "WARPSPEC", "LORENTZ", "DOPPLER", "NOSHIFT", "EXACT_RCP", "NOFAR", "TILE_SHIFT"):
+        assert getattr(ns, "VOIGT_" + n) == val["RTX_VOIGT_" + n], n
+    assert "engine.PRECISION_FLAGS[" in shim
     rtm = open(os.path.join(root, "radtxfr_b200", "radiative_transfer.py")).read()
     assert "<< 8" in rtm and "flags |= 4 if" in rtm

@@ -34,18 +34,19 @@ def main():
     wd = torch.from_numpy(w).cuda()
     od = torch.empty((66, X.size), dtype=torch.float64, device="cuda")
     if only is None:
-        a0 = db.voigt_sum(T, pd, wd, grid, flags=0).clone()
-        a1 = db.voigt_sum(T, pd, wd, grid, flags=1)
-        rel = ((a1 - a0).abs() / a0.abs().clamp_min(1e-300)).max().item()
-        print("max relative deviation FAST_RCP vs default: %.3e" % rel, flush=True)
+        a0 = db.voigt_sum(T, pd, wd, grid, flags=128 | 4096).clone()          # exact reciprocal, no far-field blocks
+        for name, fl in (("default (one-step rcp + far-field)", 0), ("far-field only", 128), ("one-step rcp only", 4096)):
+            a1 = db.voigt_sum(T, pd, wd, grid, flags=fl)
+            rel = ((a1 - a0).abs() / a0.abs().clamp_min(1e-300)).max().item()
+            print("max relative deviation of %s vs exact: %.3e" % (name, rel), flush=True)
         del a0, a1
     cases = []
     for K in (8,):
-        for fast in (0, 1, 2, 4):
-            cases.append(("cfg2 K=%d fast=%d" % (K, fast), dict(flags=fast | (K << 8)), T, pd, wd))
+        for fast in (0, 128, 4096, 128 | 4096, 2, 4):
+            cases.append(("cfg2 K=%d flags=%d" % (K, fast), dict(flags=fast | (K << 8)), T, pd, wd))
     # all-wide: every line +-25 cm^-1 -> almost every visit takes the test-free path
     cases.append(("wide25 K=8 fast=0", dict(flags=8 << 8, wing_abs=25.0), T[:8], pd[:8], wd[:8]))
-    cases.append(("wide25 K=8 fast=1", dict(flags=1 | (8 << 8), wing_abs=25.0), T[:8], pd[:8], wd[:8]))
+    cases.append(("wide25 K=8 nofar", dict(flags=4096 | (8 << 8), wing_abs=25.0), T[:8], pd[:8], wd[:8]))
     cases.append(("wide25 K=8 fp32", dict(flags=2 | (8 << 8), wing_abs=25.0), T[:8], pd[:8], wd[:8]))
     cases.append(("wide25 K=4 fast=0", dict(flags=4 << 8, wing_abs=25.0), T[:8], pd[:8], wd[:8]))
     # per-layer groups of config 2
