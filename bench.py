@@ -171,6 +171,101 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def banded_leg(args, rank, world, dev):
+    """Config 5 (BASELINE.json configs[4]): 500-6000 cm^-1, --banded-points grid points x 60 layers, --banded-lines
+    synthetic lines of eight gases, sharded by wavenumber band over the ranks with ONE all_gather
+    (distributed.compute_TUD_banded) -- the strong-scaling partitioning of the path.  Reports the device-timed rate
+    (max over ranks, results left in HBM), the end-to-end time with every rank copying the full spectra to numpy,
+    rank 0's single-GPU time for the same problem (the efficiency denominator), and whether the gathered result equals
+    the single-GPU result bit for bit on every rank; at N > 1 the atmosphere-sharded batch is checked the same way."""
+    import torch
+    import torch.distributed as dist
+    from radtxfr_b200 import distributed as D, radiative_transfer as rt, synthetic as syn
+    if world == 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+        own_group = True
+    else:
+        own_group = False
+    atm = syn.standard_atmosphere()
+    n_layers = 60
+    tabs = syn.config5_tables(args.banded_lines)
+    opts = dict(rt.options)
+    t0 = time.perf_counter()
+    db = rt.set_line_database(tabs, device=dev, opts=opts)
+    ingest_s = time.perf_counter() - t0
+    nx = args.banded_points
+    dv = (6000.0 - 500.0) / nx
+    kw = dict(Zs=atm["Zs"][:n_layers], Ts=atm["Ts"][:n_layers], Ps=atm["Ps"][:n_layers], PLs=atm["PLs"][:n_layers],
+              MFs_VAL=atm["MFs_VAL"][:n_layers], MFs_ID=atm["MFs_ID"], DVOUT=dv, N_angle=N_ANGLE)
+    reps = 3
+
+    def timed(fn):
+        fn()                                             # warm-up (workspaces, pinned staging)
+        best_dev, best_wall = 1e30, 1e30
+        for _ in range(reps):
+            dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tw = time.perf_counter(); e0.record()
+            out = fn()
+            e1.record(); torch.cuda.synchronize()
+            wall = time.perf_counter() - tw
+            t = torch.tensor([e0.elapsed_time(e1), 1e3 * wall], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)      # max over ranks
+            best_dev, best_wall = min(best_dev, t[0].item()), min(best_wall, t[1].item())
+        return out, best_dev, best_wall
+
+    (X, tau_d, lu_d, ld_d), ms_dev, _ = timed(lambda: D.compute_TUD_banded(500.0, 6000.0, dict(opts), to_host=False, **kw))
+    (_, tau_h, lu_h, ld_h), _, ms_e2e = timed(lambda: D.compute_TUD_banded(500.0, 6000.0, dict(opts), **kw))
+    # exact evals of the whole problem (outside any timed region)
+    p, w = rt.layer_weights(db, kw["Ts"], kw["Ps"], kw["PLs"], kw["MFs_VAL"], kw["MFs_ID"])
+    grid = torch.from_numpy(X).to(dev)
+    ev, evw = db.count_evals(kw["Ts"], p, w, grid)
+    del grid
+    # the same problem on ONE GPU (every rank does it, so every rank checks its gathered copy): device time of the
+    # Voigt sum + layer integration, then bit-for-bit comparison
+    o1 = dict(opts); o1["voigt"] = {"tile_k": 8}
+    ident, ms_one = True, None
+    if world > 1:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rt.compute_TUD(500.0, 6000.0, opts=dict(o1), **kw)           # warm-up: workspaces of the full width
+        e0.record()
+        X1, t1, u1, d1 = rt.compute_TUD(500.0, 6000.0, opts=dict(o1), **kw)
+        e1.record(); torch.cuda.synchronize()
+        ms_one = e0.elapsed_time(e1)
+        ident = bool(np.array_equal(t1, tau_h) and np.array_equal(u1, lu_h) and np.array_equal(d1, ld_h)
+                     and np.array_equal(tau_d.cpu().numpy(), tau_h))
+        del X1, t1, u1, d1
+        # atmosphere-sharded batch (config 3's partitioning) against the unsharded batch on this rank
+        Ts, MF = syn.perturbed_atmospheres(5, 2 * world + 1)
+        kb = dict(Zs=atm["Zs"], Ps=atm["Ps"], PLs=atm["PLs"], MFs_ID=atm["MFs_ID"], DVOUT=dv * 8, N_angle=N_ANGLE)
+        Xb, tb, ub, db_ = D.compute_TUD_batch_sharded(900.0, 1100.0, Ts, MF, dict(opts), **kb)
+        Xs, ts, us, ds = rt.compute_TUD_batch(900.0, 1100.0, Ts, MF, opts=dict(opts), **kb)
+        ident = ident and bool(torch.equal(tb, ts) and torch.equal(ub, us) and torch.equal(db_, ds))
+    flag = torch.tensor([int(ident)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if own_group:
+        dist.destroy_process_group()
+    out = {"bit_identical": bool(flag.item() == 1) if world > 1 else None,
+           "workload": "config5: 500-6000 cm^-1, %d points x %d layers, %d synthetic lines of 8 gases, band-sharded over %d "
+                       "GPU(s), one all_gather of (tau, Lu, Ld)" % (nx, n_layers, args.banded_lines, world),
+           "scaling": "strong", "evals": ev, "weideman_fraction": evw / max(1, ev), "ms": ms_dev, "evals_per_s": ev / (ms_dev * 1e-3),
+           "e2e_ms": ms_e2e, "e2e_evals_per_s": ev / (ms_e2e * 1e-3),
+           "e2e_note": "every rank copies the full (tau, Lu, Ld) = %d MB to fresh numpy arrays" % (3 * 8 * nx // 1000000),
+           "timing": "best of %d, CUDA events on the launching stream / wall clock, max over ranks" % reps,
+           "ingest_s": ingest_s}
+    if ms_one is not None:
+        out["single_gpu_ms"] = ms_one
+        out["single_gpu_evals_per_s"] = ev / (ms_one * 1e-3)
+        out["efficiency_vs_single_gpu"] = ms_one / (world * ms_dev)
+        out["single_gpu_note"] = ("radiative_transfer.compute_TUD of the same problem on rank 0's GPU, numpy out (includes "
+                                  "its 264 MB device-to-host copy, so the efficiency is slightly flattering; compare "
+                                  "evals_per_s across N in SCALE for the strict figure)")
+    return out
+
+
 # --------------------------------------------------------------------------------------------- GPU arm
 def gpu_arm(args):
     import torch
@@ -270,8 +365,12 @@ def gpu_arm(args):
         dist.barrier()
     t1 = time.perf_counter()
     ms_total = ev[0].elapsed_time(ev_end)
-    ms_voigt = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps))
-    ms_tud = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps))
+    v_steps = [ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)]
+    t_steps = [ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps)]
+    ms_voigt, ms_tud = sum(v_steps), sum(t_steps)
+
+    def stats(v):
+        return {"min": float(np.min(v)), "median": float(np.median(v)), "max": float(np.max(v))}
     launches = db.handle.launches() + h0.launches() - launches0
     tot = torch.tensor([ms_total, float(E), float(Ew), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -282,31 +381,60 @@ def gpu_arm(args):
         E_all, Ew_all, launches_all = float(E), float(Ew), float(launches)
     clk = clocks.stop(t0, t1) if rank == 0 else None
 
-    # ---- end-to-end through the reference-facing API: numpy in, numpy out, copies inside the timed region
+    # ---- end-to-end through the reference-facing API: numpy in, numpy out, copies inside the timed region.
+    # N = 1: radiative_transfer.compute_TUD.  N > 1: distributed.compute_TUD_batch_sharded -- every step hands N
+    # atmospheres (host arrays) to the ranks, each rank integrates its own, the spectra are all-gathered over NCCL and
+    # rank 0 copies the gathered result of all N atmospheres to host memory.
     e2e = None
     if not args.no_e2e:
+        from radtxfr_b200 import distributed as D
         opts = dict(rt.options)
         opts["LINE_DB"] = db
         kw = dict(Zs=atm["Zs"], Ps=atm["Ps"], PLs=atm["PLs"], MFs_ID=atm["MFs_ID"], DVOUT=DV, N_angle=N_ANGLE)
-        rt.compute_TUD(XMIN, XMAX, opts=dict(opts), Ts=Ts_all[0], MFs_VAL=MF_all[0], **kw)   # warm
+        if world == 1:
+            def e2e_step(i):
+                return rt.compute_TUD(XMIN, XMAX, opts=dict(opts), Ts=Ts_all[i], MFs_VAL=MF_all[i], **kw)
+            h2d = 8 * (3 * nL + nL * db.n_iso)  # T, p, T (TUD) and column amounts; the spectral axis is cached on the device
+            d2h = 8 * 3 * nX
+            api = "radtxfr_b200.radiative_transfer.compute_TUD (numpy in, numpy out; line table resident)"
+        else:
+            # the same N atmospheres on every rank's host (rank r's draw for step i is atmosphere r of the step)
+            allT = [torch.empty((nsteps, nL), dtype=torch.float64, device=dev) for _ in range(world)]
+            allM = [torch.empty((nsteps,) + MF_all.shape[1:], dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(allT, torch.from_numpy(Ts_all).to(dev))
+            dist.all_gather(allM, torch.from_numpy(MF_all).to(dev))
+            T_steps = torch.stack(allT, dim=1).cpu().numpy()          # [nsteps, world, nL]
+            M_steps = torch.stack(allM, dim=1).cpu().numpy()
+
+            def e2e_step(i):
+                Xo, tau_d, lu_d, ld_d = D.compute_TUD_batch_sharded(XMIN, XMAX, T_steps[i], M_steps[i], dict(opts), **kw)
+                if rank == 0:
+                    return rt._to_host(tau_d, lu_d, ld_d)
+                return None
+            h2d = 8 * (3 * nL + nL * db.n_iso)
+            d2h = 8 * 3 * nX * world
+            api = ("radtxfr_b200.distributed.compute_TUD_batch_sharded (N atmospheres as numpy in; NCCL all_gather of "
+                   "(tau, Lu, Ld); rank 0 copies all N spectra to numpy); d2h bytes are rank 0's")
+        e2e_step(0)   # warm
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0e = time.perf_counter()
         for k in range(args.steps):
-            i = args.warmup + k
-            Xo, tau_h, lu_h, ld_h = rt.compute_TUD(XMIN, XMAX, opts=dict(opts), Ts=Ts_all[i], MFs_VAL=MF_all[i], **kw)
+            e2e_step(args.warmup + k)
         torch.cuda.synchronize()
         dte = time.perf_counter() - t0e
         if world > 1:
             t = torch.tensor([dte], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dte = t.item()
-        h2d = 8 * (3 * nL + nL * db.n_iso)      # T, p, T (TUD) and column amounts; the spectral axis is cached on the device
-        d2h = 8 * 3 * nX
         e2e = {"value": E_all / dte, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": 1e3 * dte / args.steps,
-               "api": "radtxfr_b200.radiative_transfer.compute_TUD (numpy in, numpy out; line table resident)"}
+               "ms_per_step": 1e3 * dte / args.steps, "api": api}
+
+    # ---- multi-GPU parity and the band-sharded strong-scaling leg (config 5), outside the timed region above
+    banded = None
+    if not args.no_banded:
+        banded = banded_leg(args, rank, world, dev)
 
     if rank == 0:
         secs = ms_total * 1e-3
@@ -341,6 +469,7 @@ def gpu_arm(args):
             "tud_spectra_per_s": world * args.steps / secs,
             "evals_per_step": E / args.steps, "weideman_fraction": Ew / max(1, E),
             "ms_voigt_per_step": ms_voigt / args.steps, "ms_tud_per_step": ms_tud / args.steps,
+            "per_step_ms": {"voigt": stats(v_steps), "tud": stats(t_steps)},
             "ingest_s": ingest_s,
             "roofline": {"bound": "fp64", "kernel": "voigt_tile_kernel", "achieved": achieved / 1e12,
                          "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
@@ -359,6 +488,16 @@ def gpu_arm(args):
                                               "time the copy rate would need"}},
             "clocks": clk, "gpu_launches": int(launches_all),
         }
+        # layer-integration kernel against the same measured FP64 rate: SURVEY.md 8d counts 5.9e4 flop per grid point
+        # (2113 exp x 25 + recurrences) at 66 layers and 30 angles; the kernel issues ~10 FP64 operations per exp
+        tud_flops = 5.9e4 * nX
+        line["roofline_tud"] = {"bound": "fp64", "kernel": "tud_kernel", "achieved": tud_flops / (ms_tud / args.steps * 1e-3) / 1e12,
+                                "peak": peak / 1e12, "unit": "TFLOP/s", "frac": tud_flops / (ms_tud / args.steps * 1e-3) / peak,
+                                "flops_model": "5.9e4 algorithmic flop per grid point: 2113 FP64 exp x 25 + 3 x 2046 "
+                                               "recurrence + 200 (SURVEY.md 8d)"}
+        if banded:
+            line["multi_gpu_bit_identical"] = banded.pop("bit_identical")
+            line["banded"] = banded
         if e2e:
             line["e2e"] = e2e
         if cpu:
@@ -378,6 +517,9 @@ def main():
     ap.add_argument("--flags", type=int, default=0, help="RTX_VOIGT_* flags for rtx_voigt_sum")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-banded", action="store_true", help="skip the config-5 band-sharded leg and the multi-GPU parity check")
+    ap.add_argument("--banded-points", type=int, default=11_000_000)
+    ap.add_argument("--banded-lines", type=int, default=5_000_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(ILS_THREADS) ils_kernel(const double* __restri
     } else {           // Gaussian: below 3e-18 of the peak beyond 9 sigma
       s_range[0] = bisect_left_dev64(X, nx, c - 9.5 * sg);
       s_range[1] = bisect_right_dev64(X, nx, c + 9.5 * sg);
+      if (s_range[1] <= s_range[0]) { s_range[0] = 0; s_range[1] = nx; }   // centre outside the axis: sum it all
     }
   }
   __syncthreads();
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(ILS_THREADS) ils_wide_kernel(const double* __r
     const double half = (MODE == 0) ? sg : 9.5 * sg;
     s_range[0] = bisect_left_dev64(X, nx, c - half);
     s_range[1] = bisect_right_dev64(X, nx, c + half);
+    if (MODE == 1 && s_range[1] <= s_range[0]) { s_range[0] = 0; s_range[1] = nx; }
   }
   __syncthreads();
   const int64_t lo = s_range[0], hi = s_range[1];
@@ -142,6 +144,105 @@ __global__ void __launch_bounds__(ILS_THREADS) ils_wide_kernel(const double* __r
     out[(int64_t)b * ns + sidx] = a / wt;
   }
 }
+
+// Many-spectra variant, grouped (ns >= 16): one CTA owns G ADJACENT bands and 32 spectra and walks the UNION of the
+// bands' supports once, so a sample row Y[x][s0..s0+31] (one coalesced 256-byte load per warp) feeds every band of
+// the group that covers it -- MAKO bands overlap ~3.1-fold, so a band-per-CTA walk reads every sample 3.1 times,
+// a group of 8 reads (8 + 2.1)/8 = 1.26 times the unique bytes and the rest of the overlap is between neighbouring
+// CTAs that run at the same time (L2).  Lanes run along the spectrum index; per 32-sample step every lane forms the G
+// weights of ONE sample (coalesced read of X) into the warp's shared-memory tile, then all lanes stream the 32 rows
+// and take the weights as shared-memory broadcasts; bands whose support misses the step are skipped warp-uniformly.
+// The eight warps interleave the steps; the final sum over warps is in fixed order (deterministic).
+// Gaussian bands whose 9.5-sigma support holds no sample at all (centre outside the axis) fall back to the whole
+// axis, which is what the reference sums (ILS_MAKO.py:24-34).
+constexpr int ILS_G = 8;
+template <int MODE>
+__global__ void __launch_bounds__(ILS_THREADS) ils_group_kernel(const double* __restrict__ X, int64_t nx,
+                                                                const double* __restrict__ Y, int64_t ns,
+                                                                int n_bands, const double* __restrict__ centre,
+                                                                const double* __restrict__ width,
+                                                                double* __restrict__ out) {
+  constexpr int NW = ILS_THREADS / 32;
+  const int b0 = blockIdx.x * ILS_G;
+  const int ng = min(ILS_G, n_bands - b0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t sidx = (int64_t)blockIdx.y * 32 + lane;
+  const bool live = sidx < ns;
+  __shared__ int64_t s_lo[ILS_G], s_hi[ILS_G];
+  __shared__ double s_c[ILS_G], s_isg[ILS_G], s_gn[ILS_G];
+  __shared__ double s_w[NW][32][ILS_G];
+  __shared__ double s_acc[NW][ILS_G][32], s_ws[NW][ILS_G];
+  if (threadIdx.x < ILS_G) {
+    const int g = threadIdx.x;
+    int64_t lo = 0, hi = 0;
+    double c = 0.0, sg = 1.0;
+    if (g < ng) {
+      c = centre[b0 + g]; sg = width[b0 + g];
+      const double half = (MODE == 0) ? sg : 9.5 * sg;
+      lo = bisect_left_dev64(X, nx, c - half);
+      hi = bisect_right_dev64(X, nx, c + half);
+      if (MODE == 1 && hi <= lo) { lo = 0; hi = nx; }
+    }
+    s_lo[g] = lo; s_hi[g] = hi; s_c[g] = c; s_isg[g] = 1.0 / sg; s_gn[g] = sg * 2.5066282746310002;
+  }
+  __syncthreads();
+  int64_t ulo = nx, uhi = 0;
+#pragma unroll
+  for (int g = 0; g < ILS_G; ++g)
+    if (g < ng && s_hi[g] > s_lo[g]) { ulo = min(ulo, s_lo[g]); uhi = max(uhi, s_hi[g]); }
+  double acc[ILS_G], wl[ILS_G];
+#pragma unroll
+  for (int g = 0; g < ILS_G; ++g) { acc[g] = 0.0; wl[g] = 0.0; }
+  const double* __restrict__ ycol = Y + (live ? sidx : 0);
+  for (int64_t base = ulo + 32 * warp; base < uhi; base += 32 * NW) {
+    const int64_t ix = base + lane;
+    const double x = ix < uhi ? X[ix] : 0.0;
+    unsigned act = 0;                                   // bands whose support meets this step (warp-uniform)
+#pragma unroll
+    for (int g = 0; g < ILS_G; ++g) {
+      double w = 0.0;
+      if (g < ng && ix >= s_lo[g] && ix < s_hi[g]) {
+        if (MODE == 0) {
+          w = 1.0 - fabs(x - s_c[g]) * s_isg[g];        // tri(), radiative_transfer.py:1236-1239
+          if (w < 0.0) w = 0.0;
+        } else {
+          const double u = (x - s_c[g]) * s_isg[g];
+          w = exp(-0.5 * (u * u)) / s_gn[g];            // g(), ILS_MAKO.py:24
+        }
+      }
+      s_w[warp][lane][g] = w;
+      wl[g] += w;
+      if (g < ng && base < s_hi[g] && base + 32 > s_lo[g]) act |= 1u << g;
+    }
+    __syncwarp();
+    const int cnt = (int)min((int64_t)32, uhi - base);
+#pragma unroll 4
+    for (int k = 0; k < cnt; ++k) {
+      const double y = ycol[(base + k) * ns];
+#pragma unroll
+      for (int g = 0; g < ILS_G; ++g)
+        if (act & (1u << g)) acc[g] = fma(s_w[warp][k][g], y, acc[g]);
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int g = 0; g < ILS_G; ++g) {
+    double t = wl[g];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    s_acc[warp][g][lane] = acc[g];
+    if (lane == 0) s_ws[warp][g] = t;
+  }
+  __syncthreads();
+  if (warp < ng && live) {
+    const int g = warp;                                 // warp g finishes band g (ILS_G == warps per CTA)
+    double a = 0.0, wt = 0.0;
+#pragma unroll
+    for (int q = 0; q < NW; ++q) { a += s_acc[q][g][lane]; wt += s_ws[q][g]; }
+    out[(int64_t)(b0 + g) * ns + sidx] = a / wt;        // Y_out = sum(ILS*Y)/N
+  }
+}
+static_assert(ILS_G == ILS_THREADS / 32, "one finishing warp per band of the group");
 
 // thread per (x, a, t): one Planck evaluation shared by all emissivities
 __global__ void apparent_kernel(const double* __restrict__ X, int64_t nx, const double* __restrict__ emis,
@@ -277,7 +378,7 @@ extern "C" int rtx_ils_apply(rtx_handle* h, int mode, const double* X_dev, int64
                              int n_bands, const double* centre_dev, const double* width_dev, double* out_dev,
                              void* stream) {
   RTX_REQUIRE(h != nullptr, "null handle");
-  RTX_REQUIRE(mode == 0 || mode == 1, "rtx_ils_apply: mode must be 0 (triangle) or 1 (Gaussian)");
+  RTX_REQUIRE((mode & ~0x101) == 0, "rtx_ils_apply: mode must be 0 (triangle) or 1 (Gaussian) [| 0x100: band-per-CTA walk]");
   RTX_REQUIRE(nx > 0 && ns > 0 && n_bands >= 0, "rtx_ils_apply: bad sizes");
   if (n_bands == 0) return RTX_OK;
   RTX_REQUIRE(X_dev && Y_dev && centre_dev && width_dev && out_dev, "rtx_ils_apply: null pointer");
@@ -285,14 +386,23 @@ extern "C" int rtx_ils_apply(rtx_handle* h, int mode, const double* X_dev, int64
   const int64_t sblocks = wide ? (ns + 31) / 32 : (ns + ILS_SBLK - 1) / ILS_SBLK;
   RTX_REQUIRE(sblocks <= 65535, "rtx_ils_apply: too many spectra for one call (max 2097120)");
   DeviceGuard guard(h->device);
-  dim3 grid((unsigned)n_bands, (unsigned)sblocks);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (wide) {
-    if (mode == 0) ils_wide_kernel<0><<<grid, ILS_THREADS, 0, st>>>(X_dev, nx, Y_dev, ns, centre_dev, width_dev, out_dev);
-    else ils_wide_kernel<1><<<grid, ILS_THREADS, 0, st>>>(X_dev, nx, Y_dev, ns, centre_dev, width_dev, out_dev);
+  // grouped walk (each sample read once per 8 adjacent bands) when it still fills the machine; band-per-CTA otherwise
+  const int64_t groups = (n_bands + ILS_G - 1) / ILS_G;
+  if (wide && groups * sblocks >= 2LL * h->sm_count && !(mode & 0x100)) {
+    dim3 grid((unsigned)groups, (unsigned)sblocks);
+    if ((mode & 1) == 0) ils_group_kernel<0><<<grid, ILS_THREADS, 0, st>>>(X_dev, nx, Y_dev, ns, n_bands, centre_dev, width_dev, out_dev);
+    else ils_group_kernel<1><<<grid, ILS_THREADS, 0, st>>>(X_dev, nx, Y_dev, ns, n_bands, centre_dev, width_dev, out_dev);
   } else {
-    if (mode == 0) ils_kernel<0><<<grid, ILS_THREADS, 0, st>>>(X_dev, nx, Y_dev, ns, centre_dev, width_dev, out_dev);
-    else ils_kernel<1><<<grid, ILS_THREADS, 0, st>>>(X_dev, nx, Y_dev, ns, centre_dev, width_dev, out_dev);
+    mode &= 1;
+    dim3 grid((unsigned)n_bands, (unsigned)sblocks);
+    if (wide) {
+      if (mode == 0) ils_wide_kernel<0><<<grid, ILS_THREADS, 0, st>>>(X_dev, nx, Y_dev, ns, centre_dev, width_dev, out_dev);
+      else ils_wide_kernel<1><<<grid, ILS_THREADS, 0, st>>>(X_dev, nx, Y_dev, ns, centre_dev, width_dev, out_dev);
+    } else {
+      if (mode == 0) ils_kernel<0><<<grid, ILS_THREADS, 0, st>>>(X_dev, nx, Y_dev, ns, centre_dev, width_dev, out_dev);
+      else ils_kernel<1><<<grid, ILS_THREADS, 0, st>>>(X_dev, nx, Y_dev, ns, centre_dev, width_dev, out_dev);
+    }
   }
   RTX_CUDA(cudaGetLastError());
   h->launches++;

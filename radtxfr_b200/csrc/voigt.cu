@@ -671,9 +671,11 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
               // The slice that holds the core of a wide line would need per-point tests in pass 1.  Instead pass 1
               // treats it like any covered slice (closed form on every point, finite for Gamma0 > 0) and pass 2 adds
               // series - closed form on the core points.  The closed form peaks at amp/(2 pi Gamma0), 1/(2 sqrt(pi) y)
-              // times the true peak, so the cancellation costs < 3e-13 relative for y >= 1e-4; below that (and in
-              // the FP32 mode) the slice keeps the tested path.
-              sr.sub = (!F32 && RTX_CORE_SUB && y >= (FAST ? 1e-2 : 1e-4) && y < 15.0) ? 1 : 0;
+              // times the true peak, so the cancellation costs < 3e-13 relative for y >= 1e-4 with the fully refined
+              // reciprocal; with the one-step reciprocal (9e-13 per term, and pass 1 pairs lines differently from pass 2)
+              // it costs 9e-13/(2 sqrt(pi) y), hence y >= 0.1 there (< 3e-12).  Below that (and in the FP32 mode) the
+              // slice keeps the tested path.
+              sr.sub = (!F32 && RTX_CORE_SUB && y >= (FAST ? 1e-1 : 1e-4) && y < 15.0) ? 1 : 0;
               has_seg = chi > clo;
             }
           }

@@ -6,7 +6,7 @@ The path shards two ways, both exchange-free until the end:
     the atmosphere table, so rank r integrates the contiguous band [i0, i1) of the spectral axis with the full line
     table resident (the kernel's device-side binning picks the lines that reach the band -- a line halo, not a
     data halo) and the ranks all-gather (tau, Lu, Ld).  Bands start on multiples of the kernel's 2048-point tile
-    and the tile size is pinned, so the gathered result is bit-identical to a single-GPU run.
+    and the tile size is pinned, so the gathered result is bit-identical to a single-GPU run with the same tile size.
   * by atmosphere (config 3): rank r takes atmospheres r, r+world, ...; results are all-gathered (optionally after
     the MAKO ILS, which shrinks the exchange from nX to 128 values per spectrum).
 Per-layer optical depth is never exchanged.
@@ -48,6 +48,19 @@ def _dist():
     return dist
 
 
+def _all_gather_flat(out, inp, group=None):
+    """all_gather_into_tensor of flat tensors.  NCCL takes device tensors directly; under the gloo backend (CPU tests,
+    or several ranks sharing one GPU while debugging) device tensors are staged through the host."""
+    import torch
+    dist = _dist()
+    if inp.is_cuda and dist.get_backend(group) == "gloo":
+        host = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_gather_into_tensor(host, inp.cpu(), group=group)
+        out.copy_(host)
+    else:
+        dist.all_gather_into_tensor(out, inp, group=group)
+
+
 def all_gather_bands(local, bands, group=None):
     """local: tensor [n_fields, i1-i0] holding this rank's band; returns [n_fields, nx] on every rank.
     One all_gather of equal-size (padded) shards -- the path's single collective."""
@@ -62,7 +75,7 @@ def all_gather_bands(local, bands, group=None):
     pad = torch.zeros((nf, width), dtype=local.dtype, device=local.device)
     pad[:, : i1 - i0] = local
     flat = torch.empty(world * pad.numel(), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(flat, pad.reshape(-1), group=group)      # 1-D in/out works on nccl and gloo
+    _all_gather_flat(flat, pad.reshape(-1), group)                       # 1-D in/out works on nccl and gloo
     out = flat.view(world, nf, width)
     nx = bands[-1][1]
     full = torch.empty((nf, nx), dtype=local.dtype, device=local.device)
@@ -83,7 +96,7 @@ def all_gather_atmospheres(local, owners, n_atm, group=None):
     pad = torch.zeros((width,) + rest, dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     flat = torch.empty(world * pad.numel(), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(flat, pad.reshape(-1), group=group)
+    _all_gather_flat(flat, pad.reshape(-1), group)
     out = flat.view((world, width) + rest)
     full = torch.empty((n_atm,) + rest, dtype=local.dtype, device=local.device)
     for r, o in enumerate(owners):
@@ -92,10 +105,44 @@ def all_gather_atmospheres(local, owners, n_atm, group=None):
     return full
 
 
-def compute_TUD_banded(Xmin, Xmax, opts, group=None, **kwargs):
+def estimate_tile_costs(db, T, p_atm, X, tile=TILE, wing_hw=50.0, wing_abs=0.0):
+    """Relative cost of every `tile`-point tile of the axis X for the Voigt kernel: the number of (line, state) pairs
+    whose wing can reach the tile, plus the pairs whose centre lies in it (the near zone is evaluated point by point,
+    everything further out at 32 nodes per 256 points, so the work per reaching pair is roughly constant).  Host-side,
+    from the sorted line centres and the column extrema the LineDB keeps -- an estimate for balancing bands
+    ("balance bands by estimated evals, not by width"), not a count."""
+    X = np.asarray(X, dtype=float)
+    T = np.asarray(T, dtype=float).ravel()
+    p_atm = np.asarray(p_atm, dtype=float).ravel()
+    ntiles = (X.size + tile - 1) // tile
+    lo = X[np.arange(ntiles) * tile]
+    hi = X[np.minimum((np.arange(ntiles) + 1) * tile, X.size) - 1]
+    nu = db.nu_sorted
+    cost = np.zeros(ntiles)
+    if nu.size == 0:
+        return cost + 1.0
+    # wing bound per state, as the kernel's state_prep does it: max(OmegaWing, HW*Gamma0_max, HW*GammaD_max)
+    r = 296.0 / T
+    g0 = np.abs(p_atm) * db.gamma_air_max * np.maximum(r ** db.n_air_range[0], r ** db.n_air_range[1])
+    gd = db.nu_max * np.sqrt(2.0 * 1.380648813e-16 * T * np.log(2.0) / (db.mass_min * 1.66053873e-24)) / 2.99792458e10
+    wb = np.maximum(np.maximum(wing_abs, wing_hw * g0), wing_hw * gd)
+    inside = (np.searchsorted(nu, hi, side="right") - np.searchsorted(nu, lo, side="left")).astype(float)
+    for w in np.unique(np.round(wb, 6)):
+        n = float(np.sum(np.round(wb, 6) == w))
+        reach = np.searchsorted(nu, hi + w, side="right") - np.searchsorted(nu, lo - w, side="left")
+        cost += n * (reach + 2.0 * inside)
+    return cost + 1.0
+
+
+def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True, **kwargs):
     """compute_TUD with the spectral axis sharded by band across the ranks of `group`.  Same arguments and return
     value as radiative_transfer.compute_TUD (single altitude / view angle shapes follow the same squeeze rules);
-    every rank returns the full spectra.  Bit-identical to the single-GPU call."""
+    every rank returns the full spectra -- numpy arrays, or CUDA tensors with to_host=False.
+    Bands start on multiples of the kernel's 2048-point tile and the tile size is pinned (K = 8), so the gathered
+    result is bit-identical to a single-GPU compute_TUD with opts["voigt"] = {"tile_k": 8} (the automatic tile size of
+    the single-GPU call may pick 1024-point tiles, whose summation order differs).  balance=True cuts the bands by
+    estimated cost (estimate_tile_costs) instead of by size.  The three spectra of every rank travel in ONE
+    all_gather of equal-size shards; the host copy goes through the pinned, threaded path of compute_TUD."""
     import torch
     from . import engine, radiative_transfer as rt
     dist = _dist()
@@ -106,27 +153,41 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, **kwargs):
     Z_s = np.array([opts["Altitudes"]]).ravel()
     mu_s = np.array([1.0 / np.cos(opts["theta_r"])]).ravel()
     X_ = rt.make_spectral_axis(Xmin, Xmax, opts["DVOUT"])
-    bands = plan_bands(X_.size, world)
-    i0, i1 = bands[rank]
+    nX = X_.size
     db.check_temperatures(T)
     p, w = rt.layer_weights(db, T, opts["Ps"], opts["PLs"], opts["MFs_VAL"], opts["MFs_ID"])
-    nf = 2 * Z_s.size * mu_s.size + 1
-    if i1 > i0:
-        grid = engine.to_device(X_[i0:i1], db.device)
-        vs = rt._voigt_settings(opts)
-        vs["flags"] |= FORCE_K8
-        od = db.voigt_sum(T, p, w, grid, **vs)
-        tau, lu, ld = engine.tud(od, T[None, :], grid, Z, Z_s, mu_s, opts["N_angle"], opts["returnOD"])
-        n = i1 - i0
-        local = torch.cat([tau[0].reshape(n, -1).T, lu[0].reshape(n, -1).T, ld[0].reshape(1, n)], dim=0).contiguous()
-    else:
-        local = torch.zeros((nf, 0), dtype=torch.float64, device=db.device)
-    full = all_gather_bands(local, bands, group)
+    vs = rt._voigt_settings(opts)
+    vs["flags"] = (vs["flags"] & ~(0xF << 8)) | FORCE_K8
+    costs = estimate_tile_costs(db, T, p, X_, TILE, vs["wing_hw"], vs["wing_abs"]) if balance else None
+    bands = plan_bands(nX, world, weights=costs)
+    i0, i1 = bands[rank]
     k = Z_s.size * mu_s.size
-    nX = X_.size
-    tau_ = full[:k].T.reshape(nX, Z_s.size, mu_s.size).cpu().numpy()
-    Lu_ = full[k:2 * k].T.reshape(nX, Z_s.size, mu_s.size).cpu().numpy()
-    Ld_ = full[2 * k].cpu().numpy()
+    nf = 2 * k + 1
+    width = max(1, max(b - a for a, b in bands))
+    shard = torch.zeros((nf, width), dtype=torch.float64, device=db.device)       # equal-size shard, padded
+    if i1 > i0:
+        n = i1 - i0
+        grid = engine.to_device(X_[i0:i1], db.device)
+        od = db.voigt_sum(T, p, w, grid, out=rt._od_workspace(db.device, T.size, n), **vs)
+        tau, lu, ld = engine.tud(od, T[None, :], grid, Z, Z_s, mu_s, opts["N_angle"], opts["returnOD"])
+        if k == 1:
+            shard[0, :n] = tau.reshape(n); shard[1, :n] = lu.reshape(n)
+        else:
+            shard[:k, :n] = tau[0].reshape(n, k).T; shard[k:2 * k, :n] = lu[0].reshape(n, k).T
+        shard[2 * k, :n] = ld[0]
+    flat = torch.empty((world, nf, width), dtype=torch.float64, device=db.device)
+    _all_gather_flat(flat.view(-1), shard.view(-1), group)                      # the path's single collective
+    full = torch.cat([flat[r, :, : b - a] for r, (a, b) in enumerate(bands) if b > a], dim=1)     # [nf, nX]
+    if k == 1:
+        tau_d, lu_d = full[0].reshape(nX, 1, 1), full[1].reshape(nX, 1, 1)
+    else:
+        tau_d = full[:k].T.contiguous().reshape(nX, Z_s.size, mu_s.size)
+        lu_d = full[k:2 * k].T.contiguous().reshape(nX, Z_s.size, mu_s.size)
+    ld_d = full[2 * k]
+    if to_host:
+        tau_, Lu_, Ld_ = rt._to_host(tau_d, lu_d, ld_d)
+    else:
+        tau_, Lu_, Ld_ = tau_d, lu_d, ld_d
     if (len(Z_s) == 1) and (len(mu_s) == 1):
         tau_, Lu_ = tau_[:, 0, 0], Lu_[:, 0, 0]
     elif len(Z_s) == 1:

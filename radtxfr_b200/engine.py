@@ -6,7 +6,6 @@ the hot path is a kernel of libradtxfr_b200.so.  There is no CPU fallback.
 import ctypes
 import os
 import threading
-import zlib
 
 import numpy as np
 
@@ -146,20 +145,26 @@ def default_handle(device=None):
 _COLS_OPTIONAL = ("gamma_self", "n_self", "delta_self", "deltap_air", "deltap_self")
 
 
-def table_fingerprint(cols):
-    crc = 0
-    n = len(cols["nu"])
+def table_fingerprint(cols, samples=32):
+    """Cheap change detector for a hapi-style table (dict of columns): per column its identity, length and `samples`
+    evenly spaced elements -- O(columns), not O(rows), so a cached LineDB can be validated on every call (a CRC of every
+    column cost ~1 ms per call for 20 000 lines).  Appending or replacing rows / columns changes it; an in-place edit
+    that leaves every sampled element unchanged does not -- call hapi_compat.invalidate(name) (or storeTable again)
+    after such an edit."""
+    parts = []
     for k in sorted(cols):
         v = cols[k]
+        n = len(v)
+        if n == 0:
+            parts.append((k, id(v), 0))
+            continue
+        idx = range(0, n, max(1, n // samples))
         if isinstance(v, np.ndarray):
-            crc = zlib.crc32(np.ascontiguousarray(v).view(np.uint8), crc)
+            sample = v[:: max(1, n // samples)].tobytes()
         else:
-            try:
-                crc = zlib.crc32(np.asarray(v).tobytes(), crc)
-            except Exception:
-                crc = zlib.crc32(repr(v).encode(), crc)
-        crc = zlib.crc32(k.encode(), crc)
-    return (n, crc)
+            sample = tuple(v[i] for i in idx)
+        parts.append((k, id(v), n, hash(sample)))
+    return tuple(parts)
 
 
 class LineDB:
@@ -227,6 +232,12 @@ class LineDB:
         self.has_self = cat["gamma_self"] is not None
         self.nu_min = float(cat["nu"].min()) if self.n_lines else 0.0
         self.nu_max = float(cat["nu"].max()) if self.n_lines else 0.0
+        # host-side summary for cost estimates (distributed.estimate_tile_costs): sorted line centres and the extrema
+        # that bound a line's wing
+        self.nu_sorted = np.sort(cat["nu"])
+        self.gamma_air_max = float(cat["gamma_air"].max()) if self.n_lines else 0.0
+        self.n_air_range = (float(cat["n_air"].min()), float(cat["n_air"].max())) if self.n_lines else (0.0, 0.0)
+        self.mass_min = float(np.min(mass))
 
     # -- abundance factors ------------------------------------------------------------------------
     def iso_factors(self, Components=None, factor=1.0):

@@ -80,24 +80,33 @@ def _tips_db(mi):
 def storeTable(name, cols):
     """Convenience: put a dict of columns into LOCAL_TABLE_CACHE the way hapi lays tables out."""
     LOCAL_TABLE_CACHE[name] = {"header": {"table_name": name, "number_of_rows": len(cols["nu"])}, "data": cols}
+    invalidate(name)
+
+
+def invalidate(name=None):
+    """Drop the device copies of table `name` (all tables when None): the next call uploads again.  Needed only after
+    an in-place edit of column values that engine.table_fingerprint cannot see."""
+    for key in [k for k in _linedb_cache if name is None or name in k[0]]:
+        del _linedb_cache[key]
 
 
 def line_database(SourceTables, device=None):
     """Device-resident LineDB for a tuple of table names, re-uploaded only when the table data changed."""
     names = tuple(SourceTables)
-    tabs = []
+    tabs, fps = [], []
     for n in names:
         if n not in LOCAL_TABLE_CACHE:
             raise Exception("%s: no such table. Check tableList() for more info." % n)   # misc/hapi.py:10242
         data = LOCAL_TABLE_CACHE[n]["data"]
         nrow = LOCAL_TABLE_CACHE[n].get("header", {}).get("number_of_rows", len(data["nu"]))
+        fps.append((nrow, engine.table_fingerprint(data)))
         if nrow != len(data["nu"]):
             data = {k: v[:nrow] for k, v in data.items()}      # the reference loops range(number_of_rows)
         if len(data["molec_id"]) != len(data["local_iso_id"]):
             raise Exception("Lengths if mol_ids and iso_ids differ!")                     # misc/hapi.py:10246
         tabs.append(data)
     dev = engine.resolve_device(device)
-    fp = tuple(engine.table_fingerprint(t) for t in tabs)
+    fp = tuple(fps)
     key = (names, dev.index)
     hit = _linedb_cache.get(key)
     if hit is None or hit[0] != fp:

@@ -307,6 +307,8 @@ def compute_TUD_batch(Xmin, Xmax, Ts, MFs_VAL, opts=options, atm_chunk=None, ils
     PL = np.asarray(opts["PLs"], dtype=float)
     Ts = np.asarray(Ts, dtype=float)
     MF = np.asarray(MFs_VAL, dtype=float)
+    Ts = Ts.reshape(-1, Z.size)
+    MF = MF.reshape(Ts.shape[0], Z.size, MF.shape[-1])
     n_atm, nL = Ts.shape
     Z_s = np.array([opts["Altitudes"]]).ravel()
     mu_s = np.array([1.0 / np.cos(opts["theta_r"])]).ravel()
@@ -315,13 +317,17 @@ def compute_TUD_batch(Xmin, Xmax, Ts, MFs_VAL, opts=options, atm_chunk=None, ils
     db.check_temperatures(Ts)
     grid = engine.to_device(X_, db.device)
     if atm_chunk is None:
-        atm_chunk = max(1, min(n_atm, int(4e9 // (8 * nL * nX))))           # <= 4 GB of optical depth at a time
+        atm_chunk = max(1, min(max(n_atm, 1), int(4e9 // (8 * nL * nX))))   # <= 4 GB of optical depth at a time
     atm_chunk = min(int(atm_chunk), 32768)                                  # rtx_tud: n_atm <= 65535 per launch
     vs = _voigt_settings(opts)
     outs = []
     band = None
     if ils is not None:
         band = _mako_bands(X_, None, 1.0, 0.0, 1.0) if ils == "triangle" else _mako_bands_gauss()
+    if n_atm == 0:                                   # a rank that owns no atmosphere (distributed.compute_TUD_batch_sharded)
+        nout = nX if band is None else band[0].size
+        z = torch.zeros((0, nout, Z_s.size, mu_s.size), dtype=torch.float64, device=db.device)
+        return (band[0] if band is not None else X_), z, z.clone(), torch.zeros((0, nout), dtype=torch.float64, device=db.device)
     od_buf = torch.empty((atm_chunk * nL, nX), dtype=torch.float64, device=db.device)
     for a0 in range(0, n_atm, atm_chunk):
         a1 = min(n_atm, a0 + atm_chunk)

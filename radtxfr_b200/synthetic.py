@@ -56,6 +56,17 @@ def config2_tables(scale=1.0, nu_lo=690.0, nu_hi=1510.0, seed=1):
     return out
 
 
+CONFIG5_MOLECULES = (1, 2, 3, 4, 5, 6, 7, 22)             # options["MFs_ID"], radiative_transfer.py:177
+CONFIG5_SHARES = (0.25, 0.25, 0.2, 0.08, 0.05, 0.12, 0.03, 0.02)
+
+
+def config5_tables(n_lines=5_000_000, nu_lo=475.0, nu_hi=6025.0, seed=4):
+    """Config 5: all eight gases of the reference's default MFs_ID over 500-6000 cm^-1: synthetic lines,
+    seed 4, HITRAN-like shares per molecule -> {molec_id: table}."""
+    return {m: synthetic_lines(seed * 1000 + k, max(1, int(n_lines * s)), nu_lo, nu_hi, m, (1,), (1.0,))
+            for k, (m, s) in enumerate(zip(CONFIG5_MOLECULES, CONFIG5_SHARES))}
+
+
 def merge_tables(tables_by_mol):
     """Concatenate per-molecule tables into one table sorted by line centre."""
     keys = None

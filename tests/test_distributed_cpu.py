@@ -25,6 +25,25 @@ def test_plan_bands_properties():
     assert bands[0] == (0, 9 * D.TILE) and bands[1] == (9 * D.TILE, 10 * D.TILE)
 
 
+def test_estimate_tile_costs_balances_dense_regions():
+    """Cost-balanced bands: a line list three times denser in the upper half of the axis moves the cut towards it."""
+    import types
+    rng = np.random.default_rng(0)
+    nu = np.sort(np.concatenate([rng.uniform(700.0, 1100.0, 2000), rng.uniform(1100.0, 1500.0, 6000)]))
+    db = types.SimpleNamespace(nu_sorted=nu, nu_max=float(nu.max()), gamma_air_max=0.1, n_air_range=(0.4, 0.8), mass_min=18.0)
+    X = np.linspace(700.0, 1500.0, 800000)
+    T = np.linspace(290.0, 220.0, 10); p = np.geomspace(1.0, 0.01, 10)
+    cost = D.estimate_tile_costs(db, T, p, X)
+    assert cost.size == (X.size + D.TILE - 1) // D.TILE and (cost > 0).all()
+    half = cost.size // 2
+    assert 2.5 < cost[half:].sum() / cost[:half].sum() < 3.5
+    by_cost = D.plan_bands(X.size, 2, weights=cost)
+    by_size = D.plan_bands(X.size, 2)
+    assert by_cost[0][1] > by_size[0][1] and by_cost[0][1] % D.TILE == 0
+    loads = [cost[a // D.TILE:(b + D.TILE - 1) // D.TILE].sum() for a, b in by_cost]
+    assert abs(loads[0] - loads[1]) / sum(loads) < 0.02
+
+
 def test_plan_atmospheres():
     o = D.plan_atmospheres(10, 4)
     assert [list(x) for x in o] == [[0, 4, 8], [1, 5, 9], [2, 6], [3, 7]]

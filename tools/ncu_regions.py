@@ -11,10 +11,13 @@ MARKERS = [("line state (S, widths, wing)", "struct LineState"),
            ("records, searches, TIPS", "struct __align__(16) WideRec"),
            ("kernel set-up (TMA tile, registers)", "__global__ void __launch_bounds__"),
            ("prologue: records and masks", "auto produce = "),
-           ("pass 1: test-free visits", "auto consume = "),
+           ("pass 1: visit set-up", "auto consume = "),
+           ("pass 1: far-field visits (32 nodes per slice)", "// far-field visits:"),
+           ("pass 1: test-free visits", "unsigned m = s_mfull[buf][blk][warp];"),
            ("pass 1: partial visits", "m = s_mtouch["),
            ("pass 2: wings and cores", "---- pass 2"),
            ("chunk loop and barriers", "if (!WS) {"),
+           ("far-field epilogue (coefficients, Clenshaw)", "---- far-field epilogue"),
            ("(after the kernel)", "// exact eval counter")]
 RAW = ["gpu__time_duration.sum", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
