@@ -179,6 +179,13 @@ int rtx_apparent_radiance(rtx_handle* h, const double* X_dev, int64_t nx, const 
                           const double* ld_dev, const double* dT_dev, int64_t n_dT, double* L_dev,
                           double* ls_dev, void* stream);
 
+/* float32-output variant (the reference's production script casts every input to float32 and stores a float32 cube,
+ * Compute_LWIR_Apparent_Radiance.py:9-25): same FP64 arithmetic on the same double inputs, rounded once at the store. */
+int rtx_apparent_radiance_f32(rtx_handle* h, const double* X_dev, int64_t nx, const double* emis_dev, int64_t n_emis,
+                              const double* Ts_dev, int64_t n_atm, const double* tau_dev, const double* la_dev,
+                              const double* ld_dev, const double* dT_dev, int64_t n_dT, float* L_dev,
+                              float* ls_dev, void* stream);
+
 /* Per-pixel mixed-material variant: the inner loop of LWIR_HSI_gen (LWIR_HSI_Generator.py:148-166).
  * For pixel k: em = sum_m frac[k][m]*emis[mat[k][m]][:],  L[k][x] = tau[atm[k]][x]*(em*B(X[x],T[k]) +
  * (1-em)*Ld[atm[k]][x]) + La[atm[k]][x].   emis_dev [n_emis][nx], tau/la/ld [n_atm][nx] (band-minor, the
@@ -188,11 +195,20 @@ int rtx_hsi_pixels(rtx_handle* h, const double* X_dev, int64_t nx, const double*
                    int64_t n_pix, const int32_t* atm_idx_dev, const double* T_pix_dev, int n_mix,
                    const int32_t* mat_idx_dev, const double* frac_dev, double* L_dev, void* stream);
 
+/* float32 cube (config 4's "FP32 variant"): L_dev [n_pix][nx] float. */
+int rtx_hsi_pixels_f32(rtx_handle* h, const double* X_dev, int64_t nx, const double* emis_dev, int64_t n_emis,
+                       const double* tau_dev, const double* la_dev, const double* ld_dev, int64_t n_atm,
+                       int64_t n_pix, const int32_t* atm_idx_dev, const double* T_pix_dev, int n_mix,
+                       const int32_t* mat_idx_dev, const double* frac_dev, float* L_dev, void* stream);
+
 /* ---- subsystem 4: MAKO instrument line shape ---------------------------------------------
  * The weighted-mean resampling at the heart of ILS_MAKO (triangle: radiative_transfer.py:1236-1256;
  * Gaussian: ILS_MAKO.py:24-34).  Band centres and widths are prepared by the shim exactly as the
  * reference does (sort, clip, gradient; :1226-1241).
  *   mode 0: w = max(0, 1-|x-c_b|/s_b);  mode 1: w = exp(-0.5((x-c_b)/s_b)^2)/(s_b*sqrt(2pi))
+ *   (experiment bits: | 0x100 band-per-CTA walk, | 0x200 grouped walk without TMA staging, | 0x400 / 0x800 two / one
+ *    spectra per lane, | 0x1000 groups of 16 bands; default for ns >= 16: groups of 8 adjacent bands, tiles of 32-64 rows
+ *    x 64-32 spectra staged in shared memory by 2-D tensor-map TMA copies)
  *   X_dev [nx] ascending, Y_dev [nx][ns], centre_dev/width_dev [n_bands], out_dev [n_bands][ns]
  *   out[b][s] = sum_x w*Y / sum_x w */
 int rtx_ils_apply(rtx_handle* h, int mode, const double* X_dev, int64_t nx, const double* Y_dev, int64_t ns,

@@ -41,6 +41,10 @@ _SIGNATURES = {
                               c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
     "rtx_hsi_pixels": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                        c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "rtx_apparent_radiance_f32": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p],
+    "rtx_hsi_pixels_f32": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                           c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "rtx_ils_apply": [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p,
                       c_void_p, c_void_p],
     "rtx_smooth_sym": [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p],

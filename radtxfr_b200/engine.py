@@ -434,7 +434,8 @@ def ils_apply(mode, X, Y, centres, widths, device=None):
     return out
 
 
-def apparent_radiance(X, emis, Ts, tau, La, Ld, dT=None, return_Ls=False, device=None):
+def apparent_radiance(X, emis, Ts, tau, La, Ld, dT=None, return_Ls=False, device=None, out_dtype=None):
+    """rtx_apparent_radiance; out_dtype=torch.float32 selects the float32-output variant (rtx_apparent_radiance_f32)."""
     torch = _torch()
     dev = resolve_device(device if not (isinstance(tau, torch.Tensor) and tau.is_cuda) else tau.device)
     h = default_handle(dev)
@@ -447,17 +448,18 @@ def apparent_radiance(X, emis, Ts, tau, La, Ld, dT=None, return_Ls=False, device
     dTt = to_device(dT, dev).reshape(-1) if dT is not None else None
     nT = dTt.numel() if dTt is not None else 1
     shape = (nx, emis.shape[1], nA) + ((nT,) if dTt is not None else ())
-    L = torch.empty(shape, dtype=torch.float64, device=dev)
+    f32 = out_dtype == torch.float32
+    L = torch.empty(shape, dtype=torch.float32 if f32 else torch.float64, device=dev)
     Ls = torch.empty_like(L) if return_Ls else None
     if L.numel():
-        _lib.call("rtx_apparent_radiance", h.h, _ptr(X), nx, _ptr(emis), emis.shape[1], _ptr(Ts), nA, _ptr(tau),
-                  _ptr(La), _ptr(Ld), _ptr(dTt), nT, _ptr(L), _ptr(Ls), _stream(dev))
+        _lib.call("rtx_apparent_radiance_f32" if f32 else "rtx_apparent_radiance", h.h, _ptr(X), nx, _ptr(emis),
+                  emis.shape[1], _ptr(Ts), nA, _ptr(tau), _ptr(La), _ptr(Ld), _ptr(dTt), nT, _ptr(L), _ptr(Ls), _stream(dev))
     return (L, Ls) if return_Ls else L
 
 
-def hsi_pixels(X, emis, tau, La, Ld, atm_idx, T_pix, mat_idx, frac, device=None):
+def hsi_pixels(X, emis, tau, La, Ld, atm_idx, T_pix, mat_idx, frac, device=None, out_dtype=None):
     """rtx_hsi_pixels: emis [n_emis, nx], tau/La/Ld [n_atm, nx], per-pixel atm_idx [n_pix], T_pix [n_pix],
-    mat_idx/frac [n_pix, n_mix] -> L [n_pix, nx]."""
+    mat_idx/frac [n_pix, n_mix] -> L [n_pix, nx] (float64, or float32 with out_dtype=torch.float32)."""
     torch = _torch()
     dev = resolve_device(device if not (isinstance(tau, torch.Tensor) and tau.is_cuda) else tau.device)
     h = default_handle(dev)
@@ -470,9 +472,10 @@ def hsi_pixels(X, emis, tau, La, Ld, atm_idx, T_pix, mat_idx, frac, device=None)
     T_pix = to_device(T_pix, dev).reshape(n_pix)
     mat_idx = to_device(mat_idx, dev, torch.int32).reshape(n_pix, -1)
     frac = to_device(frac, dev).reshape(n_pix, mat_idx.shape[1])
-    L = torch.empty((n_pix, nx), dtype=torch.float64, device=dev)
+    f32 = out_dtype == torch.float32
+    L = torch.empty((n_pix, nx), dtype=torch.float32 if f32 else torch.float64, device=dev)
     if L.numel():
-        _lib.call("rtx_hsi_pixels", h.h, _ptr(X), nx, _ptr(emis), emis.shape[0], _ptr(tau), _ptr(La), _ptr(Ld),
-                  tau.shape[0], n_pix, _ptr(atm_idx), _ptr(T_pix), mat_idx.shape[1], _ptr(mat_idx), _ptr(frac),
-                  _ptr(L), _stream(dev))
+        _lib.call("rtx_hsi_pixels_f32" if f32 else "rtx_hsi_pixels", h.h, _ptr(X), nx, _ptr(emis), emis.shape[0], _ptr(tau),
+                  _ptr(La), _ptr(Ld), tau.shape[0], n_pix, _ptr(atm_idx), _ptr(T_pix), mat_idx.shape[1], _ptr(mat_idx),
+                  _ptr(frac), _ptr(L), _stream(dev))
     return L

@@ -427,10 +427,18 @@ def BT2L(X_in, T_in, wavelength=False, bad_value=np.nan, spectral_dim=0):
 def compute_LWIR_apparent_radiance(X, emis, Ts, tau, La, Ld, dT=None, return_Ls=False):
     """L = tau*(emis*B(T) + (1-emis)*Ld) + La for every (emissivity, atmosphere[, dT]) combination:
     radiative_transfer.py:1017-1069.  Shapes: X (nX,), emis (nX,nE), Ts (nA,), tau/La/Ld (nX,nA), dT (nT,) ->
-    L (nX,nE,nA) or (nX,nE,nA,nT)."""
+    L (nX,nE,nA) or (nX,nE,nA,nT).  When every array argument is float32 -- the reference's production script casts
+    them so (Compute_LWIR_Apparent_Radiance.py:9-25) and numpy then returns float32 -- the result is float32 too:
+    evaluated in FP64 from the float32 values and rounded once, i.e. within float32 rounding of the reference."""
     torch = engine._torch()
     as_tensor = any(isinstance(a, torch.Tensor) for a in (emis, tau, La, Ld))
-    out = engine.apparent_radiance(X, emis, Ts, tau, La, Ld, dT=dT, return_Ls=return_Ls)
+    arrs = [a for a in (X, emis, Ts, tau, La, Ld, dT) if a is not None]
+
+    def is_f32(a):
+        return (a.dtype == torch.float32) if isinstance(a, torch.Tensor) else (getattr(a, "dtype", None) == np.float32)
+    f32 = all(is_f32(a) for a in arrs)
+    out = engine.apparent_radiance(X, emis, Ts, tau, La, Ld, dT=dT, return_Ls=return_Ls,
+                                   out_dtype=torch.float32 if f32 else None)
     if as_tensor:
         return out
     if return_Ls:

@@ -413,7 +413,7 @@ def test_reduce_resolution_golden(mods):
 
 
 def test_ils_many_spectra(mods):
-    """The coalesced many-spectra ILS kernel (ns >= 16), both line shapes, ragged ns, against the oracle."""
+    """The coalesced many-spectra ILS kernels (ns >= 16), both line shapes, ragged ns, against the oracle."""
     rt, ilsg, port = mods["rt"], mods["ilsg"], mods["port"]
     rng = np.random.default_rng(8)
     X = np.linspace(700.0, 1400.0, 3501)
@@ -423,6 +423,33 @@ def test_ils_many_spectra(mods):
         assert_parity(t, port.ils_mako_triangle(X, Y)[1], RTOL, FLOOR, "tri ns=%d" % ns)
         Xg, g = ilsg.ILS_MAKO(X, Y)
         assert_parity(g, port.ils_mako_gauss(X, Y)[1], RTOL, FLOOR, "gauss ns=%d" % ns)
+
+
+def test_ils_grouped_walks(mods):
+    """Enough spectra for the grouped walks: TMA-staged groups of 8 adjacent bands with 2 (0x400) or 1 (0x800) spectra per
+    lane (default for even ns), groups of 16 (0x1000), the grouped walk without staging (0x200, also the fallback for odd ns) and the
+    band-per-CTA walk (0x100)
+    agree with each other to rounding and with the oracle; ragged last spectra block; a Gaussian band whose centre lies
+    outside the axis (empty 9.5-sigma support) falls back to the whole axis like the reference's sum."""
+    torch, engine, rt, port = mods["torch"], mods["engine"], mods["rt"], mods["port"]
+    rng = np.random.default_rng(18)
+    X = np.linspace(700.0, 1400.0, 2801)
+    tri = rt._mako_bands(X, None, 1.0, 0.0, 1.0)
+    gau = rt._mako_bands_gauss()
+    for ns in (2600, 1301):                                  # even -> TMA staging; odd -> plain grouped walk
+        Y = rng.uniform(0, 10, (X.size, ns))
+        Yd = torch.from_numpy(Y).cuda()
+        for mode, bands in ((0, tri), (1, gau)):
+            outs = {v: engine.ils_apply(mode | v, X, Yd, bands[1], bands[2]).cpu().numpy() for v in (0, 0x400, 0x800, 0x1400, 0x200, 0x100)}
+            for v in (0x400, 0x800, 0x1400, 0x200, 0x100):
+                ok = np.isfinite(outs[0x100])
+                assert np.array_equal(np.isfinite(outs[v]), ok)
+                assert np.max(np.abs(outs[v][ok] - outs[0][ok]) / np.abs(outs[0][ok])) < 1e-13, (ns, mode, hex(v))
+        cols = [0, 31, 32, ns - 1]
+        assert_parity(engine.ils_apply(0, X, Yd, tri[1], tri[2]).cpu().numpy()[:, cols],
+                      port.ils_mako_triangle(X, Y[:, cols])[1], RTOL, FLOOR, "grouped tri ns=%d" % ns)
+        assert_parity(engine.ils_apply(1, X, Yd, gau[1], gau[2]).cpu().numpy()[:, cols],
+                      port.ils_mako_gauss(X, Y[:, cols])[1], RTOL, FLOOR, "grouped gauss ns=%d" % ns)
 
 
 def test_sdvoigt_lut_and_afit_xs(mods, tmp_path):
@@ -454,19 +481,43 @@ def test_sdvoigt_lut_and_afit_xs(mods, tmp_path):
 
 
 def test_hsi_pixels(mods):
-    engine, port, syn = mods["engine"], mods["port"], mods["syn"]
+    """Per-pixel mixed-material radiance (LWIR_HSI_Generator.py:148-166): 128-band MAKO axis and a 300-point axis
+    (more bands than threads), pixel counts that do not fill the last group, three-material mixes, and the float32
+    cube (config 4's FP32 variant: same arithmetic, rounded at the store)."""
+    torch, engine, port, syn = mods["torch"], mods["engine"], mods["port"], mods["syn"]
     rng = np.random.default_rng(7)
-    X = port.mako_axis(np.array([700.0, 1400.0]))
-    nE, nA, nP = 9, 4, 1000
-    emis = syn.synthetic_emissivities(3, nE, X).T.copy()
-    tau = rng.uniform(0.2, 1, (nA, X.size)); La = rng.uniform(0, 300, (nA, X.size)); Ld = rng.uniform(0, 600, (nA, X.size))
-    atm = rng.integers(0, nA, nP); Tp = rng.uniform(270, 320, nP)
-    mat = rng.integers(0, nE, (nP, 2)); fr = rng.uniform(0, 1, (nP, 2)); fr /= fr.sum(1)[:, None]
-    L = engine.hsi_pixels(X, emis, tau, La, Ld, atm, Tp, mat, fr).cpu().numpy()
-    em = np.array([np.dot(fr[i], emis[mat[i]]) for i in range(nP)])       # LWIR_HSI_Generator.py:159
-    B = port.planckian(X, Tp).T
-    ref = tau[atm] * (em * B + (1 - em) * Ld[atm]) + La[atm]
-    assert_parity(L, ref, RTOL, FLOOR, "hsi pixels")
+    for X, nP, nM in ((port.mako_axis(np.array([700.0, 1400.0])), 1000, 2), (np.linspace(750.0, 1300.0, 300), 77, 3),
+                      (np.linspace(750.0, 1300.0, 5), 4097, 1), (np.linspace(750.0, 1300.0, 40), 130, 5)):
+        nE, nA = 9, 4
+        emis = syn.synthetic_emissivities(3, nE, X).T.copy()
+        tau = rng.uniform(0.2, 1, (nA, X.size)); La = rng.uniform(0, 300, (nA, X.size)); Ld = rng.uniform(0, 600, (nA, X.size))
+        atm = rng.integers(0, nA, nP); Tp = rng.uniform(270, 320, nP)
+        mat = rng.integers(0, nE, (nP, nM)); fr = rng.uniform(0, 1, (nP, nM)); fr /= fr.sum(1)[:, None]
+        L = engine.hsi_pixels(X, emis, tau, La, Ld, atm, Tp, mat, fr).cpu().numpy()
+        em = np.array([np.dot(fr[i], emis[mat[i]]) for i in range(nP)])       # LWIR_HSI_Generator.py:159
+        B = port.planckian(X, Tp).T
+        ref = tau[atm] * (em * B + (1 - em) * Ld[atm]) + La[atm]
+        assert_parity(L, ref, RTOL, FLOOR, "hsi pixels nx=%d" % X.size)
+        L32 = engine.hsi_pixels(X, emis, tau, La, Ld, atm, Tp, mat, fr, out_dtype=torch.float32)
+        assert L32.dtype == torch.float32
+        assert np.array_equal(L32.cpu().numpy(), L.astype(np.float32))        # rounded once at the store
+
+
+def test_apparent_radiance_float32(mods):
+    """compute_LWIR_apparent_radiance called the way the production script calls it (every input float32, dT =
+    arange(-10, 10.5, 0.5); Compute_LWIR_Apparent_Radiance.py:9-25) returns float32 like numpy does, within float32
+    rounding of the reference's own float32 result (tests/golden/sensor_f32.npz, minted from the reference)."""
+    rt, port = mods["rt"], mods["port"]
+    g = golden("sensor_f32.npz")
+    args = [g[k] for k in ("X", "emis", "Ts", "tau", "La", "Ld")]
+    L = rt.compute_LWIR_apparent_radiance(*args, g["dT"])
+    assert L.dtype == np.float32 and L.shape == g["L"].shape
+    assert_parity(L.astype(float), g["L"].astype(float), 1e-5, 1e-8, "float32 apparent radiance vs reference")
+    L0 = rt.compute_LWIR_apparent_radiance(*args)
+    assert L0.dtype == np.float32
+    assert_parity(L0.astype(float), g["L0"].astype(float), 1e-5, 1e-8, "float32 apparent radiance (no dT)")
+    ref64 = port.apparent_radiance(*[a.astype(float) for a in args], dT=g["dT"].astype(float))
+    assert np.array_equal(L, ref64.astype(np.float32)) or np.max(np.abs(L - ref64) / np.abs(ref64)) < 1.2e-7
 
 
 def test_full_size_properties(mods):

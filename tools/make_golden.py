@@ -144,6 +144,20 @@ def g_sensor():
          planck_kat=r.planckian(500., 296.), planck_grid=Pl, planck_um=Pw)
 
 
+def g_sensor_f32():
+    """The float32 call of the production script (Compute_LWIR_Apparent_Radiance.py:9-25): every input cast to float32,
+    dT = arange(-10, 10.5, 0.5); numpy then evaluates the whole expression in float32."""
+    r = R.rt()
+    g = np.load(os.path.join(OUT, "sensor.npz"))
+    X, emis, Ts, tau, La, Ld = (g[k].astype(np.float32) for k in ("Xo", "emis", "Ts", "tau", "La", "Ld"))
+    dT = np.arange(-10, 10.5, 0.5).astype(np.float32)
+    L = r.compute_LWIR_apparent_radiance(X, emis, Ts, tau, La, Ld, dT)
+    L0 = r.compute_LWIR_apparent_radiance(X, emis, Ts, tau, La, Ld)
+    assert L.dtype == np.float32 and L0.dtype == np.float32
+    save("sensor_f32.npz", source="radiative_transfer.py:1017-1069 called as Compute_LWIR_Apparent_Radiance.py:9-25 does (float32)",
+         X=X, emis=emis, Ts=Ts, tau=tau, La=La, Ld=Ld, dT=dT, L=L, L0=L0)
+
+
 def g_bt():
     r = R.rt()
     rng = np.random.default_rng(60)
@@ -319,6 +333,6 @@ def g_mbi():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi", "lorentz", "doppler", "spectra"]
+    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi", "lorentz", "doppler", "spectra", "sensor_f32"]
     for w in which:
         globals()["g_" + w]()
