@@ -220,9 +220,9 @@ int rtx_ils_apply(rtx_handle* h, int mode, const double* X_dev, int64_t nx, cons
  * rtx_smooth_sym: column-wise for Y_dev[n][m]: symmetric=0 gives smooth(y) (the reference's reflect-pad / convolve
  * with the NORMALISED window window_dev[window_len] / trim, :1266-1323), symmetric=1 gives
  * 0.5*(smooth(y) + smooth(y[::-1])[::-1]) as reduceResolution uses it (:1330).
- * rtx_spline_eval: C2 cubic-spline interpolation of the columns of Y_dev[n][m] on the knots X_dev[n] (ascending) at
- * Xo_dev[n_out] -> out_dev[n_out][m]; equals scipy interp1d(kind="cubic") to rounding for points at least 40 knots
- * away from the ends of the data (reduceResolution's own output axis always is). */
+ * rtx_spline_eval: C2 cubic-spline interpolation of the columns of Y_dev[n][m] on the knots X_dev[n] (ascending, n >= 4)
+ * at Xo_dev[n_out] -> out_dev[n_out][m]; not-a-knot end conditions and end-polynomial extrapolation, i.e. scipy
+ * interp1d(kind="cubic", fill_value="extrapolate") as reduceResolution calls it (:1331-1333), to rounding. */
 int rtx_smooth_sym(rtx_handle* h, const double* Y_dev, int64_t n, int64_t m, const double* window_dev, int window_len,
                    int symmetric, double* out_dev, void* stream);
 int rtx_spline_eval(rtx_handle* h, const double* X_dev, const double* Y_dev, int64_t n, int64_t m,

@@ -582,11 +582,13 @@ __global__ void smooth_sym_kernel(const double* __restrict__ Y, int64_t n, int64
   out[idx] = symmetric ? 0.5 * acc : acc;
 }
 
-// Cubic-spline interpolation (scipy interp1d(kind="cubic"): C2 cubic spline through all knots).  The spline's
-// second derivatives decay like (2-sqrt(3))^k away from a knot, so each output point solves the tridiagonal system
-// only on a window of HW knots either side of its interval (truncation < 1e-20 for HW = 40); the window ends use the
-// natural condition, which is exact to rounding whenever the point is >= HW knots from the ends of the data -- always
-// the case for reduceResolution's own output axis, which starts smFactor knots inside.
+// Cubic-spline interpolation (scipy interp1d(kind="cubic"): the C2 cubic spline through all knots with NOT-A-KNOT end
+// conditions).  The spline's second derivatives decay like (2-sqrt(3))^k away from a knot, so each output point solves
+// the tridiagonal system only on a window of HW knots either side of its interval (truncation < 1e-20 for HW = 40).
+// A window end that lies inside the data uses the natural condition (M = 0 there, exact to rounding); a window end
+// that IS an end of the data uses the reference's not-a-knot condition (third derivative continuous across the second
+// knot: M_0 = M_1 (1 + h0/h1) - M_2 h0/h1, eliminated into the first row), so points near the ends of the data -- and
+// beyond them (fill_value="extrapolate" continues the end polynomial) -- agree with scipy as well.
 constexpr int SPL_HW = 40;
 __global__ void spline_eval_kernel(const double* __restrict__ X, const double* __restrict__ Y, int64_t n, int64_t m,
                                    const double* __restrict__ Xo, int64_t no, double* __restrict__ out) {
@@ -597,28 +599,34 @@ __global__ void spline_eval_kernel(const double* __restrict__ X, const double* _
   int64_t i = bisect_right_dev64(X, n, xo) - 1;          // X[i] <= xo < X[i+1]
   i = max((int64_t)0, min(n - 2, i));                    // ends: extrapolate with the end polynomial
   const int64_t k0 = max((int64_t)0, i - SPL_HW), k1 = min(n - 1, i + 1 + SPL_HW);
-  const int nk = (int)(k1 - k0 + 1);                     // knots in the window, <= 2*HW+2
-  double cp[2 * SPL_HW + 2], dp[2 * SPL_HW + 2];         // Thomas algorithm workspace (second derivatives)
-  cp[0] = 0.0; dp[0] = 0.0;                              // natural: M_0 = 0
+  const int nk = (int)(k1 - k0 + 1);                     // knots in the window, 4 <= nk <= 2*HW+2
+  const bool left_end = (k0 == 0), right_end = (k1 == n - 1);
+  double cp[2 * SPL_HW + 2], dp[2 * SPL_HW + 2];         // Thomas algorithm workspace; dp ends up holding M_k
+  cp[0] = 0.0; dp[0] = 0.0;
   for (int k = 1; k < nk - 1; ++k) {
     const int64_t g = k0 + k;
     const double h0 = X[g] - X[g - 1], h1 = X[g + 1] - X[g];
     const double rhs = 6.0 * ((Y[(g + 1) * m + c] - Y[g * m + c]) / h1 - (Y[g * m + c] - Y[(g - 1) * m + c]) / h0);
-    const double den = 2.0 * (h0 + h1) - h0 * cp[k - 1];
-    cp[k] = h1 / den;
-    dp[k] = (rhs - h0 * dp[k - 1]) / den;
+    double a = h0, b = 2.0 * (h0 + h1), cc = h1;
+    if (k == 1 && left_end) { a = 0.0; b = 3.0 * h0 + 2.0 * h1 + h0 * h0 / h1; cc = h1 - h0 * h0 / h1; }
+    if (k == nk - 2 && right_end) { a = h0 - h1 * h1 / h0; b = 2.0 * h0 + 3.0 * h1 + h1 * h1 / h0; cc = 0.0; }   // nk >= 4: never row 1
+    const double den = b - a * cp[k - 1];
+    cp[k] = cc / den;
+    dp[k] = (rhs - a * dp[k - 1]) / den;
   }
-  // back substitution down to the interval's two knots
-  double Mn = 0.0;                                        // M_{nk-1} = 0
+  // back substitution: dp[k] <- M_k  (M at a natural window end is 0)
+  dp[nk - 1] = 0.0;
+  for (int k = nk - 2; k >= 1; --k) dp[k] = dp[k] - cp[k] * dp[k + 1];
+  if (right_end) {
+    const double r = (X[k1] - X[k1 - 1]) / (X[k1 - 1] - X[k1 - 2]);
+    dp[nk - 1] = dp[nk - 2] * (1.0 + r) - dp[nk - 3] * r;
+  }
+  if (left_end) {
+    const double r = (X[1] - X[0]) / (X[2] - X[1]);
+    dp[0] = dp[1] * (1.0 + r) - dp[2] * r;
+  }
   const int ki = (int)(i - k0);
-  double Mi1 = 0.0, Mi = 0.0;
-  for (int k = nk - 2; k >= ki; --k) {
-    const double Mk = (k >= 1) ? dp[k] - cp[k] * Mn : 0.0;
-    if (k == ki + 1) Mi1 = Mk;
-    if (k == ki) Mi = Mk;
-    Mn = Mk;
-  }
-  if (ki + 1 == nk - 1) Mi1 = 0.0;
+  const double Mi = dp[ki], Mi1 = dp[ki + 1];
   const double h = X[i + 1] - X[i];
   const double A = (X[i + 1] - xo) / h, B = (xo - X[i]) / h;
   out[idx] = A * Y[i * m + c] + B * Y[(i + 1) * m + c] +

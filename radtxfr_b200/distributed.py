@@ -112,23 +112,28 @@ def estimate_tile_costs(db, T, p_atm, X, tile=TILE, wing_hw=50.0, wing_abs=0.0):
     from the sorted line centres and the column extrema the LineDB keeps -- an estimate for balancing bands
     ("balance bands by estimated evals, not by width"), not a count."""
     X = np.asarray(X, dtype=float)
-    T = np.asarray(T, dtype=float).ravel()
-    p_atm = np.asarray(p_atm, dtype=float).ravel()
     ntiles = (X.size + tile - 1) // tile
     lo = X[np.arange(ntiles) * tile]
     hi = X[np.minimum((np.arange(ntiles) + 1) * tile, X.size) - 1]
+    return _tile_costs_from_edges(db, T, p_atm, lo, hi, wing_hw, wing_abs)
+
+
+def _tile_costs_from_edges(db, T, p_atm, lo, hi, wing_hw, wing_abs):
+    """estimate_tile_costs from the first (lo) and last (hi) wavenumber of every tile."""
+    T = np.asarray(T, dtype=float).ravel()
+    p_atm = np.asarray(p_atm, dtype=float).ravel()
     nu = db.nu_sorted
-    cost = np.zeros(ntiles)
+    cost = np.zeros(lo.size)
     if nu.size == 0:
         return cost + 1.0
     # wing bound per state, as the kernel's state_prep does it: max(OmegaWing, HW*Gamma0_max, HW*GammaD_max)
     r = 296.0 / T
     g0 = np.abs(p_atm) * db.gamma_air_max * np.maximum(r ** db.n_air_range[0], r ** db.n_air_range[1])
     gd = db.nu_max * np.sqrt(2.0 * 1.380648813e-16 * T * np.log(2.0) / (db.mass_min * 1.66053873e-24)) / 2.99792458e10
-    wb = np.maximum(np.maximum(wing_abs, wing_hw * g0), wing_hw * gd)
+    wb = np.round(np.maximum(np.maximum(wing_abs, wing_hw * g0), wing_hw * gd), 6)
     inside = (np.searchsorted(nu, hi, side="right") - np.searchsorted(nu, lo, side="left")).astype(float)
-    for w in np.unique(np.round(wb, 6)):
-        n = float(np.sum(np.round(wb, 6) == w))
+    for w in np.unique(wb):
+        n = float(np.sum(wb == w))
         reach = np.searchsorted(nu, hi + w, side="right") - np.searchsorted(nu, lo - w, side="left")
         cost += n * (reach + 2.0 * inside)
     return cost + 1.0
@@ -152,13 +157,20 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
     Z = np.asarray(opts["Zs"], dtype=float); T = np.asarray(opts["Ts"], dtype=float)
     Z_s = np.array([opts["Altitudes"]]).ravel()
     mu_s = np.array([1.0 / np.cos(opts["theta_r"])]).ravel()
-    X_ = rt.make_spectral_axis(Xmin, Xmax, opts["DVOUT"])
-    nX = X_.size
+    # the full axis lives on the device across calls (radiative_transfer._device_axis, LRU); on a cache hit the host
+    # copy is rebuilt only after the kernels are in flight
+    X_, grid_full = rt._device_axis(Xmin, Xmax, opts["DVOUT"], db.device)
+    nX = grid_full.numel()
     db.check_temperatures(T)
     p, w = rt.layer_weights(db, T, opts["Ps"], opts["PLs"], opts["MFs_VAL"], opts["MFs_ID"])
     vs = rt._voigt_settings(opts)
     vs["flags"] = (vs["flags"] & ~(0xF << 8)) | FORCE_K8
-    costs = estimate_tile_costs(db, T, p, X_, TILE, vs["wing_hw"], vs["wing_abs"]) if balance else None
+    costs = None
+    if balance:
+        ntiles = (nX + TILE - 1) // TILE
+        edges = torch.cat([grid_full[::TILE], grid_full[-1:]]).cpu().numpy()       # first point of every tile + the last point
+        costs = _tile_costs_from_edges(db, T, p, edges[:-1], np.append(edges[1:-1], edges[-1]), vs["wing_hw"], vs["wing_abs"])
+        assert costs.size == ntiles
     bands = plan_bands(nX, world, weights=costs)
     i0, i1 = bands[rank]
     k = Z_s.size * mu_s.size
@@ -167,7 +179,7 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
     shard = torch.zeros((nf, width), dtype=torch.float64, device=db.device)       # equal-size shard, padded
     if i1 > i0:
         n = i1 - i0
-        grid = engine.to_device(X_[i0:i1], db.device)
+        grid = grid_full[i0:i1]
         od = db.voigt_sum(T, p, w, grid, out=rt._od_workspace(db.device, T.size, n), **vs)
         tau, lu, ld = engine.tud(od, T[None, :], grid, Z, Z_s, mu_s, opts["N_angle"], opts["returnOD"])
         if k == 1:
@@ -178,6 +190,8 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
     flat = torch.empty((world, nf, width), dtype=torch.float64, device=db.device)
     _all_gather_flat(flat.view(-1), shard.view(-1), group)                      # the path's single collective
     full = torch.cat([flat[r, :, : b - a] for r, (a, b) in enumerate(bands) if b > a], dim=1)     # [nf, nX]
+    if X_ is None:
+        X_ = rt.make_spectral_axis(Xmin, Xmax, opts["DVOUT"])                    # while the GPU works
     if k == 1:
         tau_d, lu_d = full[0].reshape(nX, 1, 1), full[1].reshape(nX, 1, 1)
     else:

@@ -412,6 +412,26 @@ def test_reduce_resolution_golden(mods):
     assert rt.smooth(Y[:, 0], 2) is Y[:, 0] or np.array_equal(rt.smooth(Y[:, 0], 2), Y[:, 0])
 
 
+def test_reduce_resolution_ends_golden(mods):
+    """reduceResolution where the spline's end conditions matter (scipy interp1d(kind='cubic') is a not-a-knot spline
+    and extrapolates with the end polynomial): smFactor = 3 (X_out starts three knots inside the data), a caller-supplied
+    X_out from outside the data range to outside it, and a 12-knot axis (both ends inside every window); against the
+    reference's outputs (tests/golden/reduce2.npz)."""
+    rt = mods["rt"]
+    g = golden("reduce2.npz")
+    rng = np.random.default_rng(71)
+    X = np.linspace(700.0, 760.0, 2401)
+    Y = np.cumsum(rng.normal(0, 1, (X.size, 2)), axis=0) * 0.02 + np.cos(X / 3.0)[:, None]
+    Xo3, Yo3 = rt.reduceResolution(X, Y, 0.075)
+    assert_parity(Xo3, g["Xo3"], 1e-12, 0.0, "smFactor 3 X_out")
+    assert_parity(Yo3, g["Yo3"], RTOL, FLOOR, "smFactor 3 Y_out")
+    Yfull = rt.reduceResolution(X, Y, 0.25, X_out=g["Xfull"])
+    assert_parity(Yfull, g["Yfull"], RTOL, FLOOR, "X_out across and beyond the data")
+    Xs = np.linspace(700.0, 701.0, 12)
+    Yshort = rt.reduceResolution(Xs, np.sin(Xs * 9.0) + Xs, 0.3, X_out=np.linspace(699.9, 701.1, 41))
+    assert_parity(Yshort, g["Yshort"], RTOL, FLOOR, "12-knot axis")
+
+
 def test_ils_many_spectra(mods):
     """The coalesced many-spectra ILS kernels (ns >= 16), both line shapes, ragged ns, against the oracle."""
     rt, ilsg, port = mods["rt"], mods["ilsg"], mods["port"]

@@ -194,6 +194,26 @@ def g_reduce():
          Xo=Xo, Yo=Yo, Xo5=Xo5, Yo5=Yo5, s11=s11, s10f=s10f)
 
 
+def g_reduce2():
+    """reduceResolution near and beyond the ends of the data, where the spline's not-a-knot end conditions matter:
+    the smallest smoothing factor the reference smooths with (3), and a caller-supplied X_out that spans the whole
+    input range and extrapolates beyond it."""
+    np.int = int
+    r = R.rt()
+    rng = np.random.default_rng(71)
+    X = np.linspace(700.0, 760.0, 2401)                       # dX_in = 0.025
+    Y = np.cumsum(rng.normal(0, 1, (X.size, 2)), axis=0) * 0.02 + np.cos(X / 3.0)[:, None]
+    Xo3, Yo3 = r.reduceResolution(X, Y, 0.075)                # smFactor = 3
+    Xfull = np.concatenate([[699.2, 699.9, 700.0, 700.01, 700.03, 700.05, 700.3], np.linspace(701.0, 759.0, 117),
+                            [759.7, 759.95, 759.99, 760.0, 760.4]])
+    Yfull = r.reduceResolution(X, Y, 0.25, X_out=Xfull)       # smFactor = 10, X_out from outside to outside
+    Xs = np.linspace(700.0, 701.0, 12)                        # fewer knots than one window: both ends not-a-knot
+    Ys = np.sin(Xs * 9.0) + Xs
+    Yshort = r.reduceResolution(Xs, Ys, 0.3, X_out=np.linspace(699.9, 701.1, 41))
+    save("reduce2.npz", source="radiative_transfer.py:1326-1350 reduceResolution (with np.int = int)", seed=71,
+         Xo3=Xo3, Yo3=Yo3, Xfull=Xfull, Yfull=Yfull, Yshort=Yshort)
+
+
 def optcols_table():
     rng = np.random.default_rng(9)
     cols = syn.synthetic_lines(56, 300, 1180.0, 1320.0, 1)
@@ -333,6 +353,6 @@ def g_mbi():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi", "lorentz", "doppler", "spectra", "sensor_f32"]
+    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi", "lorentz", "doppler", "spectra", "sensor_f32", "reduce2"]
     for w in which:
         globals()["g_" + w]()
