@@ -36,6 +36,7 @@ extern "C" {
 #define RTX_MAX_LAYERS 256 /* layers per atmosphere (reference table: 66) */
 #define RTX_MAX_ALT 32     /* sensor altitudes per call */
 #define RTX_MAX_MU 8       /* view angles per call */
+#define RTX_MAX_EXTRA_DILUENTS 4 /* broadening species besides air and self per line table */
 
 typedef struct rtx_handle rtx_handle;
 
@@ -72,6 +73,19 @@ int rtx_lines_upload(rtx_handle* h, int64_t n, const double* nu, const double* s
                      const double* n_self, const double* delta_air, const double* deltap_air,
                      const double* delta_self, const double* deltap_self, const int32_t* iso_idx);
 int rtx_lines_count(rtx_handle* h, int64_t* n);
+
+/* Optional columns of the table uploaded last, host pointers in that table's ORIGINAL row order, copied; NULL = absent.
+ * rtx_lines_set_sd: the speed-dependence columns SD_air / SD_self read by absorptionCoefficient_SDVoigt
+ * (misc/hapi.py:10883-10890).
+ * rtx_lines_set_diluent: one more broadening species in slot 0..RTX_MAX_EXTRA_DILUENTS-1 -- the columns gamma_<sp>,
+ * n_<sp> (NULL -> n_air, misc/hapi.py:11101-11109), delta_<sp>, deltap_<sp>, SD_<sp> that hapi's Diluent={'<sp>': x}
+ * loop reads (misc/hapi.py:11090-11128).
+ * rtx_voigt_set_mix: the fractions x of the extra species for the following rtx_voigt_sum / rtx_voigt_count calls on
+ * this handle (default: all zero). */
+int rtx_lines_set_sd(rtx_handle* h, const double* sd_air, const double* sd_self);
+int rtx_lines_set_diluent(rtx_handle* h, int slot, const double* gamma, const double* n, const double* delta,
+                          const double* deltap, const double* sd);
+int rtx_voigt_set_mix(rtx_handle* h, int n_extra, const double* x_extra);
 
 /* Line-file readers (host only, no handle, no GPU needed).  Call with capacity 0 and NULL columns to count rows,
  * then again with arrays of that size; any column pointer may be NULL.
@@ -119,6 +133,9 @@ int rtx_tape3_read(const char* path, double vmin, double vmax, int64_t capacity,
 #define RTX_VOIGT_NOFAR 4096    /* disable the far-field blocks: evaluate every (line, grid point) pair at the grid point
                                  * itself (default: slices a window covers from >= 0.375 slice widths away are summed
                                  * at 32 Chebyshev nodes and interpolated, relative error < 1e-13) */
+#define RTX_VOIGT_SDVOIGT 8192  /* absorptionCoefficient_SDVoigt (misc/hapi.py:10657-10905): lines whose Gamma2 = sum_d x_d
+                                 * SD_d p gamma_d is non-zero take the quadratic speed-dependent profile (pcqsdhc PART2-4,
+                                 * misc/hapi.py:9923-10020); the rest is the Voigt driver */
 #define RTX_VOIGT_TILE_SHIFT 8 /* bits 8..11: force 256*K grid points per CTA, K in {1,2,4,8} (0 = automatic).
                                 * The automatic choice between K = 8 and K = 4 reads 8 bytes back from the device
                                 * (one stream synchronisation after a tiny kernel); force K to keep the call fully

@@ -147,6 +147,116 @@ def profile_voigt(sg0, GamD, Gam0, sg):
     return (1.0 / np.pi) * ((rpi * cte) * wr)
 
 
+def cpf3(X, Y):
+    """misc/hapi.py:9645-9670: asymptotic series of w(z) for "region 3" of pcqsdhc (15 terms)."""
+    X = np.atleast_1d(np.asarray(X, dtype=float))
+    Y = np.atleast_1d(np.asarray(Y, dtype=float))
+    zone, zi = 1.0 + 0.0j, 0.0 + 1.0j
+    tt = np.array([0.5, 1.5, 2.5, 3.5, 4.5, 5.5, 6.5, 7.5, 8.5, 9.5, 10.5, 11.5, 12.5, 13.5, 14.5])
+    zm1 = zone / (X + zi * Y).astype(complex)
+    zm2 = zm1 ** 2
+    zsum = zone
+    zterm = zone
+    for tt_i in tt:
+        zterm = zterm * (zm2 * tt_i)
+        zsum = zsum + zterm
+    zsum = zsum * (zi * zm1 * 0.564189583547756)
+    return zsum.real, zsum.imag
+
+
+def pcqsdhc(sg0, GamD, Gam0, Gam2, Shift0, Shift2, anuVC, eta, sg):
+    """pCqSDHC (Hartmann-Tran) profile, misc/hapi.py:9846-10023, all four parts.  Returns (real, imag) of the
+    normalised line shape.  PART3 of the reference indexes `sqrt(X)` with the whole X instead of the PART3 subset
+    (:9994-9996, usable only when every point is in PART3); the evident intent (the subset) is restated here."""
+    sg = np.atleast_1d(np.asarray(sg, dtype=float))
+    npts = sg.size
+    A = np.zeros(npts, dtype=complex)
+    B = np.zeros(npts, dtype=complex)
+    cte = np.sqrt(np.log(2.0)) / GamD
+    rpi = np.sqrt(np.pi)
+    iz = 0.0 + 1.0j
+    c0 = complex(Gam0 + 1.0j * Shift0)
+    c2 = complex(Gam2 + 1.0j * Shift2)
+    c0t = complex((1.0 - eta) * (c0 - 1.5 * c2) + anuVC)
+    c2t = complex((1.0 - eta) * c2)
+
+    def W(x, y):
+        wr, wi = hum1_wei(x, y)
+        return wr + 1.0j * wi
+
+    if abs(c2t) == 0.0:                                            # PART1
+        Z1 = (iz * (sg0 - sg) + c0t) * cte
+        w1 = W(-Z1.imag, Z1.real)
+        A = rpi * cte * w1
+        i1 = np.abs(Z1) <= 4.0e3
+        if np.any(i1):
+            B = rpi * cte * ((1.0 - Z1 ** 2) * w1 + Z1 / rpi)
+        if np.any(~i1):
+            B = cte * (rpi * w1 + 0.5 / Z1 - 0.75 / (Z1 ** 3))
+    else:
+        X = (iz * (sg0 - sg) + c0t) / c2t
+        Y = complex(1.0 / ((2.0 * cte * c2t)) ** 2)
+        csqrtY = (Gam2 - iz * Shift2) / (2.0 * cte * (1.0 - eta) * (Gam2 ** 2 + Shift2 ** 2))
+        i2 = np.abs(X) <= 3.0e-8 * abs(Y)
+        i3 = (abs(Y) <= 1.0e-15 * np.abs(X)) & ~i2
+        i4 = ~(i2 | i3)
+        if np.any(i4):                                             # PART4 (the main part)
+            Xt = X[i4]
+            Z1 = np.sqrt(Xt + Y) - csqrtY
+            Z2 = Z1 + 2.0 * csqrtY
+            x1, y1, x2, y2 = -Z1.imag, Z1.real, -Z2.imag, Z2.real
+            S1 = np.sqrt(x1 ** 2 + y1 ** 2)
+            S2 = np.sqrt(x2 ** 2 + y2 ** 2)
+            D = np.abs(S1 - S2)
+            mx, mn = np.maximum(S1, S2), np.minimum(S1, S2)
+            w1 = np.zeros(Xt.size, dtype=complex)
+            w2 = np.zeros(Xt.size, dtype=complex)
+            i_c3 = (D <= 1.0) & (mx > 8.0) & (mn <= 8.0)
+            if np.any(i_c3):
+                a, b = cpf3(x1[i_c3], y1[i_c3]); w1[i_c3] = a + 1.0j * b
+                a, b = cpf3(x2[i_c3], y2[i_c3]); w2[i_c3] = a + 1.0j * b
+            if np.any(~i_c3):
+                w1[~i_c3] = W(x1[~i_c3], y1[~i_c3])
+                w2[~i_c3] = W(x2[~i_c3], y2[~i_c3])
+            A[i4] = rpi * cte * (w1 - w2)
+            B[i4] = (-1.0 + rpi / (2.0 * csqrtY) * (1.0 - Z1 ** 2) * w1 - rpi / (2.0 * csqrtY) * (1.0 - Z2 ** 2) * w2) / c2t
+        if np.any(i2):                                             # PART2
+            Xt = X[i2]
+            Z1 = (iz * (sg0 - sg[i2]) + c0t) * cte
+            Z2 = np.sqrt(Xt + Y) + csqrtY
+            w1 = W(-Z1.imag, Z1.real)
+            w2 = W(-Z2.imag, Z2.real)
+            A[i2] = rpi * cte * (w1 - w2)
+            B[i2] = (-1.0 + rpi / (2.0 * csqrtY) * (1.0 - Z1 ** 2) * w1 - rpi / (2.0 * csqrtY) * (1.0 - Z2 ** 2) * w2) / c2t
+        if np.any(i3):                                             # PART3
+            Xt = X[i3]
+            sq = np.sqrt(Xt + Y)
+            w1 = W(-sq.imag, sq.real)
+            ia = np.abs(np.sqrt(Xt)) <= 4.0e3
+            At = np.zeros(Xt.size, dtype=complex)
+            Bt = np.zeros(Xt.size, dtype=complex)
+            if np.any(ia):
+                sx = np.sqrt(Xt[ia])
+                wb = W(-sx.imag, sx.real)
+                At[ia] = (2.0 * rpi / c2t) * (1.0 / rpi - sx * wb)
+                Bt[ia] = (1.0 / c2t) * (-1.0 + 2.0 * rpi * (1.0 - Xt[ia] - 2.0 * Y) * (1.0 / rpi - sx * wb)
+                                        + 2.0 * rpi * sq[ia] * w1[ia])
+            if np.any(~ia):
+                xn = Xt[~ia]
+                At[~ia] = (1.0 / c2t) * (1.0 / xn - 1.5 / (xn ** 2))
+                Bt[~ia] = (1.0 / c2t) * (-1.0 + (1.0 - xn - 2.0 * Y) * (1.0 / xn - 1.5 / (xn ** 2))
+                                         + 2.0 * rpi * sq[~ia] * w1[~ia])
+            A[i3] = At
+            B[i3] = Bt
+    LS = (1.0 / np.pi) * (A / (1.0 - (anuVC - eta * (c0 - 1.5 * c2)) * A + eta * c2 * B))
+    return LS.real, LS.imag
+
+
+def profile_sdvoigt(sg0, GamD, Gam0, Gam2, Shift0, Shift2, sg):
+    """PROFILE_SDVOIGT, misc/hapi.py:10116-10128."""
+    return pcqsdhc(sg0, GamD, Gam0, Gam2, Shift0, Shift2, 0.0, 0.0, sg)
+
+
 # ----------------------------------------------------------------------------- line quantities
 def line_strength(sw, T, Q_T, Q_ref, elower, nu):
     """EnvironmentDependency_Intensity, misc/hapi.py:10169-10175."""
@@ -218,6 +328,7 @@ def line_state(cols, T, p, Diluent=None, GammaL="gamma_air", Components=None, In
     keep &= ~(S < IntensityThreshold)                            # misc/hapi.py:11082
     Gam0 = np.zeros(n)
     Shift0 = np.zeros(n)
+    Gam2 = np.zeros(n)
     n_air = _col(cols, "n_air", n)
     for species, abun in Diluent.items():                        # misc/hapi.py:11090-11128
         s = species.lower()
@@ -232,8 +343,9 @@ def line_state(cols, T, p, Diluent=None, GammaL="gamma_air", Components=None, In
         dlt = _col(cols, "delta_" + s, n)
         dlp = _col(cols, "deltap_" + s, n)
         Shift0 = Shift0 + abun * ((dlt + dlp * (T - T_REF)) * p / P_REF)
+        Gam2 = Gam2 + abun * (_col(cols, "SD_" + s, n) * p / P_REF) * gam      # SDVoigt driver only, misc/hapi.py:10883-10890
     wing = np.maximum(np.maximum(OmegaWing, OmegaWingHW * Gam0), OmegaWingHW * GamD)   # :11131
-    return dict(nu=nu, S=S, GamD=GamD, Gam0=Gam0, Shift0=Shift0, wing=wing, ampl=ampl, keep=keep)
+    return dict(nu=nu, S=S, GamD=GamD, Gam0=Gam0, Shift0=Shift0, Gam2=Gam2, wing=wing, ampl=ampl, keep=keep)
 
 
 def absorption_coefficient_voigt(cols, T=296.0, p=1.0, OmegaGrid=None, OmegaWing=0.0, OmegaWingHW=50.0,
@@ -264,6 +376,29 @@ def absorption_coefficient_voigt(cols, T=296.0, p=1.0, OmegaGrid=None, OmegaWing
             evals_w += int(np.count_nonzero(np.abs((sg - (nu[r] + Sh[r])) * cte) + Gam0[r] * cte < 15.0))
     if return_evals:
         return Omegas, Xsect, evals, evals_w
+    return Omegas, Xsect
+
+
+def absorption_coefficient_sdvoigt(cols, T=296.0, p=1.0, OmegaGrid=None, OmegaWing=0.0, OmegaWingHW=50.0,
+                                   IntensityThreshold=0.0, GammaL="gamma_air", HITRAN_units=True, Diluent=None,
+                                   Components=None):
+    """absorptionCoefficient_SDVoigt, misc/hapi.py:10657-10905: Gamma2 = sum_d x_d * SD_d * p/pref * gamma_d(ref)
+    (:10883-10890), Shift2 = 0, profile PROFILE_SDVOIGT(nu, GamD, Gam0, Gam2, Shift0, 0, ...) with the line shift passed
+    into the profile (:10899)."""
+    Omegas = np.sort(np.asarray(OmegaGrid, dtype=float))
+    Xsect = np.zeros(Omegas.size)
+    factor = 1.0 if HITRAN_units else volume_concentration(p, T)
+    st = line_state(cols, T, p, Diluent, GammaL, Components, IntensityThreshold, OmegaWing, OmegaWingHW)
+    nu, S, GamD, Gam0, Gam2, Sh, W, ampl, keep = (st[k] for k in ("nu", "S", "GamD", "Gam0", "Gam2", "Shift0", "wing",
+                                                                  "ampl", "keep"))
+    lo_all = np.searchsorted(Omegas, nu - W, side="right")
+    hi_all = np.searchsorted(Omegas, nu + W, side="right")
+    for r in np.nonzero(keep)[0]:
+        lo, hi = int(lo_all[r]), int(hi_all[r])
+        if hi <= lo:
+            continue
+        V = profile_sdvoigt(nu[r], GamD[r], Gam0[r], Gam2[r], Sh[r], 0.0, Omegas[lo:hi])[0]
+        Xsect[lo:hi] += factor * ampl[r] * S[r] * V
     return Omegas, Xsect
 
 

@@ -97,6 +97,16 @@ def ref_xsect(cols, T, p, grid, name="__oracle__", **kw):
     return om, xs
 
 
+def ref_xsect_sd(cols, T, p, grid, name="__oracle_sd__", **kw):
+    """sigma(omega) from the reference's absorptionCoefficient_SDVoigt (misc/hapi.py:10657)."""
+    h = hapi()
+    inject_table(name, cols)
+    with contextlib.redirect_stdout(io.StringIO()):
+        om, xs = h.absorptionCoefficient_SDVoigt(SourceTables=name, Environment={"T": float(T), "p": float(p)},
+                                                 OmegaGrid=grid, **kw)
+    return om, xs
+
+
 def ref_tud(tables_by_mol, Xmin, Xmax, **kw):
     """Run the reference's compute_TUD body unmodified (radiative_transfer.py:274-392) with
     compute_OD replaced by the hapi-based wiring of SURVEY.md App. B.1."""

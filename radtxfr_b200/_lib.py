@@ -25,6 +25,9 @@ _SIGNATURES = {
     "rtx_set_iso_table": [c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "rtx_lines_upload": [c_void_p, c_int64] + [c_void_p] * 12,
     "rtx_lines_count": [c_void_p, POINTER(c_int64)],
+    "rtx_lines_set_sd": [c_void_p, c_void_p, c_void_p],
+    "rtx_lines_set_diluent": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "rtx_voigt_set_mix": [c_void_p, c_int, c_void_p],
     "rtx_par_read": [c_char_p, c_int64] + [c_void_p] * 10 + [POINTER(c_int64)],
     "rtx_tape3_write": [c_char_p, c_int64] + [c_void_p] * 9,
     "rtx_tape3_read": [c_char_p, c_double, c_double, c_int64] + [c_void_p] * 9 + [POINTER(c_int64)],

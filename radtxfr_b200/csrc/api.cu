@@ -48,6 +48,9 @@ static void free_lines(LineTable& L) {
                      &L.deltap_air, &L.delta_self, &L.deltap_self};
   for (double** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
   if (L.iso) cudaFree(L.iso);
+  for (double* p : {L.sd_air, L.sd_self}) if (p) cudaFree(p);
+  for (int e = 0; e < RTX_MAX_EXTRA_DILUENTS; ++e)
+    for (double* p : {L.xg[e], L.xn[e], L.xd[e], L.xdp[e], L.xsd[e]}) if (p) cudaFree(p);
   L = LineTable();
 }
 
@@ -248,8 +251,61 @@ extern "C" int rtx_lines_upload(rtx_handle* h, int64_t n, const double* nu, cons
     std::vector<double> v_pa = gather(deltap_air, 0.0), v_ps = gather(deltap_self, 0.0);
     if ((rc = upload(&L.deltap_air, v_pa)) || (rc = upload(&L.deltap_self, v_ps))) { free_lines(L); return rc; }
   }
+  L.order = order;
   free_lines(h->lines);
   h->lines = L;
+  for (double& x : h->x_extra) x = 0.0;
+  return RTX_OK;
+}
+
+// gather a caller-order host column into sorted order, pad, upload (nullptr stays nullptr)
+static int upload_sorted(const LineTable& L, const double* src, double** dst, double* vmin, double* vmax) {
+  if (*dst) { cudaFree(*dst); *dst = nullptr; }
+  if (!src) return RTX_OK;
+  std::vector<double> v((size_t)L.n_pad, 0.0);
+  for (int64_t i = 0; i < L.n; ++i) {
+    v[i] = src[L.order[i]];
+    if (!std::isfinite(v[i])) { rtx_set_error("non-finite value in an optional line column"); return RTX_E_INVALID; }
+  }
+  if (vmin && vmax) {
+    *vmin = *vmax = 0.0;
+    if (L.n > 0) { auto mm = std::minmax_element(v.begin(), v.begin() + L.n); *vmin = *mm.first; *vmax = *mm.second; }
+  }
+  return upload(dst, v);
+}
+
+extern "C" int rtx_lines_set_sd(rtx_handle* h, const double* sd_air, const double* sd_self) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  if (h->lines.n_pad == 0) { rtx_set_error("rtx_lines_set_sd: upload a line table first"); return RTX_E_STATE; }
+  DeviceGuard guard(h->device);
+  int rc;
+  if ((rc = upload_sorted(h->lines, sd_air, &h->lines.sd_air, nullptr, nullptr))) return rc;
+  if (sd_self && !h->lines.gamma_self) sd_self = nullptr;      // no gamma_self column: Gamma2 gets SD*0 (misc/hapi.py:10890)
+  return upload_sorted(h->lines, sd_self, &h->lines.sd_self, nullptr, nullptr);
+}
+
+extern "C" int rtx_lines_set_diluent(rtx_handle* h, int slot, const double* gamma, const double* n, const double* delta,
+                                     const double* deltap, const double* sd) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  RTX_REQUIRE(slot >= 0 && slot < RTX_MAX_EXTRA_DILUENTS, "rtx_lines_set_diluent: slot out of range");
+  if (h->lines.n_pad == 0) { rtx_set_error("rtx_lines_set_diluent: upload a line table first"); return RTX_E_STATE; }
+  DeviceGuard guard(h->device);
+  LineTable& L = h->lines;
+  int rc;
+  double lo, hi;
+  if ((rc = upload_sorted(L, gamma, &L.xg[slot], &lo, &hi))) return rc;
+  L.xg_max[slot] = gamma ? std::max(fabs(lo), fabs(hi)) : 0.0;
+  if ((rc = upload_sorted(L, n, &L.xn[slot], &L.xn_min[slot], &L.xn_max[slot]))) return rc;
+  if (!n) { L.xn_min[slot] = L.nair_min; L.xn_max[slot] = L.nair_max; }
+  if ((rc = upload_sorted(L, delta, &L.xd[slot], nullptr, nullptr))) return rc;
+  if ((rc = upload_sorted(L, deltap, &L.xdp[slot], nullptr, nullptr))) return rc;
+  return upload_sorted(L, sd, &L.xsd[slot], nullptr, nullptr);
+}
+
+extern "C" int rtx_voigt_set_mix(rtx_handle* h, int n_extra, const double* x_extra) {
+  RTX_REQUIRE(h != nullptr, "null handle");
+  RTX_REQUIRE(n_extra >= 0 && n_extra <= RTX_MAX_EXTRA_DILUENTS && (n_extra == 0 || x_extra), "rtx_voigt_set_mix: bad arguments");
+  for (int e = 0; e < RTX_MAX_EXTRA_DILUENTS; ++e) h->x_extra[e] = e < n_extra ? x_extra[e] : 0.0;
   return RTX_OK;
 }
 

@@ -30,6 +30,13 @@ struct LineTable {
          *delta_self = nullptr, *deltap_self = nullptr;
   int32_t* iso = nullptr;
   bool has_deltap = false;
+  // speed-dependence columns SD_air / SD_self (absorptionCoefficient_SDVoigt) and extra broadening species
+  // (gamma_<sp>, n_<sp>, delta_<sp>, deltap_<sp>, SD_<sp>), all optional
+  double *sd_air = nullptr, *sd_self = nullptr;
+  double *xg[RTX_MAX_EXTRA_DILUENTS] = {}, *xn[RTX_MAX_EXTRA_DILUENTS] = {}, *xd[RTX_MAX_EXTRA_DILUENTS] = {},
+         *xdp[RTX_MAX_EXTRA_DILUENTS] = {}, *xsd[RTX_MAX_EXTRA_DILUENTS] = {};
+  double xg_max[RTX_MAX_EXTRA_DILUENTS] = {}, xn_min[RTX_MAX_EXTRA_DILUENTS] = {}, xn_max[RTX_MAX_EXTRA_DILUENTS] = {};
+  std::vector<int64_t> order;   // sorted position -> row of the caller's table (for columns uploaded later)
   // extrema used for the conservative per-state wing bound
   double nu_min = 0, nu_max = 0, gair_max = 0, gself_max = 0, nair_min = 0, nair_max = 0, nself_min = 0,
          nself_max = 0;
@@ -50,6 +57,7 @@ struct rtx_handle {
   double* d_cheb = nullptr;                            // Chebyshev tables of the Voigt far-field blocks
   uint64_t launches = 0;
   int last_K = 0;                                      // tile size of the last rtx_voigt_sum
+  double x_extra[RTX_MAX_EXTRA_DILUENTS] = {};         // fractions of the extra broadening species (rtx_voigt_set_mix)
 };
 
 void rtx_set_error(const std::string& msg);

@@ -114,6 +114,12 @@ struct VoigtParams {
   const int32_t* bins;  // [n_states][n_tiles][2]
   double* out;
   int has_self, has_deltap, use_tma;
+  // speed dependence (absorptionCoefficient_SDVoigt) and extra broadening species
+  const double *sd_air, *sd_self;
+  int n_extra, sdv;
+  const double *xg[RTX_MAX_EXTRA_DILUENTS], *xn[RTX_MAX_EXTRA_DILUENTS], *xd[RTX_MAX_EXTRA_DILUENTS],
+      *xdp[RTX_MAX_EXTRA_DILUENTS], *xsd[RTX_MAX_EXTRA_DILUENTS];
+  double xx[RTX_MAX_EXTRA_DILUENTS];
   const double* cheb;   // [32] Chebyshev nodes cos(theta_k), then [32][32] node-values -> coefficients matrix [k][m]
   int far_ok;    // far-field blocks enabled
   int lorentz;   // PROFILE_LORENTZ instead of PROFILE_VOIGT: no Doppler width, wing = max(OmegaWing, HW*Gamma0)
@@ -122,10 +128,12 @@ struct VoigtParams {
 
 // Everything the reference derives for one line at one (T, p): misc/hapi.py:11058-11131.
 struct LineState {
-  double nu, sg0, W, gamD, gam0, amp;
+  double nu, sg0, W, gamD, gam0, gam2, amp;
   bool keep;
 };
 
+// EXT = false compiles the speed-dependence / extra-species terms out (the common case: air and self only)
+template <bool EXT>
 __device__ __forceinline__ LineState line_state(const VoigtParams& P, int64_t li, int s, double T, double p,
                                                 double lnr) {
   LineState L;
@@ -154,6 +162,22 @@ __device__ __forceinline__ LineState line_state(const VoigtParams& P, int64_t li
     if (P.has_deltap) d += P.deltap_self[li] * (T - RTX_TREF);
     sh += P.x_self * (d * p);
   }
+  double g2 = 0.0;                                               // Gamma2 of the SDVoigt driver, misc/hapi.py:10883-10890
+  if (EXT && P.sdv) {
+    if (P.sd_air) g2 += P.x_air * (P.sd_air[li] * p) * P.gamma_air[li];
+    if (P.has_self && P.sd_self) g2 += P.x_self * (P.sd_self[li] * p) * P.gamma_self[li];
+  }
+  for (int e = 0; EXT && e < P.n_extra; ++e) {                   // any other species of Diluent={...}, :11090-11128
+    if (P.xx[e] == 0.0 || !P.xg[e]) continue;
+    const double gam = P.xg[e][li];
+    const double rp = exp((P.xn[e] ? P.xn[e][li] : P.n_air[li]) * lnr);
+    g0 += P.xx[e] * (gam * p * rp);
+    double d = P.xd[e] ? P.xd[e][li] : 0.0;
+    if (P.xdp[e]) d += P.xdp[e][li] * (T - RTX_TREF);
+    sh += P.xx[e] * (d * p);
+    if (P.sdv && P.xsd[e]) g2 += P.xx[e] * (P.xsd[e][li] * p) * gam;
+  }
+  L.gam2 = g2;
   if (P.doppler) {                                               // misc/hapi.py:11510-11546 (Doppler driver)
     g0 = 0.0;
     sh = (P.doppler == 1) ? P.delta_air[li] * p : 0.0;           // Shift0DB*p/pref, air only, no T dependence
@@ -251,6 +275,110 @@ __device__ __forceinline__ double weideman_re(double x, double y) {
   return fma(2.0, fma(pr, qr, -(pi * qi)), RTX_INV_SQRT_PI * ir);
 }
 
+// ---- complex w(z) and the quadratic speed-dependent profile (absorptionCoefficient_SDVoigt) -------------------------
+// w(x+iy) as hum1_wei returns it (misc/hapi.py:9833-9844): the one-term asymptote t/(0.5+t^2)/sqrt(pi), t = y - ix,
+// or, where |x|+y < 15, Weideman's 24-term series -- real and imaginary part.
+__device__ __forceinline__ void w_hum1_wei(double x, double y, double& wr, double& wi) {
+  if (fabs(x) + y < 15.0) {
+    const double L = RTX_WEIDEMAN_L;
+    const double dr = L + y, nr = L - y;
+    const double m2 = fma(dr, dr, x * x);
+    const double inv = 1.0 / m2;
+    const double Zr = fma(nr, dr, -(x * x)) * inv, Zi = (2.0 * L * x) * inv;
+    const double s = 2.0 * Zr, t = -fma(Zr, Zr, Zi * Zi);
+    double u2 = c_weideman[0];
+    double u1 = fma(s, u2, c_weideman[1]);
+#pragma unroll
+    for (int k = 2; k < 23; ++k) {
+      const double u0 = fma(s, u1, fma(t, u2, c_weideman[k]));
+      u2 = u1;
+      u1 = u0;
+    }
+    const double pr = fma(Zr, u1, fma(t, u2, c_weideman[23])), pi = Zi * u1;
+    const double ir = dr * inv, ii = x * inv;                     // 1/(L-iz)
+    const double qr = fma(ir, ir, -(ii * ii)), qi = 2.0 * ir * ii;
+    wr = fma(2.0, fma(pr, qr, -(pi * qi)), RTX_INV_SQRT_PI * ir);
+    wi = fma(2.0, fma(pr, qi, pi * qr), RTX_INV_SQRT_PI * ii);
+  } else {
+    const double dr = 0.5 + y * y - x * x, di = -2.0 * x * y;     // 0.5 + t^2
+    const double inv = RTX_INV_SQRT_PI / fma(dr, dr, di * di);
+    wr = (y * dr - x * di) * inv;                                 // t * conj(den) / |den|^2
+    wi = (-x * dr - y * di) * inv;
+  }
+}
+// cpf3 (misc/hapi.py:9645-9670): 15-term asymptotic series, real part and imaginary part
+__device__ __forceinline__ void w_cpf3(double x, double y, double& wr, double& wi) {
+  const double inv = 1.0 / fma(x, x, y * y);
+  const double ar = x * inv, ai = -y * inv;                       // zm1 = 1/(x+iy)
+  const double br = ar * ar - ai * ai, bi = 2.0 * ar * ai;        // zm2
+  double tr = 1.0, ti = 0.0, sr = 1.0, si = 0.0;
+#pragma unroll
+  for (int k = 0; k < 15; ++k) {
+    const double f = 0.5 + (double)k;
+    const double nr = (tr * br - ti * bi) * f, ni = (tr * bi + ti * br) * f;
+    tr = nr; ti = ni;
+    sr += tr; si += ti;
+  }
+  // zsum *= i*zm1*pipwoeronehalf
+  const double c = 0.564189583547756;
+  const double mr = -ai * c, mi = ar * c;                         // i*zm1*c
+  wr = sr * mr - si * mi;
+  wi = sr * mi + si * mr;
+}
+__device__ __forceinline__ void csqrt_dev(double a, double b, double& re, double& im) {
+  const double r = hypot(a, b);
+  if (r == 0.0) { re = 0.0; im = 0.0; return; }
+  if (a >= 0.0) { re = sqrt(0.5 * (r + a)); im = b / (2.0 * re); }
+  else { const double t = sqrt(0.5 * (r - a)); im = b >= 0.0 ? t : -t; re = b / (2.0 * im); }
+}
+// Real part of the pCqSDHC line shape (misc/hapi.py:9846-10023) for eta = anuVC = Shift2 = 0 and Gam2 != 0 -- what
+// PROFILE_SDVOIGT asks of it from the SDVoigt driver (misc/hapi.py:10116-10128, 10899).  d = sg - (sg0 + Shift0),
+// c0tr = Gam0 - 1.5 Gam2.  With these arguments the common part reduces to LS = Aterm / pi (:10022).
+__device__ __noinline__ double sdvoigt_re(double d, double c0tr, double gam2, double cte) {
+  const double xr = c0tr / gam2, xi = -d / gam2;                  // X = (i(sg0 - sg) + c0t)/c2t
+  const double h = 1.0 / (2.0 * cte * gam2);                      // csqrtY (real: Shift2 = 0);  Y = h^2
+  const double Y = h * h;
+  const double ax = hypot(xr, xi);
+  if (ax <= 3.0e-8 * Y) {                                         // PART2
+    double sr, si, w1r, w1i, w2r, w2i;
+    csqrt_dev(xr + Y, xi, sr, si);
+    w_hum1_wei(d * cte, c0tr * cte, w1r, w1i);                    // Z1 = (i(sg0 - sg) + c0t)*cte
+    w_hum1_wei(-si, sr + h, w2r, w2i);                            // Z2 = sqrt(X+Y) + csqrtY
+    return (cte * RTX_INV_SQRT_PI) * (w1r - w2r);
+  }
+  if (Y <= 1.0e-15 * ax) {                                        // PART3
+    double qr, qi;
+    csqrt_dev(xr, xi, qr, qi);                                    // sqrt(X)
+    double ar, ai;                                                // Aterm * c2t
+    if (hypot(qr, qi) <= 4.0e3) {
+      double wr, wi;
+      w_hum1_wei(-qi, qr, wr, wi);
+      ar = 2.0 * RTX_SQRT_PI * (RTX_INV_SQRT_PI - (qr * wr - qi * wi));
+      ai = 2.0 * RTX_SQRT_PI * (-(qr * wi + qi * wr));
+    } else {
+      const double n2 = fma(xr, xr, xi * xi);
+      const double ir = xr / n2, ii = -xi / n2;                   // 1/X
+      ar = ir - 1.5 * (ir * ir - ii * ii);
+      ai = ii - 1.5 * (2.0 * ir * ii);
+    }
+    (void)ai;
+    return ar / gam2 / RTX_PI;
+  }
+  double sr, si;                                                  // PART4
+  csqrt_dev(xr + Y, xi, sr, si);
+  const double x1 = -si, y1 = sr - h, y2 = sr + h;                // Z1 = sqrt(X+Y) - csqrtY, Z2 = Z1 + 2 csqrtY
+  const double S1 = sqrt(x1 * x1 + y1 * y1), S2 = sqrt(x1 * x1 + y2 * y2);
+  double w1r, w1i, w2r, w2i;
+  if (fabs(S1 - S2) <= 1.0 && fmax(S1, S2) > 8.0 && fmin(S1, S2) <= 8.0) {
+    w_cpf3(x1, y1, w1r, w1i);
+    w_cpf3(x1, y2, w2r, w2i);
+  } else {
+    w_hum1_wei(x1, y1, w1r, w1i);
+    w_hum1_wei(x1, y2, w2r, w2i);
+  }
+  return (cte * RTX_INV_SQRT_PI) * (w1r - w2r);
+}
+
 struct __align__(16) WideRec {
   double sg0, a, ah, m, c;
   short lo, hi, clo, chi;
@@ -341,7 +469,8 @@ struct PrepParams {
   double *st_q, *st_d, *st_wb;
   double x_air, x_self, wing_abs, wing_hw;
   double nu_max, gair_max, gself_max, nair_min, nair_max, nself_min, nself_max;
-  int doppler;
+  int doppler, n_extra;
+  double xx[RTX_MAX_EXTRA_DILUENTS], xg_max[RTX_MAX_EXTRA_DILUENTS], xn_min[RTX_MAX_EXTRA_DILUENTS], xn_max[RTX_MAX_EXTRA_DILUENTS];
 };
 
 __global__ void state_prep_kernel(PrepParams P) {
@@ -363,7 +492,9 @@ __global__ void state_prep_kernel(PrepParams P) {
   const double lnr = log(RTX_TREF / T);
   const double ra = fmax(exp(P.nair_min * lnr), exp(P.nair_max * lnr));
   const double rs = fmax(exp(P.nself_min * lnr), exp(P.nself_max * lnr));
-  const double g0 = fabs(p) * (fabs(P.x_air) * P.gair_max * ra + fabs(P.x_self) * P.gself_max * rs);
+  double g0 = fabs(p) * (fabs(P.x_air) * P.gair_max * ra + fabs(P.x_self) * P.gself_max * rs);
+  for (int e = 0; e < P.n_extra; ++e)
+    g0 += fabs(p) * fabs(P.xx[e]) * P.xg_max[e] * fmax(exp(P.xn_min[e] * lnr), exp(P.xn_max[e] * lnr));
   double wb = fmax(fmax(P.wing_abs, P.wing_hw * g0), P.wing_hw * dmax * P.nu_max);
   P.st_wb[s] = wb * (1.0 + 1e-6) + 1e-9;
 }
@@ -471,7 +602,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
 // cores stay in FP64.
 // WS = warp-specialised variant: NPW extra producer warps run the prologue one chunk ahead (double-buffered
 // records, mbarrier full/empty handshake); the eight consumer warps never meet at a block-wide barrier.
-template <int K, int MODE, bool WS>
+template <int K, int MODE, bool WS, bool EXT = false>
 __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RTX_MINBLOCKS_K4 : RTX_MINBLOCKS)) voigt_tile_kernel(const VoigtParams P) {
   constexpr bool FAST = (MODE == 1);
   constexpr bool F32 = (MODE == 2);
@@ -588,7 +719,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       sr.sub = 0;
       double h_keep = 0.0;
       if (li < last) {
-        const LineState L = line_state(P, li, s, T, p, lnr);
+        const LineState L = line_state<EXT>(P, li, s, T, p, lnr);
         if (L.keep) {
           const int lo = count_le(s_grid, ts, L.nu - L.W);                // bisect(Omegas, nu-W), misc/hapi.py:11133
           const int hi = count_le(s_grid, ts, L.nu + L.W);                // bisect(Omegas, nu+W), misc/hapi.py:11134
@@ -657,7 +788,14 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
               }
             }
             sr.lo = (short)lo; sr.hi = (short)hi; sr.clo = (short)clo; sr.chi = (short)chi;
-            if (P.doppler) {
+            if (EXT && P.sdv && L.gam2 != 0.0) {
+              // speed-dependent line (Gamma2 != 0): the whole window goes to pass 2, evaluated with pcqsdhc PART2-4
+              sr.a = L.gam0 - 1.5 * L.gam2;             // Re c0t
+              sr.ah = L.gam2;
+              sr.cw = L.amp;
+              sr.sub = 2;
+              has_seg = true; sr.s = sr.clo = (short)lo; sr.e = sr.chi = (short)hi;
+            } else if (P.doppler) {
               // cSqrtLn2divSqrtPi*exp(-cLn2*((sg-sg0)/GamD)**2)/GamD (misc/hapi.py:10160, hapi's truncated constants):
               // the whole window is a "core" of pass 2, evaluated with exp instead of the rational series
               sr.cte = 0.8325546111576705 / L.gamD;     // sqrt(cLn2), cLn2 = 0.6931471805599
@@ -906,8 +1044,10 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
           const int ic = ok[h] ? ii[h] : own_lo;
           const double om = s_grid[ic];
           const double x = __dmul_rn(om - rec.sg0, rec.cte);
-          vv[h] = rec.cw * (P.doppler ? exp(-(x * x)) : weideman_re(x, rec.y));
-          if (rec.sub && rec.lo <= own_lo && rec.hi >= own_hi)        // pass 1 took this slice test-free
+          vv[h] = rec.cw * ((EXT && rec.sub == 2) ? sdvoigt_re(om - rec.sg0, rec.a, rec.ah, rec.cte)
+                            : P.doppler  ? exp(-(x * x))
+                                         : weideman_re(x, rec.y));
+          if (rec.sub == 1 && rec.lo <= own_lo && rec.hi >= own_hi)   // pass 1 took this slice test-free
             vv[h] = cheap_term<FAST>(om, rec.sg0, -rec.a, -rec.ah, rec.m, rec.c, vv[h]);   // same reciprocal as pass 1
         }
 #pragma unroll
@@ -1016,7 +1156,7 @@ __global__ void count_kernel(const VoigtParams P, unsigned long long* __restrict
     const int s = (int)(i / P.n_lines);
     const int64_t li = i % P.n_lines;
     const double T = P.T[s], p = P.p[s];
-    const LineState L = line_state(P, li, s, T, p, log(RTX_TREF / T));
+    const LineState L = line_state<true>(P, li, s, T, p, log(RTX_TREF / T));
     if (L.keep) {
       const int64_t lo = bisect_right_dev64(P.grid, P.nx, L.nu - L.W);
       const int64_t hi = bisect_right_dev64(P.grid, P.nx, L.nu + L.W);
@@ -1059,13 +1199,13 @@ size_t tile_smem_bytes() {
                                       (sizeof(SegRec) + (MODE == 2 ? sizeof(WideRec) : 0));
 }
 
-template <int K, int MODE, bool WS>
+template <int K, int MODE, bool WS, bool EXT = false>
 int launch_tile(const VoigtParams& P, cudaStream_t st) {
   const size_t smem = tile_smem_bytes<K, MODE, WS>();
-  RTX_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<K, MODE, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RTX_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<K, MODE, WS, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t blocks = (int64_t)P.n_tiles * P.n_states;
   if (blocks > 2147483647LL) { rtx_set_error("rtx_voigt_sum: too many (tile, state) pairs for one launch"); return RTX_E_INVALID; }
-  voigt_tile_kernel<K, MODE, WS><<<(unsigned)blocks, WS ? NT + 32 * NPW : NT, smem, st>>>(P);
+  voigt_tile_kernel<K, MODE, WS, EXT><<<(unsigned)blocks, WS ? NT + 32 * NPW : NT, smem, st>>>(P);
   RTX_CUDA(cudaGetLastError());
   return RTX_OK;
 }
@@ -1101,6 +1241,13 @@ int fill_params(rtx_handle* h, VoigtParams& P, int n_states, const double* T, co
   P.T = T; P.p = p; P.weight = weight; P.n_iso = h->n_iso; P.n_states = n_states;
   P.x_air = x_air; P.x_self = x_self; P.wing_abs = wing_abs; P.wing_hw = wing_hw; P.s_thr = s_thr;
   P.grid = grid; P.nx = nx;
+  P.sd_air = L.sd_air; P.sd_self = L.sd_self;
+  P.n_extra = 0; P.sdv = 0;
+  for (int e = 0; e < RTX_MAX_EXTRA_DILUENTS; ++e) {
+    P.xg[e] = L.xg[e]; P.xn[e] = L.xn[e]; P.xd[e] = L.xd[e]; P.xdp[e] = L.xdp[e]; P.xsd[e] = L.xsd[e];
+    P.xx[e] = L.xg[e] ? h->x_extra[e] : 0.0;
+    if (P.xx[e] != 0.0) P.n_extra = e + 1;
+  }
   P.has_self = (x_self != 0.0) ? 1 : 0;
   P.has_deltap = L.has_deltap ? 1 : 0;
   P.use_tma = ((reinterpret_cast<uintptr_t>(grid) & 15u) == 0) ? 1 : 0;
@@ -1124,6 +1271,10 @@ int run_prep(rtx_handle* h, VoigtParams& P, cudaStream_t st, double** st_wb_out)
   Q.nu_max = L.nu_max; Q.gair_max = L.gair_max; Q.gself_max = L.gself_max; Q.nair_min = L.nair_min;
   Q.nair_max = L.nair_max; Q.nself_min = L.nself_min; Q.nself_max = L.nself_max;
   Q.doppler = P.doppler;
+  Q.n_extra = P.n_extra;
+  for (int e = 0; e < RTX_MAX_EXTRA_DILUENTS; ++e) {
+    Q.xx[e] = P.xx[e]; Q.xg_max[e] = L.xg_max[e]; Q.xn_min[e] = L.xn_min[e]; Q.xn_max[e] = L.xn_max[e];
+  }
   state_prep_kernel<<<(P.n_states + 127) / 128, 128, 0, st>>>(Q);
   RTX_CUDA(cudaGetLastError());
   h->launches++;
@@ -1155,6 +1306,8 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
   P.lorentz = (flags & RTX_VOIGT_LORENTZ) ? 1 : 0;
   P.doppler = (flags & RTX_VOIGT_DOPPLER) ? ((flags & RTX_VOIGT_NOSHIFT) ? 2 : 1) : 0;
   RTX_REQUIRE(!(P.lorentz && P.doppler), "RTX_VOIGT_LORENTZ and RTX_VOIGT_DOPPLER are exclusive");
+  P.sdv = (flags & RTX_VOIGT_SDVOIGT) ? 1 : 0;
+  RTX_REQUIRE(!(P.sdv && (P.lorentz || P.doppler)), "RTX_VOIGT_SDVOIGT excludes the Lorentz and Doppler drivers");
   double* st_wb = nullptr;
   rc = run_prep(h, P, st, &st_wb);
   if (rc) return rc;
@@ -1209,8 +1362,11 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
   // RTX_VOIGT_EXACT_RCP adds the second step (full double precision)
   const int mode = (flags & RTX_VOIGT_FP32) ? 2 : ((flags & RTX_VOIGT_EXACT_RCP) ? 0 : 1);
   const bool ws = (flags & RTX_VOIGT_WARPSPEC) != 0;
+  // speed dependence / extra broadening species: the extended instantiation (FP64, not warp-specialised)
+  const bool ext = P.sdv || P.n_extra > 0;
 #define RTX_LAUNCH(KK)                                                                                        \
-  (ws ? (mode == 2 ? launch_tile<KK, 2, true>(P, st) : mode == 1 ? launch_tile<KK, 1, true>(P, st) : launch_tile<KK, 0, true>(P, st)) \
+  (ext ? (mode == 0 ? launch_tile<KK, 0, false, true>(P, st) : launch_tile<KK, 1, false, true>(P, st))          \
+   : ws ? (mode == 2 ? launch_tile<KK, 2, true>(P, st) : mode == 1 ? launch_tile<KK, 1, true>(P, st) : launch_tile<KK, 0, true>(P, st)) \
       : (mode == 2 ? launch_tile<KK, 2, false>(P, st) : mode == 1 ? launch_tile<KK, 1, false>(P, st) : launch_tile<KK, 0, false>(P, st)))
   switch (K) {
     case 8: rc = RTX_LAUNCH(8); break;

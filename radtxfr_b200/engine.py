@@ -36,6 +36,8 @@ def _torch():
 # RTX_VOIGT_* flag bits (include/radtxfr_b200.h)
 VOIGT_FP32, VOIGT_WARPSPEC, VOIGT_LORENTZ, VOIGT_DOPPLER, VOIGT_NOSHIFT = 2, 4, 16, 32, 64
 VOIGT_EXACT_RCP, VOIGT_NOFAR, VOIGT_TILE_SHIFT = 128, 4096, 8
+VOIGT_SDVOIGT = 8192
+MAX_EXTRA_DILUENTS = 4
 # precision names of the shims -> flags.  "fp64" (default): FP64 with the one-Newton-step reciprocal (<= 9e-13 per
 # term) and far-field blocks (< 1e-13); "fp64_fast" is the same thing (kept for round-1 callers); "fp64_exact":
 # every (line, grid point) pair evaluated at the grid point with the fully refined reciprocal; "fp32": optional
@@ -230,6 +232,30 @@ class LineDB:
                   _hptr(cat["n_self"]), _hptr(cat["delta_air"]), _hptr(cat["deltap_air"]),
                   _hptr(cat["delta_self"]), _hptr(cat["deltap_self"]), _hptr(iso_idx))
         self.has_self = cat["gamma_self"] is not None
+        # speed-dependence columns and broadening species other than air / self (hapi reads whatever gamma_<sp>,
+        # n_<sp>, delta_<sp>, deltap_<sp>, SD_<sp> columns the table has: misc/hapi.py:11090-11128, 10883-10890)
+        low = [{k.lower(): k for k in t} for t in tables]
+
+        def column_ci(name):
+            if not any(name in lo for lo in low):
+                return None
+            parts = [np.asarray(t[lo[name]], dtype=np.float64) if name in lo else np.zeros(n, dtype=np.float64)
+                     for t, lo, n in zip(tables, low, n_each)]
+            return np.ascontiguousarray(np.concatenate(parts))
+        sd_air, sd_self = column_ci("sd_air"), column_ci("sd_self")
+        self.has_sd = sd_air is not None or sd_self is not None
+        if self.has_sd and self.n_lines:
+            _lib.call("rtx_lines_set_sd", self.handle.h, _hptr(sd_air), _hptr(sd_self))
+        species = sorted({k[6:] for lo in low for k in lo if k.startswith("gamma_")} - {"air", "self"})
+        if len(species) > MAX_EXTRA_DILUENTS:
+            raise ValueError("line table has %d broadening species besides air and self; at most %d are supported"
+                             % (len(species), MAX_EXTRA_DILUENTS))
+        self.extra_species = species
+        for slot, sp in enumerate(species):
+            cols = [column_ci(p + sp) for p in ("gamma_", "n_", "delta_", "deltap_", "sd_")]
+            self.has_sd = self.has_sd or cols[4] is not None
+            if self.n_lines:
+                _lib.call("rtx_lines_set_diluent", self.handle.h, slot, *[_hptr(c) for c in cols])
         self.nu_min = float(cat["nu"].min()) if self.n_lines else 0.0
         self.nu_max = float(cat["nu"].max()) if self.n_lines else 0.0
         # host-side summary for cost estimates (distributed.estimate_tile_costs): sorted line centres and the extrema
@@ -270,10 +296,19 @@ class LineDB:
                 raise Exception("TIPS: no data for M,I = %d,%d." % mi)               # misc/hapi.py:9581
 
     # -- kernels ------------------------------------------------------------------------------------
+    def _set_mix(self, x_extra):
+        """Fractions of the extra broadening species ({species: x}) for the next kernel call (rtx_voigt_set_mix)."""
+        x = np.zeros(MAX_EXTRA_DILUENTS)
+        for sp, val in (x_extra or {}).items():
+            if sp.lower() in self.extra_species:
+                x[self.extra_species.index(sp.lower())] += float(val)
+        _lib.call("rtx_voigt_set_mix", self.handle.h, MAX_EXTRA_DILUENTS, _hptr(x))
+
     def voigt_sum(self, T, p, weight, grid, x_air=1.0, x_self=0.0, wing_abs=0.0, wing_hw=50.0, s_threshold=0.0,
-                  out=None, flags=0):
+                  out=None, flags=0, x_extra=None):
         """out[s, i] = sum_lines weight[s, iso]*S(T_s)*V(grid[i]) (rtx_voigt_sum).  All arguments may be numpy
-        or CUDA tensors; returns a CUDA float64 tensor [n_states, nx]."""
+        or CUDA tensors; returns a CUDA float64 tensor [n_states, nx].  x_extra: {species: fraction} for broadening
+        species other than air / self that the table has columns for (others contribute nothing, as in hapi)."""
         torch = _torch()
         dev = self.device
         T = to_device(T, dev).reshape(-1)
@@ -289,13 +324,18 @@ class LineDB:
             return out
         if self.n_lines == 0:
             return out.zero_()
+        if self.extra_species:
+            self._set_mix(x_extra)
         _lib.call("rtx_voigt_sum", self.handle.h, n_states, _ptr(T), _ptr(p), _ptr(weight), float(x_air),
                   float(x_self), float(wing_abs), float(wing_hw), float(s_threshold), _ptr(grid), nx, _ptr(out),
                   int(flags), _stream(dev))
         return out
 
-    def count_evals(self, T, p, weight, grid, x_air=1.0, x_self=0.0, wing_abs=0.0, wing_hw=50.0, s_threshold=0.0):
+    def count_evals(self, T, p, weight, grid, x_air=1.0, x_self=0.0, wing_abs=0.0, wing_hw=50.0, s_threshold=0.0,
+                    x_extra=None):
         """(evals, evals in the Weideman region) exactly as SURVEY.md 8d defines them (rtx_voigt_count)."""
+        if self.extra_species:
+            self._set_mix(x_extra)
         torch = _torch()
         dev = self.device
         T = to_device(T, dev).reshape(-1)

@@ -183,11 +183,12 @@ def absorptionCoefficient_Voigt(Components=None, SourceTables=None, partitionFun
         elif GammaL == 'gamma_self': Diluent = {'self': 1.}
         else: raise Exception('Unknown GammaL value: %s' % GammaL)                 # misc/hapi.py:11032
     x_air = x_self = 0.0
-    for key, val in Diluent.items():
-        k = key.lower()
+    x_extra = {}
+    for key, val in Diluent.items():          # any species: hapi reads gamma_<sp>, n_<sp>, delta_<sp>, ... and treats a
+        k = key.lower()                        # missing gamma_<sp> column as zero broadening (misc/hapi.py:11090-11128)
         if k == 'air': x_air += float(val)
         elif k == 'self': x_self += float(val)
-        else: raise NotImplementedError("diluent %r: only 'air' and 'self' broadening are supported" % key)
+        else: x_extra[k] = x_extra.get(k, 0.0) + float(val)
     if x_self != 0.0 and not db.has_self:
         x_self = 0.0      # no gamma_self column: the reference's try/except gives Gamma0DB = 0 (:11097-11100)
 
@@ -196,7 +197,7 @@ def absorptionCoefficient_Voigt(Components=None, SourceTables=None, partitionFun
         db.check_tips(w_iso != 0.0)
     xs = db.voigt_sum(np.array([T]), np.array([p]), w_iso[None, :], Omegas, x_air=x_air, x_self=x_self,
                       wing_abs=float(OmegaWing), wing_hw=float(OmegaWingHW),
-                      s_threshold=float(IntensityThreshold),
+                      s_threshold=float(IntensityThreshold), x_extra=x_extra,
                       flags=engine.PRECISION_FLAGS[VARIABLES["precision"]] | int(_profile_flags))[0]
     if as_tensor:
         return Omegas, xs
@@ -204,16 +205,13 @@ def absorptionCoefficient_Voigt(Components=None, SourceTables=None, partitionFun
 
 
 def absorptionCoefficient_SDVoigt(*args, **kwargs):
-    """Speed-dependent Voigt driver of hapi (misc/hapi.py:10657-10905) for tables WITHOUT speed-dependence columns
-    -- the situation of the reference's only hapi call site (misc/RT_gen_AbsXS_files.py:90: plain HITRAN tables).
-    With SD_<diluent> absent hapi sets Gamma2 = Shift2 = 0 (:10883-10890) and pcqsdhc takes its PART1 branch, i.e.
-    the Voigt profile centred on nu + Shift0 (the centre is formed as (nu - omega) + Shift0 instead of
-    (nu + Shift0) - omega: a last-bit difference).  Tables that do carry SD_* columns raise NotImplementedError."""
-    st = kwargs.get("SourceTables", args[1] if len(args) > 1 else None)
-    names = st if type(st) in (list, tuple) else [st]
-    for n in names:
-        if n in LOCAL_TABLE_CACHE and any(k.lower().startswith("sd_") for k in LOCAL_TABLE_CACHE[n]["data"]):
-            raise NotImplementedError("speed-dependent broadening (SD_* columns) is not on the accelerated path")
+    """Speed-dependent Voigt driver of hapi (misc/hapi.py:10657-10905).  Gamma2 = sum_d x_d * SD_d * p/pref * gamma_d
+    over the diluents (:10883-10890), Shift2 = 0; lines with Gamma2 != 0 take the quadratic speed-dependent profile
+    (pcqsdhc PART2-4, :9923-10020, with cpf3 :9645-9670 where the reference selects it), lines with Gamma2 == 0 --
+    every line of a table without SD_<diluent> columns, the situation of the reference's only hapi call site,
+    misc/RT_gen_AbsXS_files.py:90 -- its PART1 branch, i.e. the Voigt profile centred on nu + Shift0 (the reference
+    forms that centre as (nu - omega) + Shift0 instead of (nu + Shift0) - omega: a last-bit difference)."""
+    kwargs["_profile_flags"] = int(kwargs.get("_profile_flags", 0)) | engine.VOIGT_SDVOIGT
     return absorptionCoefficient_Voigt(*args, **kwargs)
 
 

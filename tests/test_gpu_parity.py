@@ -495,9 +495,37 @@ def test_sdvoigt_lut_and_afit_xs(mods, tmp_path):
     assert np.array_equal(np.frombuffer(open(f, "rb").read(), dtype=np.uint8), g["afit_bytes"])
     X, Y, T, P, ID, name = formats.AFIT_XS_read(f)
     assert np.array_equal(Y, g["xs0"]) and (T, P, ID, name) == (296.0, 101325.0, 2, "HITRAN2016-synthetic")
-    hapi.storeTable("sd", dict(cols, SD_air=np.full(250, 0.1)))
-    with pytest.raises(NotImplementedError):
-        hapi.absorptionCoefficient_SDVoigt(SourceTables="sd", OmegaGrid=grid)
+
+
+def test_sdvoigt_speed_dependence_and_diluents(mods):
+    """True speed-dependent Voigt (tables with SD_<diluent> columns: pcqsdhc PART2-4 with cpf3 where the reference selects
+    it) and broadening species other than air / self (gamma_h2, n_h2, delta_h2, deltap_h2; gamma_he without an n column;
+    a species the table has no columns for contributes nothing), against the reference's own outputs
+    (tests/golden/sdvoigt.npz) and the oracle port of pcqsdhc."""
+    import make_golden as mg
+    hapi, port = mods["hapi"], mods["port"]
+    g = golden("sdvoigt.npz")
+    cols = mg.sdv_table()
+    hapi.storeTable("sdv", cols)
+    grid = np.linspace(1200.0, 1300.0, 20001)
+    for k, (T, p, dil) in enumerate(mg.SDV_CASES):
+        _, xs = hapi.absorptionCoefficient_SDVoigt(SourceTables="sdv", Environment={"T": T, "p": p}, OmegaGrid=grid,
+                                                   Diluent=dil)
+        assert_parity(xs, g["sd%d" % k], RTOL, FLOOR, "SDVoigt with SD columns, case %d" % k)
+        _, plain = hapi.absorptionCoefficient_Voigt(SourceTables="sdv", Environment={"T": T, "p": p}, OmegaGrid=grid,
+                                                    Diluent=dil)
+        assert np.max(np.abs(plain - g["sd%d" % k])) > 1e-3 * np.max(g["sd%d" % k])      # the SD columns matter
+    for k, (T, p, dil) in enumerate(mg.DIL_CASES):
+        _, xs = hapi.absorptionCoefficient_Voigt(SourceTables="sdv", Environment={"T": T, "p": p}, OmegaGrid=grid,
+                                                 Diluent=dil)
+        assert_parity(xs, g["dil%d" % k], RTOL, FLOOR, "Voigt with h2/he/co2 diluents, case %d" % k)
+    # tiny Gamma2 (PART2 of pcqsdhc: |X| <= 3e-8 |Y|) and a fine grid, against the oracle port
+    tiny = dict(cols, SD_air=np.full(300, 1e-13))
+    hapi.storeTable("sdv_tiny", tiny)
+    fine = np.linspace(1240.0, 1242.0, 4001)
+    _, xs = hapi.absorptionCoefficient_SDVoigt(SourceTables="sdv_tiny", Environment={"T": 260.0, "p": 0.5}, OmegaGrid=fine)
+    _, ref = port.absorption_coefficient_sdvoigt(tiny, T=260.0, p=0.5, OmegaGrid=fine)
+    assert_parity(xs, ref, RTOL, FLOOR, "SDVoigt PART2")
 
 
 def test_hsi_pixels(mods):

@@ -195,3 +195,27 @@ def test_doppler():
         _, xs = port.absorption_coefficient_doppler(cols, T=T, p=p, OmegaGrid=grid, **kw)
         ref = np.zeros_like(xs); ref[g["idx%d" % k]] = g["xs%d" % k]
         assert_parity(xs, ref, what="Doppler %d" % k, **TIGHT)
+
+
+def test_sdvoigt_and_diluents_port():
+    """The port of pcqsdhc (all parts) / absorptionCoefficient_SDVoigt and the generic diluent loop against the reference's
+    outputs for a table with SD_air / SD_self / gamma_h2 / gamma_he columns (tests/golden/sdvoigt.npz)."""
+    import make_golden as mg
+    g = golden("sdvoigt.npz")
+    cols = mg.sdv_table()
+    grid = np.linspace(1200.0, 1300.0, 20001)
+    for k, (T, p, dil) in enumerate(mg.SDV_CASES[:2]):
+        _, xs = port.absorption_coefficient_sdvoigt(cols, T=T, p=p, OmegaGrid=grid, Diluent=dil)
+        assert_parity(xs, g["sd%d" % k], rtol=1e-11, floor=1e-15, what="SDVoigt port case %d" % k)
+    T, p, dil = mg.DIL_CASES[1]
+    _, xs = port.absorption_coefficient_voigt(cols, T=T, p=p, OmegaGrid=grid, Diluent=dil)
+    assert_parity(xs, g["dil1"], what="diluent port", **TIGHT)
+    # cpf3 against the reference's own series evaluated in complex arithmetic
+    x, y = np.array([9.0, -7.5, 8.2]), np.array([1.0, 3.0, 0.05])
+    z = x + 1j * y
+    s, t = 1.0 + 0j, 1.0 + 0j
+    for k in range(15):
+        t = t * ((1 / z) ** 2 * (k + 0.5)); s = s + t
+    ref = s * (1j / z * 0.564189583547756)
+    wr, wi = port.cpf3(x, y)
+    assert np.allclose(wr, ref.real, rtol=1e-14) and np.allclose(wi, ref.imag, rtol=1e-14)

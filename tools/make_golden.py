@@ -237,6 +237,40 @@ def g_optcols():
     save("optcols.npz", source="misc/hapi.py:10906-11141 with n_self/delta_self/deltap_* columns and diluent mixes", **out)
 
 
+def sdv_table():
+    """300 H2O lines with speed-dependence columns for air and self, and a third broadening species (H2)."""
+    rng = np.random.default_rng(19)
+    cols = syn.synthetic_lines(58, 300, 1180.0, 1320.0, 1)
+    n = 300
+    cols["SD_air"] = np.where(rng.random(n) < 0.2, 0.0, rng.uniform(0.05, 0.2, n))      # a fifth of the lines: no SD
+    cols["SD_self"] = rng.uniform(0.05, 0.15, n)
+    cols["n_self"] = rng.uniform(0.3, 0.9, n)
+    cols["delta_self"] = rng.uniform(-0.02, 0.01, n)
+    cols["gamma_h2"] = rng.uniform(0.03, 0.12, n)
+    cols["n_h2"] = rng.uniform(0.3, 0.7, n)
+    cols["delta_h2"] = rng.uniform(-0.01, 0.01, n)
+    cols["deltap_h2"] = rng.uniform(-2e-5, 2e-5, n)
+    cols["gamma_he"] = rng.uniform(0.01, 0.05, n)                                       # no n_he column -> n_air
+    return cols
+
+
+SDV_CASES = [(296.0, 1.0, {"air": 1.0}), (250.0, 0.3, {"air": 0.7, "self": 0.3}), (230.0, 0.02, {"air": 1.0}),
+             (280.0, 0.5, {"air": 0.5, "h2": 0.3, "he": 0.2})]
+DIL_CASES = [(296.0, 1.0, {"h2": 1.0}), (260.0, 0.4, {"air": 0.5, "h2": 0.3, "he": 0.15, "co2": 0.05})]
+
+
+def g_sdvoigt():
+    cols = sdv_table()
+    grid = np.linspace(1200.0, 1300.0, 20001)
+    out = {}
+    for k, (T, p, dil) in enumerate(SDV_CASES):
+        _, out["sd%d" % k] = R.ref_xsect_sd(cols, T, p, grid, Diluent=dil)
+    for k, (T, p, dil) in enumerate(DIL_CASES):
+        _, out["dil%d" % k] = R.ref_xsect(cols, T, p, grid, Diluent=dil)
+    save("sdvoigt.npz", source="misc/hapi.py:10657-10905 absorptionCoefficient_SDVoigt with SD_<diluent> columns (pcqsdhc "
+         "PART2-4, :9923-10020); :10906-11141 with gamma_h2 / gamma_he diluents", **out)
+
+
 def g_lut():
     """SDVoigt on a table without SD columns (the reference's own call convention, misc/RT_gen_AbsXS_files.py:90)
     and the AFIT_XS writer, whose source is lifted out of the script with ast (the script itself fetches HITRAN
@@ -353,6 +387,6 @@ def g_mbi():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi", "lorentz", "doppler", "spectra", "sensor_f32", "reduce2"]
+    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi", "lorentz", "doppler", "spectra", "sensor_f32", "reduce2", "sdvoigt"]
     for w in which:
         globals()["g_" + w]()
