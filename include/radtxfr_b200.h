@@ -174,6 +174,33 @@ int rtx_tud(rtx_handle* h, int n_atm, int n_layers, const double* od_dev, const 
             const double* mu_host, int n_mu, int n_angle, int return_od, double* tau_dev, double* lu_dev,
             double* ld_dev, void* stream);
 
+/* ---- the whole path for a host without Python ------------------------------------------------------------------
+ * rtx_set_iso_molecules: molecule number and abundance factor (factor * abundance / natural_abundance,
+ * misc/hapi.py:11136-11138) of every isotopologue of the table set by rtx_set_iso_table.  Host pointers, copied.
+ * rtx_layer_weights: pressures in atm and the per-(state, isotopologue) column amounts that turn the Voigt sum into a
+ * layer's optical depth -- what the reference gets from LBLRTM per layer (compute_OD, radiative_transfer.py:395-456)
+ * and SURVEY.md App. B.1 wires through hapi:
+ *     weight[s][iso] = (MF[s][m(iso)] * 1e-6) * volumeConcentration(p_s, T_s) * (PL_s * 1e5) * factor[iso]
+ *   T_dev [K], P_pa_dev [Pa], PL_km_dev [km]: [n_states];  mf_ppmv_dev [n_states][n_mol] with the molecule numbers
+ *   mf_id_host[n_mol] (MFs_VAL / MFs_ID of the reference's options, radiative_transfer.py:171-177);
+ *   p_atm_dev [n_states], weight_dev [n_states][n_iso] are written.
+ * rtx_tud_from_lines: atmosphere tables in, (tau, Lu, Ld) out, for n_atm atmospheres of n_layers layers each -- the body
+ * of the production loop `for jj: compute_TUD(..., MFs_VAL=MFs_VAL[jj], Ts=Ts[jj])` (Generate_LWIR_TUD.py:117-122) with
+ * compute_TUD = radiative_transfer.py:274-392.  Column amounts, Voigt sums (rtx_voigt_sum arguments x_air .. voigt_flags)
+ * and layer integration (rtx_tud arguments Z_host .. return_od) run back to back on `stream`; optical depth lives in
+ * the handle's scratch (at most 4 GB at a time).  T / P / PL: [n_atm][n_layers], mf: [n_atm][n_layers][n_mol]; outputs
+ * as rtx_tud. */
+int rtx_set_iso_molecules(rtx_handle* h, int n_iso, const int32_t* molec_id, const double* factor);
+int rtx_layer_weights(rtx_handle* h, int n_states, const double* T_dev, const double* P_pa_dev, const double* PL_km_dev,
+                      const double* mf_ppmv_dev, int n_mol, const int32_t* mf_id_host, double* p_atm_dev,
+                      double* weight_dev, void* stream);
+int rtx_tud_from_lines(rtx_handle* h, int n_atm, int n_layers, const double* T_dev, const double* P_pa_dev,
+                       const double* PL_km_dev, const double* mf_ppmv_dev, int n_mol, const int32_t* mf_id_host,
+                       double x_air, double x_self, double wing_abs, double wing_hw, double s_threshold, int voigt_flags,
+                       const double* grid_dev, int64_t nx, const double* Z_host, const double* alt_host, int n_alt,
+                       const double* mu_host, int n_mu, int n_angle, int return_od, double* tau_dev, double* lu_dev,
+                       double* ld_dev, void* stream);
+
 /* planckian(X, T) in wavenumber or wavelength form (radiative_transfer.py:792-848):
  * out_dev[nx][nT].  wavelength!=0 selects the micrometre branch (the mean(X)<50 heuristic lives in
  * the shim). */
@@ -231,6 +258,14 @@ int rtx_hsi_pixels_f32(rtx_handle* h, const double* X_dev, int64_t nx, const dou
 int rtx_ils_apply(rtx_handle* h, int mode, const double* X_dev, int64_t nx, const double* Y_dev, int64_t ns,
                   int n_bands, const double* centre_dev, const double* width_dev, double* out_dev,
                   void* stream);
+
+/* Band centres and widths of the MAKO line shapes, host only (no handle): mode 0 = triangle, exactly as
+ * radiative_transfer.py:1226-1241 derives them (optional res_factor interpolation of the 128 band wavelengths, sort of
+ * 1e4/lambda, clip to the open interval (xmin, xmax) = (X.min(), X.max()), half-base fwhm_sf*|gradient|*1.6, centres
+ * scale*X_out + shift); mode 1 = Gaussian of ILS_MAKO.py:20-22 (no clip, sigma = |gradient|; res_factor, fwhm_sf, shift,
+ * scale ignored).  res_factor <= 0 means none.  Call with capacity 0 to get the band count in *n_out. */
+int rtx_mako_bands(int mode, double xmin, double xmax, double res_factor, double fwhm_sf, double shift, double scale,
+                   int capacity, double* X_out, double* centre, double* width, int* n_out);
 
 /* ---- reduceResolution / smooth (radiative_transfer.py:1266-1350), the step after TUD in the production driver
  * (Generate_LWIR_TUD.py:82-85,124-126).

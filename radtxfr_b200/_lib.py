@@ -38,6 +38,14 @@ _SIGNATURES = {
     "rtx_tips": [c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "rtx_tud": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int,
                 c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "rtx_set_iso_molecules": [c_void_p, c_int, c_void_p, c_void_p],
+    "rtx_layer_weights": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                          c_void_p],
+    "rtx_tud_from_lines": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                           c_double, c_double, c_double, c_double, c_double, c_int, c_void_p, c_int64, c_void_p,
+                           c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "rtx_mako_bands": [c_int, c_double, c_double, c_double, c_double, c_double, c_double, c_int, c_void_p, c_void_p,
+                       c_void_p, POINTER(c_int)],
     "rtx_planck": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p],
     "rtx_brightness": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_double, c_void_p, c_void_p],
     "rtx_apparent_radiance": [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,

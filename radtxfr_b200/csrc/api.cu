@@ -61,6 +61,9 @@ extern "C" int rtx_destroy(rtx_handle* h) {
   for (double* p : {h->d_mass, h->d_tipsT, h->d_q, h->d_qref, h->d_state}) if (p) cudaFree(p);
   if (h->d_bins) cudaFree(h->d_bins);
   if (h->d_cheb) cudaFree(h->d_cheb);
+  if (h->d_iso_mol) cudaFree(h->d_iso_mol);
+  if (h->d_iso_factor) cudaFree(h->d_iso_factor);
+  if (h->d_pipe) cudaFree(h->d_pipe);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   delete h;
   return RTX_OK;

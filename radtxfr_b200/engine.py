@@ -231,6 +231,9 @@ class LineDB:
                   _hptr(cat["elower"]), _hptr(cat["gamma_air"]), _hptr(cat["gamma_self"]), _hptr(cat["n_air"]),
                   _hptr(cat["n_self"]), _hptr(cat["delta_air"]), _hptr(cat["deltap_air"]),
                   _hptr(cat["delta_self"]), _hptr(cat["deltap_self"]), _hptr(iso_idx))
+        _lib.call("rtx_set_iso_molecules", self.handle.h, n_iso,
+                  _hptr(np.ascontiguousarray(self.iso_molecule.astype(np.int32)) if len(pairs) else np.zeros(1, np.int32)),
+                  _hptr(np.ascontiguousarray(self.iso_factors(None, 1.0))))
         self.has_self = cat["gamma_self"] is not None
         # speed-dependence columns and broadening species other than air / self (hapi reads whatever gamma_<sp>,
         # n_<sp>, delta_<sp>, deltap_<sp>, SD_<sp> columns the table has: misc/hapi.py:11090-11128, 10883-10890)
@@ -364,6 +367,64 @@ class LineDB:
         out = torch.empty((T.numel(), self.n_iso), dtype=torch.float64, device=self.device)
         _lib.call("rtx_tips", self.handle.h, T.numel(), _ptr(T), _ptr(out), _stream(self.device))
         return out
+
+
+    def layer_weights(self, T, P_pa, PL_km, MF_VAL, MF_ID):
+        """rtx_layer_weights: (p_atm [n], weights [n, n_iso]) as CUDA tensors; T, P_pa, PL_km [n], MF_VAL [n, n_mol]."""
+        torch = _torch()
+        dev = self.device
+        T = to_device(T, dev).reshape(-1)
+        n = T.numel()
+        P = to_device(P_pa, dev).reshape(n)
+        PL = to_device(PL_km, dev).reshape(n)
+        MF = to_device(MF_VAL, dev).reshape(n, -1)
+        ids = np.ascontiguousarray(np.asarray(MF_ID).ravel().astype(np.int32))
+        p_atm = torch.empty(n, dtype=torch.float64, device=dev)
+        w = torch.empty((n, self.n_iso), dtype=torch.float64, device=dev)
+        _lib.call("rtx_layer_weights", self.handle.h, n, _ptr(T), _ptr(P), _ptr(PL), _ptr(MF), ids.size, _hptr(ids),
+                  _ptr(p_atm), _ptr(w), _stream(dev))
+        return p_atm, w
+
+    def tud_from_lines(self, T, P_pa, PL_km, MF_VAL, MF_ID, grid, Z, altitudes, mu, n_angle, return_od=False,
+                       x_air=1.0, x_self=0.0, wing_abs=0.0, wing_hw=50.0, s_threshold=0.0, flags=0):
+        """rtx_tud_from_lines: T, P_pa, PL_km [n_atm, nL], MF_VAL [n_atm, nL, n_mol] -> (tau, lu, ld) CUDA tensors of
+        shapes [n_atm, nx, n_alt, n_mu], same, [n_atm, nx]."""
+        torch = _torch()
+        dev = self.device
+        T = to_device(T, dev)
+        if T.dim() == 1:
+            T = T.unsqueeze(0)
+        n_atm, nL = T.shape
+        P = to_device(np.broadcast_to(np.asarray(P_pa, dtype=float), (n_atm, nL)) if not isinstance(P_pa, torch.Tensor) else P_pa, dev).reshape(n_atm, nL)
+        PL = to_device(np.broadcast_to(np.asarray(PL_km, dtype=float), (n_atm, nL)) if not isinstance(PL_km, torch.Tensor) else PL_km, dev).reshape(n_atm, nL)
+        MF = to_device(MF_VAL, dev).reshape(n_atm, nL, -1)
+        ids = np.ascontiguousarray(np.asarray(MF_ID).ravel().astype(np.int32))
+        grid = to_device(grid, dev).reshape(-1)
+        nx = grid.numel()
+        Z = np.ascontiguousarray(np.asarray(Z, dtype=np.float64).ravel())
+        alt = np.ascontiguousarray(np.asarray(altitudes, dtype=np.float64).ravel())
+        mu = np.ascontiguousarray(np.asarray(mu, dtype=np.float64).ravel())
+        tau = torch.empty((n_atm, nx, alt.size, mu.size), dtype=torch.float64, device=dev)
+        lu = torch.empty_like(tau)
+        ld = torch.empty((n_atm, nx), dtype=torch.float64, device=dev)
+        _lib.call("rtx_tud_from_lines", self.handle.h, n_atm, nL, _ptr(T), _ptr(P), _ptr(PL), _ptr(MF), ids.size, _hptr(ids),
+                  float(x_air), float(x_self), float(wing_abs), float(wing_hw), float(s_threshold), int(flags), _ptr(grid), nx,
+                  _hptr(Z), _hptr(alt), alt.size, _hptr(mu), mu.size, int(n_angle), int(bool(return_od)), _ptr(tau), _ptr(lu),
+                  _ptr(ld), _stream(dev))
+        return tau, lu, ld
+
+
+def mako_bands(mode, xmin, xmax, res_factor=None, fwhm_sf=1.0, shift=0.0, scale=1.0):
+    """rtx_mako_bands (host only): (X_out, centres, widths) of the triangle (mode 0) or Gaussian (mode 1) MAKO bands."""
+    n = ctypes.c_int()
+    rf = float(res_factor) if res_factor else 0.0
+    _lib.call("rtx_mako_bands", int(mode), float(xmin), float(xmax), rf, float(fwhm_sf), float(shift), float(scale), 0,
+              None, None, None, ctypes.byref(n))
+    X, c, w = (np.empty(max(n.value, 0)) for _ in range(3))
+    if n.value:
+        _lib.call("rtx_mako_bands", int(mode), float(xmin), float(xmax), rf, float(fwhm_sf), float(shift), float(scale),
+                  n.value, _hptr(X), _hptr(c), _hptr(w), ctypes.byref(n))
+    return X, c, w
 
 
 # --------------------------------------------------------------------------------------------- line-less ops

@@ -312,10 +312,11 @@ def compute_TUD_batch(Xmin, Xmax, Ts, MFs_VAL, opts=options, atm_chunk=None, ils
     n_atm, nL = Ts.shape
     Z_s = np.array([opts["Altitudes"]]).ravel()
     mu_s = np.array([1.0 / np.cos(opts["theta_r"])]).ravel()
-    X_ = make_spectral_axis(Xmin, Xmax, opts["DVOUT"])
+    X_, grid = _device_axis(Xmin, Xmax, opts["DVOUT"], db.device)
+    if X_ is None:
+        X_ = make_spectral_axis(Xmin, Xmax, opts["DVOUT"])
     nX = X_.size
     db.check_temperatures(Ts)
-    grid = engine.to_device(X_, db.device)
     if atm_chunk is None:
         atm_chunk = max(1, min(max(n_atm, 1), int(4e9 // (8 * nL * nX))))   # <= 4 GB of optical depth at a time
     atm_chunk = min(int(atm_chunk), 32768)                                  # rtx_tud: n_atm <= 65535 per launch
@@ -328,16 +329,15 @@ def compute_TUD_batch(Xmin, Xmax, Ts, MFs_VAL, opts=options, atm_chunk=None, ils
         nout = nX if band is None else band[0].size
         z = torch.zeros((0, nout, Z_s.size, mu_s.size), dtype=torch.float64, device=db.device)
         return (band[0] if band is not None else X_), z, z.clone(), torch.zeros((0, nout), dtype=torch.float64, device=db.device)
-    od_buf = torch.empty((atm_chunk * nL, nX), dtype=torch.float64, device=db.device)
+    Pb = np.ascontiguousarray(np.broadcast_to(P, (n_atm, nL)))
+    PLb = np.ascontiguousarray(np.broadcast_to(PL, (n_atm, nL)))
     for a0 in range(0, n_atm, atm_chunk):
         a1 = min(n_atm, a0 + atm_chunk)
         na = a1 - a0
-        p, w = layer_weights(db, Ts[a0:a1], P[None, :], PL[None, :], MF[a0:a1], opts["MFs_ID"])
-        pb = np.broadcast_to(p, (na, nL))
-        od = db.voigt_sum(Ts[a0:a1].reshape(-1), np.ascontiguousarray(pb).reshape(-1), w.reshape(na * nL, -1), grid,
-                          out=od_buf[: na * nL], **vs)
-        tau, lu, ld = engine.tud(od.view(na, nL, nX), Ts[a0:a1], grid, Z, Z_s, mu_s, opts["N_angle"],
-                                 opts["returnOD"])
+        # column amounts, Voigt sums and layer integration back to back inside the library (rtx_tud_from_lines); the
+        # optical depth of the chunk lives in the handle's scratch
+        tau, lu, ld = db.tud_from_lines(Ts[a0:a1], Pb[a0:a1], PLb[a0:a1], MF[a0:a1], opts["MFs_ID"], grid, Z, Z_s, mu_s,
+                                        opts["N_angle"], opts["returnOD"], **vs)
         if band is not None:
             mode = 0 if ils == "triangle" else 1
             na_, nx_, nal, nmu = tau.shape
@@ -518,24 +518,14 @@ def _mako_um():
 
 
 def _mako_bands(X, resFactor, fwhm_sf, shift, scale):
-    """Band centres / triangle half-bases exactly as radiative_transfer.py:1226-1241 derives them."""
-    X_out = _mako_um()
-    if resFactor is not None:
-        _x0 = np.linspace(0, 1, len(X_out))
-        _x1 = np.linspace(0, 1, int(len(X_out) * resFactor))
-        X_out = np.interp(_x1, _x0, X_out)
-    X_out = np.sort(10000.0 / X_out)
-    xmin, xmax = float(np.min(X)), float(np.max(X))
-    X_out = X_out[(X_out > xmin) & (X_out < xmax)]
-    if X_out.size == 0:
-        return X_out, X_out, X_out
-    sigma_out = fwhm_sf * np.abs(np.gradient(X_out)) * 1.6 if X_out.size > 1 else np.full(1, np.nan)
-    return X_out, scale * X_out + shift, sigma_out
+    """Band centres / triangle half-bases exactly as radiative_transfer.py:1226-1241 derives them (rtx_mako_bands)."""
+    X = np.asarray(X)
+    return engine.mako_bands(0, float(np.min(X)), float(np.max(X)), resFactor, fwhm_sf, shift, scale)
 
 
 def _mako_bands_gauss():
-    X_out = np.sort(10000.0 / _mako_um())               # ILS_MAKO.py:20-21
-    return X_out, X_out, np.abs(np.gradient(X_out))
+    """ILS_MAKO.py:20-22: all 128 bands, sigma = |gradient| (rtx_mako_bands, mode 1)."""
+    return engine.mako_bands(1, 0.0, 0.0)
 
 
 def _ils(mode, X, Y, bands, returnX):

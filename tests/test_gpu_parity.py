@@ -873,3 +873,52 @@ def test_c_abi_from_plain_c(mods, tmp_path):
     grid = 999.0 + 2.0 * np.arange(20001) / 20000.0
     _, ref = port.absorption_coefficient_voigt(cols, T=296.0, p=1.0, OmegaGrid=grid, Components=[(1, 1, port.tables()["iso_abundance"][port.tables()["index"][(1, 1)]])])
     assert abs(peaks[0] / ref.max() - 1.0) < 1e-5, (peaks[0], ref.max())       # the example prints 7 digits
+
+
+def test_tud_from_plain_c(mods, tmp_path):
+    """examples/tud_from_c.c: the whole path -- line table + atmosphere table in, (tau, Lu, Ld) out through
+    rtx_tud_from_lines, then rtx_mako_bands + rtx_ils_apply -- from plain C, compared with the CPU oracle on the same
+    inputs (the example's synthetic partition functions are handed to the oracle, which interpolates them with the
+    reference's own AtoB routine)."""
+    import subprocess
+    from test_host_logic import _build_c_example
+    port = mods["port"]
+    exe = _build_c_example(tmp_path, "tud_from_c")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    tud = np.array([[float(x) for x in ln.split()[1:]] for ln in r.stdout.splitlines() if ln.startswith("TUD ")])
+    bands = np.array([[float(x) for x in ln.split()[1:]] for ln in r.stdout.splitlines() if ln.startswith("BAND ")])
+    assert tud.shape[0] >= 7 and bands.shape[0] >= 4
+    # the same inputs for the oracle
+    i = np.arange(40)
+    cols = {1: {}, 2: {}}
+    full = dict(nu=700.0 + 17.5 * i + 3.0 * np.sin(1.7 * i), sw=1e-20 * (1.0 + 0.5 * np.cos(0.9 * i)), elower=100.0 + 60.0 * i,
+                gamma_air=0.05 + 0.03 * np.sin(0.3 * i) ** 2, n_air=0.5 + 0.2 * np.cos(0.5 * i) ** 2, delta_air=-0.002 + 0.0001 * i)
+    for m in (1, 2):
+        sel = (i % 2) == (m - 1)
+        cols[m] = {k: v[sel] for k, v in full.items()}
+        cols[m]["molec_id"] = np.full(sel.sum(), m); cols[m]["local_iso_id"] = np.full(sel.sum(), 1)
+    tipsT = 70.0 + (3000.0 - 70.0) * np.arange(119) / 118
+    qtab = {1: 170.0 * (tipsT / 296.0) ** 1.5, 2: 280.0 * (tipsT / 296.0)}
+    t = port.tables()
+    saved = (port.tips_q, t["iso_mass"].copy(), t["iso_abundance"].copy())
+    try:
+        port.tips_q = lambda M, I, T: port._lagrange(T, tipsT, qtab[M], 119)
+        t["iso_mass"][t["index"][(1, 1)]] = 18.010565; t["iso_mass"][t["index"][(2, 1)]] = 43.98983
+        t["iso_abundance"][t["index"][(1, 1)]] = 1.0; t["iso_abundance"][t["index"][(2, 1)]] = 1.0
+        Z = np.array([0.5, 1.5, 3.0, 6.0, 12.0, 25.0]); T = np.array([290.0, 283.0, 272.0, 252.0, 217.0, 222.0])
+        P = np.array([95000.0, 84000.0, 70000.0, 47000.0, 19000.0, 2500.0]); PL = np.array([1.0, 1.0, 2.0, 4.0, 8.0, 18.0])
+        MF = np.stack([9000.0 / (1 + np.arange(6) ** 2), np.full(6, 400.0), np.full(6, 2.0e5)], axis=1)
+        grid = 700.0 + (1400.0 - 700.0) * np.arange(14000) / 13999
+        OD = np.stack([port.layer_od(cols, grid, T[l], P[l], PL[l], MF[l], np.array([1, 2, 7])) for l in range(6)], axis=1)
+        tau, Lu, Ld = port.tud_from_od(grid, OD, Z, T)
+        Xo, R = port.ils_mako_triangle(grid, np.stack([tau, Lu, Ld], axis=1))
+    finally:
+        port.tips_q = saved[0]; t["iso_mass"][:] = saved[1]; t["iso_abundance"][:] = saved[2]
+    idx = tud[:, 0].astype(int)
+    assert np.array_equal(tud[:, 1], grid[idx])
+    for col, ref, name in ((2, tau, "tau"), (3, Lu, "Lu"), (4, Ld, "Ld")):
+        assert_parity(tud[:, col], ref[idx], RTOL, FLOOR, "plain C " + name)
+    b = bands[:, 0].astype(int)
+    assert np.array_equal(bands[:, 1], Xo[b])
+    assert_parity(bands[:, 2:5], R[b], RTOL, FLOOR, "plain C MAKO bands")

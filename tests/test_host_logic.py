@@ -190,13 +190,13 @@ def test_hapi_spectrum_helpers_golden():
         np.testing.assert_allclose(y, g[key], rtol=1e-14, atol=0)
 
 
-def _build_c_example(tmp_path):
+def _build_c_example(tmp_path, name="voigt_from_c"):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     libdir = os.path.join(root, "radtxfr_b200")
-    exe = str(tmp_path / "voigt_from_c")
-    subprocess.run(["gcc", "-std=c11", "-Wall", "-I", os.path.join(root, "include"),
-                    os.path.join(root, "examples", "voigt_from_c.c"), "-L", libdir, "-lradtxfr_b200",
+    exe = str(tmp_path / name)
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", name + ".c"), "-L", libdir, "-lradtxfr_b200",
                     "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
     return exe
 
@@ -208,10 +208,31 @@ def test_c_abi_from_plain_c_without_gpu(tmp_path):
     import torch
     if torch.cuda.is_available():
         pytest.skip("covered by the GPU test")
-    exe = _build_c_example(tmp_path)
-    r = subprocess.run([exe], capture_output=True, text=True)
-    assert r.returncode == 77, (r.returncode, r.stdout, r.stderr)
-    assert "no CPU fallback" in r.stdout
+    for name in ("voigt_from_c", "tud_from_c"):
+        exe = _build_c_example(tmp_path, name)
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 77, (name, r.returncode, r.stdout, r.stderr)
+        assert "no CPU fallback" in r.stdout
+
+
+def test_mako_bands_c_abi_matches_reference_derivation():
+    """rtx_mako_bands (host only, no GPU needed) against the reference's derivation restated in the oracle
+    (radiative_transfer.py:1226-1241, ILS_MAKO.py:20-22): band axis bit-identical, incl. resFactor, clip, empty result."""
+    from oracle import port
+    from radtxfr_b200 import engine
+    X = np.linspace(700.0, 1400.0, 701)
+    for rf, fw, sh, sc in ((None, 1.0, 0.0, 1.0), (2, 0.8, 0.3, 1.001), (0.5, 1.3, -0.2, 0.999)):
+        Xo, c, w = engine.mako_bands(0, X.min(), X.max(), rf, fw, sh, sc)
+        ref = port.mako_axis(X, rf, clip=True)
+        assert np.array_equal(Xo, ref) and np.array_equal(c, sc * ref + sh)
+        assert np.array_equal(w, fw * np.abs(np.gradient(ref)) * 1.6)
+    Xc = np.linspace(900.0, 1000.0, 11)
+    Xo, c, w = engine.mako_bands(0, 900.0, 1000.0)
+    assert np.array_equal(Xo, port.mako_axis(Xc, None, clip=True)) and 0 < Xo.size < 128
+    assert engine.mako_bands(0, 10.0, 20.0)[0].size == 0
+    Xg, cg, wg = engine.mako_bands(1, 0.0, 0.0)
+    ref = port.mako_axis(X, None, clip=False)
+    assert np.array_equal(Xg, ref) and np.array_equal(cg, ref) and np.array_equal(wg, np.abs(np.gradient(ref)))
 
 
 def test_flag_literals_match_header():

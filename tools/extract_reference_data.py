@@ -65,3 +65,17 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def write_mako_include():
+    """csrc/mako_table.inc: the MAKO band centres as a C array for rtx_mako_bands (same values as the npz)."""
+    z = np.load(os.path.join(os.path.dirname(HERE), "radtxfr_b200", "data", "spectro_tables.npz"))
+    m = z["mako_um"]
+    lines = ["// MAKO band centres in micrometres: the 128 literals of radiative_transfer.py:1092-1223 (a data table of the instrument),",
+             "// written by tools/extract_reference_data.py from radtxfr_b200/data/spectro_tables.npz.  Do not edit by hand.",
+             "static const double RTX_MAKO_UM[128] = {"]
+    for i in range(0, 128, 4):
+        lines.append("    " + ", ".join(repr(float(v)) for v in m[i:i + 4]) + ",")
+    lines.append("};")
+    with open(os.path.join(os.path.dirname(HERE), "radtxfr_b200", "csrc", "mako_table.inc"), "w") as f:
+        f.write("\n".join(lines) + "\n")
