@@ -80,6 +80,37 @@ def generate_LWIR_TUD(T, H2O, O3, CO2, Xmin=690, Xmax=1410, DV=0.0005, DV_out=0.
     return X_out, np.concatenate(ODs, axis=2), np.concatenate(Las, axis=2), np.concatenate(Lds, axis=1)
 
 
+def generate_LWIR_TUD_MAKO(X_HI, tau_HI, La_HI, Ld_HI, Ts):
+    """The MAKO-resolution atmosphere database of Generate_LWIR_TUD_MAKO.py:34-52: the Gaussian MAKO line shape
+    (ILS_MAKO.py:2-35) applied to the high-resolution tau / La / Ld [nX, nA] -- one device call on the stacked
+    spectra instead of three per-spectrum Python loops --, atmospheres ordered by band-mean transmittance, bands by
+    wavenumber.  Returns numpy arrays X [128], tau, La, Ld [128, nA], Ts [nA]."""
+    torch = engine._torch()
+    tau_HI, La_HI, Ld_HI = (np.asarray(a, dtype=float) for a in (tau_HI, La_HI, Ld_HI))
+    nA = tau_HI.shape[1]
+    bands = rt._mako_bands_gauss()
+    dev = engine.resolve_device(None)
+    Y = torch.cat([engine.to_device(a, dev) for a in (tau_HI, La_HI, Ld_HI)], dim=1).contiguous()      # [nX, 3 nA]
+    R = engine.ils_apply(1, np.asarray(X_HI, dtype=float), Y, bands[1], bands[2]).cpu().numpy()
+    X = bands[0]
+    tau, La, Ld = R[:, :nA], R[:, nA:2 * nA], R[:, 2 * nA:]
+    ixSrt = np.argsort(np.mean(tau, axis=0))                              # Generate_LWIR_TUD_MAKO.py:40-44
+    tau, La, Ld, Ts = tau[:, ixSrt], La[:, ixSrt], Ld[:, ixSrt], np.asarray(Ts)[ixSrt]
+    ixSrt = np.argsort(X)                                                 # :46-50
+    return X[ixSrt], tau[ixSrt, :], La[ixSrt, :], Ld[ixSrt, :], Ts
+
+
+def compute_LWIR_apparent_radiance_sweep(X, emis, Ts, tau, La, Ld, dT=None):
+    """The apparent-radiance data set of Compute_LWIR_Apparent_Radiance.py:9-26: every input cast to float32,
+    surface-temperature offsets dT = arange(-10, 10.5, 0.5), L [nX, nE, nA, nT] float32 from the float32-output kernel
+    (half the bytes of this write-bound step) and the surface temperatures T = Ts[:, None] + dT[None, :]."""
+    f32 = [np.asarray(a).astype(np.float32) for a in (X, emis, Ts, tau, La, Ld)]
+    dT = np.arange(-10, 10.5, 0.5).astype(np.float32) if dT is None else np.asarray(dT).astype(np.float32)
+    L = rt.compute_LWIR_apparent_radiance(*f32, dT)
+    T = f32[2][:, np.newaxis] + dT[np.newaxis, :]
+    return L, T
+
+
 # Dataset attributes of the reference's HDF5 product (Generate_LWIR_TUD.py:157-221): units / name / info / label
 TUD_DATASET_ATTRS = {
     "X": ("cm^{-1}", "Wavenumbers", "Spectral axis for tau, La, Ld", r"$\tilde{\nu} \,\, \left[\si{cm^{-1}} \right]$"),

@@ -922,3 +922,28 @@ def test_tud_from_plain_c(mods, tmp_path):
     b = bands[:, 0].astype(int)
     assert np.array_equal(bands[:, 1], Xo[b])
     assert_parity(bands[:, 2:5], R[b], RTOL, FLOOR, "plain C MAKO bands")
+
+
+def test_mako_database_and_apparent_radiance_flows(mods):
+    """The two production flows downstream of the TUD sweep: Generate_LWIR_TUD_MAKO.py:34-52 (Gaussian MAKO line shape on
+    tau / La / Ld, atmospheres sorted by band-mean transmittance) and Compute_LWIR_Apparent_Radiance.py:9-26 (float32
+    sweep over 41 surface-temperature offsets), against the oracle's restatement of the same steps."""
+    from radtxfr_b200 import drivers
+    port = mods["port"]
+    rng = np.random.default_rng(31)
+    X = np.linspace(700.0, 1400.0, 3501)
+    nA = 23
+    tau = np.clip(np.cumsum(rng.normal(0, 0.01, (X.size, nA)), axis=0) + rng.uniform(0.3, 0.9, nA), 0.0, 1.0)
+    La = rng.uniform(0, 300, (X.size, nA)); Ld = rng.uniform(0, 600, (X.size, nA)); Ts = rng.uniform(270, 310, nA)
+    Xo, t, a, d, Tso = drivers.generate_LWIR_TUD_MAKO(X, tau, La, Ld, Ts)
+    Xr, tr = port.ils_mako_gauss(X, tau); _, ar = port.ils_mako_gauss(X, La); _, dr = port.ils_mako_gauss(X, Ld)
+    ix = np.argsort(np.mean(tr, axis=0)); ixx = np.argsort(Xr)
+    assert np.array_equal(Xo, Xr[ixx]) and np.array_equal(Tso, Ts[ix])
+    for got, ref, name in ((t, tr, "tau"), (a, ar, "La"), (d, dr, "Ld")):
+        assert_parity(got, ref[:, ix][ixx, :], RTOL, FLOOR, "MAKO database " + name)
+    emis = mods["syn"].synthetic_emissivities(5, 7, Xo)
+    L, T = drivers.compute_LWIR_apparent_radiance_sweep(Xo, emis, Tso, t, a, d)
+    assert L.dtype == np.float32 and L.shape == (Xo.size, 7, nA, 41) and T.shape == (nA, 41) and T.dtype == np.float32
+    f32 = [np.asarray(v).astype(np.float32).astype(float) for v in (Xo, emis, Tso, t, a, d)]
+    ref = port.apparent_radiance(*f32, dT=np.arange(-10, 10.5, 0.5).astype(np.float32).astype(float))
+    assert_parity(L.astype(float), ref, 1e-5, 1e-8, "float32 apparent-radiance sweep")
