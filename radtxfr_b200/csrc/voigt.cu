@@ -139,12 +139,8 @@ __device__ __forceinline__ LineState line_state(const VoigtParams& P, int64_t li
   LineState L;
   const double nu = P.nu[li];
   const int iso = P.iso[li];
-  const double wgt = P.weight[(int64_t)s * P.n_iso + iso];
-  // S(T) = sw*Qref/Q * ch/zn, EnvironmentDependency_Intensity (misc/hapi.py:10169-10175); zn is folded
-  // into s0 at ingest.
-  const double ch = exp(-RTX_C2_HAPI * P.elower[li] / T) * (1.0 - exp(-RTX_C2_HAPI * nu / T));
-  const double S = P.s0[li] * P.st_q[(int64_t)s * P.n_iso + iso] * ch;
-  L.keep = !(S < P.s_thr) && (wgt != 0.0);                       // :11066, :11082
+  L.keep = true;
+  L.amp = 0.0;                                                   // set by line_strength() once the line is known to reach
   L.gamD = P.st_d[(int64_t)s * P.n_iso + iso] * nu;              // :11087 (unshifted centre)
   // Gamma0 and Shift0 over the diluents, :11090-11128
   double g0 = 0.0, sh = 0.0;
@@ -188,8 +184,18 @@ __device__ __forceinline__ LineState line_state(const VoigtParams& P, int64_t li
   L.W = P.doppler ? fmax(P.wing_abs, P.wing_hw * L.gamD)         // :11540
       : P.lorentz ? fmax(P.wing_abs, P.wing_hw * g0)                  // misc/hapi.py:11375 (Lorentz driver)
                   : fmax(fmax(P.wing_abs, P.wing_hw * g0), P.wing_hw * L.gamD);  // :11131
-  L.amp = wgt * S;
   return L;
+}
+// S(T) = sw*Qref/Q * ch/zn, EnvironmentDependency_Intensity (misc/hapi.py:10169-10175; zn is folded into s0 at ingest),
+// times the caller's weight; and the reference's filters (:11066 component / weight, :11082 intensity threshold).
+// Kept apart from line_state so that the two exponentials are spent only on lines whose window reaches the tile.
+__device__ __forceinline__ void line_strength(const VoigtParams& P, int64_t li, int s, double T, LineState& L) {
+  const int iso = P.iso[li];
+  const double wgt = P.weight[(int64_t)s * P.n_iso + iso];
+  const double ch = exp(-RTX_C2_HAPI * P.elower[li] / T) * (1.0 - exp(-RTX_C2_HAPI * L.nu / T));
+  const double S = P.s0[li] * P.st_q[(int64_t)s * P.n_iso + iso] * ch;
+  L.keep = !(S < P.s_thr) && (wgt != 0.0);
+  L.amp = wgt * S;
 }
 
 // |x|+y < 15 exactly as hum1_wei tests it (misc/hapi.py:9841) on x = -((sg0-sg)*cte), y = Gam0*cte
@@ -406,27 +412,25 @@ static_assert(sizeof(WideRec32) <= sizeof(WideRec), "WideRec32 must fit a WideRe
 // inside (test-free path), bit 16+q = it covers the slice from far away (far-field nodes)
 // With core_ok a covered slice is test-free even when the core lies inside it: pass 1 then evaluates the closed form
 // on the core points too and pass 2 adds (series - closed form) there.
-__device__ __forceinline__ unsigned slice_masks(int lo, int hi, int clo, int chi, int slice, bool core_ok, bool far_ok,
-                                                double sg0, const double* __restrict__ s_grid) {
-  unsigned m = 0;
+// s_far[q] / s_far[8 + q]: a line centre at or below / at or above these values is "far" from slice q (set per tile).
+__device__ __forceinline__ unsigned range_mask(int a, int b) {        // bits a..b inclusive, empty when a > b
+  return a > b ? 0u : (((2u << b) - 1u) & ~((1u << a) - 1u));
+}
+template <int SLICE>
+__device__ __forceinline__ unsigned slice_masks(int lo, int hi, int clo, int chi, bool core_ok, bool far_ok, double sg0,
+                                                const double* __restrict__ s_far) {
+  constexpr int NQ = NT / 32;
+  const unsigned touch = range_mask(lo / SLICE, (hi - 1) / SLICE);                      // hi > lo
+  const unsigned cover = range_mask((lo + SLICE - 1) / SLICE, hi / SLICE - 1) & ((1u << NQ) - 1u);
+  const unsigned core = chi > clo ? range_mask(clo / SLICE, (chi - 1) / SLICE) : 0u;
+  unsigned far = 0;
+  if (far_ok && (cover & ~core)) {
 #pragma unroll
-  for (int q = 0; q < NT / 32; ++q) {
-    const int a = q * slice, b = a + slice;
-    const bool touch = (hi > a) && (lo < b);
-    const bool cover = (lo <= a) && (hi >= b);
-    const bool nocore = (chi <= clo) || (chi <= a) || (clo >= b);
-    bool far = false;
-    if (far_ok && cover && nocore) {
-      const double gf = s_grid[a], gl = s_grid[b - 1];
-      const double D = RTX_FAR_FRAC * (gl - gf);
-      far = (sg0 <= gf - D) || (sg0 >= gl + D);
-    }
-    const bool full = cover && !far && (core_ok || nocore);
-    m |= (touch ? 1u : 0u) << q;
-    m |= (full ? 1u : 0u) << (8 + q);
-    m |= (far ? 1u : 0u) << (16 + q);
+    for (int q = 0; q < NQ; ++q) far |= ((sg0 <= s_far[q] || sg0 >= s_far[NQ + q]) ? 1u : 0u) << q;
+    far &= cover & ~core;
   }
-  return m;
+  const unsigned full = cover & ~far & (core_ok ? ~0u : ~core);
+  return (touch & ((1u << NQ) - 1u)) | (full << 8) | (far << 16);
 }
 // per-line record: [s, e) is evaluated by pass 2, of which [clo, chi) is the Weideman core (empty: clo == chi)
 // It is also the pass-1 record of the FP64 kernels: [lo, hi) is the line's window, [clo, chi) its Weideman core.
@@ -666,6 +670,17 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
     }
   }
 
+  // far-field reach of every slice: a line centred at or below s_far[q] (left of the slice) or at or above
+  // s_far[8 + q] (right of it) is at least RTX_FAR_FRAC slice widths away from every point of slice q
+  __shared__ double s_far[2 * (NT / 32)];
+  if (tid < NT / 32) {
+    const double gf = s_grid[tid * (32 * K)], gl = s_grid[tid * (32 * K) + 32 * K - 1];
+    const double D = RTX_FAR_FRAC * (gl - gf);
+    s_far[tid] = gf - D;
+    s_far[NT / 32 + tid] = gl + D;
+  }
+  __syncthreads();
+
   double acc[K];
   double w[K];
   float w32[K], w32l[K], a32[K];
@@ -719,11 +734,14 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       sr.sub = 0;
       double h_keep = 0.0;
       if (li < last) {
-        const LineState L = line_state<EXT>(P, li, s, T, p, lnr);
-        if (L.keep) {
+        LineState L = line_state<EXT>(P, li, s, T, p, lnr);
+        {
           const int lo = count_le(s_grid, ts, L.nu - L.W);                // bisect(Omegas, nu-W), misc/hapi.py:11133
           const int hi = count_le(s_grid, ts, L.nu + L.W);                // bisect(Omegas, nu+W), misc/hapi.py:11134
-          if (hi > lo) {
+          // the bins are cut with a per-state bound on the wing, so a good part of the candidates does not reach the
+          // tile: their strength is never computed (blocks of 32 candidates are neighbours in nu, so whole warps skip)
+          if (hi > lo) line_strength(P, li, s, T, L);
+          if (hi > lo && L.keep) {
             // Lorentz profile Gam0/(pi*(Gam0^2+d^2)) (misc/hapi.py:10142-10150) = the closed form below with h = 0 and
             // no Weideman region
             const double cte = RTX_SQRT_LN2 / L.gamD;                      // misc/hapi.py:9900
@@ -831,7 +849,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
           w3.lo = sr.lo; w3.hi = sr.hi; w3.core_lo = sr.clo; w3.core_hi = sr.chi;
           *reinterpret_cast<WideRec32*>(&wide_b[k]) = w3;
         }
-        wm = slice_masks(sr.lo, sr.hi, sr.clo, sr.chi, 32 * K, sr.sub != 0, K >= 4 && P.far_ok != 0, sr.sg0, s_grid);   // K < 4: too few points per node to pay
+        wm = slice_masks<32 * K>(sr.lo, sr.hi, sr.clo, sr.chi, sr.sub != 0, K >= 4 && P.far_ok != 0, sr.sg0, s_far);   // K < 4: too few points per node to pay
       }
       if (is_wide || has_seg) seg_b[k] = sr;
       if (has_seg) {
@@ -1156,7 +1174,8 @@ __global__ void count_kernel(const VoigtParams P, unsigned long long* __restrict
     const int s = (int)(i / P.n_lines);
     const int64_t li = i % P.n_lines;
     const double T = P.T[s], p = P.p[s];
-    const LineState L = line_state<true>(P, li, s, T, p, log(RTX_TREF / T));
+    LineState L = line_state<true>(P, li, s, T, p, log(RTX_TREF / T));
+    line_strength(P, li, s, T, L);
     if (L.keep) {
       const int64_t lo = bisect_right_dev64(P.grid, P.nx, L.nu - L.W);
       const int64_t hi = bisect_right_dev64(P.grid, P.nx, L.nu + L.W);
