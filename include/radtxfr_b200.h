@@ -137,9 +137,9 @@ int rtx_tape3_read(const char* path, double vmin, double vmax, int64_t capacity,
                                  * SD_d p gamma_d is non-zero take the quadratic speed-dependent profile (pcqsdhc PART2-4,
                                  * misc/hapi.py:9923-10020); the rest is the Voigt driver */
 #define RTX_VOIGT_TILE_SHIFT 8 /* bits 8..11: force 256*K grid points per CTA, K in {1,2,4,8} (0 = automatic).
-                                * The automatic choice between K = 8 and K = 4 reads 8 bytes back from the device
-                                * (one stream synchronisation after a tiny kernel); force K to keep the call fully
-                                * asynchronous, e.g. under CUDA-graph capture, or to pin the summation order. */
+                                * The automatic choice between K = 8 and K = 4 is made on the device (both grids are
+                                * launched, the one not chosen retires at once), so the call never synchronises;
+                                * force K to pin the summation order (e.g. for bit-identical sharded results). */
 int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, const double* p_dev,
                   const double* weight_dev, double x_air, double x_self, double wing_abs, double wing_hw,
                   double s_threshold, const double* grid_dev, int64_t nx, double* out_dev, int flags,
@@ -289,7 +289,8 @@ int rtx_measure_fp64_peak(rtx_handle* h, double* flops_per_s);
 int rtx_weideman_coeffs(double* out24);
 /* Number of kernels this library has launched on this handle since creation. */
 int rtx_launch_count(rtx_handle* h, uint64_t* n);
-/* Tile size the last rtx_voigt_sum on this handle used: K = grid points per CTA / 256 (0 before the first call). */
+/* Tile size the last rtx_voigt_sum on this handle used: K = grid points per CTA / 256 (0 before the first call).  When
+ * the size was chosen on the device this reads 8 bytes back and synchronises the stream of that call. */
 int rtx_voigt_last_tile(rtx_handle* h, int* K);
 
 #ifdef __cplusplus

@@ -108,6 +108,14 @@ extern "C" int rtx_stream_sync(rtx_handle* h, void* stream) {
 }
 extern "C" int rtx_voigt_last_tile(rtx_handle* h, int* K) {
   RTX_REQUIRE(h && K, "rtx_voigt_last_tile: null pointer");
+  if (h->last_K < 0 && h->d_last_stat) {          // chosen on the device: read the statistic back (synchronises)
+    DeviceGuard guard(h->device);
+    double v = 0.0;
+    RTX_CUDA(cudaMemcpyAsync(&v, h->d_last_stat, sizeof(double), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(h->last_stream)));
+    RTX_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(h->last_stream)));
+    h->last_K = v < 1200.0 ? 4 : 8;               // RTX_K4_WINDOW of csrc/voigt.cu
+    h->d_last_stat = nullptr;
+  }
   *K = h->last_K;
   return RTX_OK;
 }

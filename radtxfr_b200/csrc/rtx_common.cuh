@@ -56,7 +56,9 @@ struct rtx_handle {
   double* h_pin = nullptr;                             // 2 pinned doubles for small read-backs
   double* d_cheb = nullptr;                            // Chebyshev tables of the Voigt far-field blocks
   uint64_t launches = 0;
-  int last_K = 0;                                      // tile size of the last rtx_voigt_sum
+  int last_K = 0;                                      // tile size of the last rtx_voigt_sum (-1: chosen on the device)
+  const double* d_last_stat = nullptr;                 // window statistic that decided it
+  void* last_stream = nullptr;
   double x_extra[RTX_MAX_EXTRA_DILUENTS] = {};
   int32_t* d_iso_mol = nullptr;  double* d_iso_factor = nullptr;     // rtx_set_iso_molecules
   double* d_pipe = nullptr;  size_t pipe_cap = 0;                    // scratch of rtx_tud_from_lines (doubles)         // fractions of the extra broadening species (rtx_voigt_set_mix)

@@ -122,6 +122,7 @@ struct VoigtParams {
   double xx[RTX_MAX_EXTRA_DILUENTS];
   const double* cheb;   // [32] Chebyshev nodes cos(theta_k), then [32][32] node-values -> coefficients matrix [k][m]
   int far_ok;    // far-field blocks enabled
+  const double* sel;   // device-side tile-size choice: run only if (sel[0] < RTX_K4_WINDOW) == (K == 4); null = run
   int lorentz;   // PROFILE_LORENTZ instead of PROFILE_VOIGT: no Doppler width, wing = max(OmegaWing, HW*Gamma0)
   int doppler;   // PROFILE_DOPPLER (absorptionCoefficient_Doppler): 1 = with line shift, 2 = LineShift=False
 };
@@ -446,10 +447,14 @@ static_assert(sizeof(SegRec) == 80, "one 80-byte record per line");
 // Doppler factor sqrt(2kT ln2/(m c^2)) (misc/hapi.py:11085-11087), conservative wing bound.
 __device__ __forceinline__ double tips_lagrange(double aa, const double* __restrict__ A,
                                                 const double* __restrict__ B, int npt) {
-  int I = -1;
-  for (int c = 2; c <= npt; ++c)
-    if (A[c - 1] >= aa) { I = c; break; }
-  if (I < 0) return nan("");
+  // I = the first c in [2, npt] with A[c-1] >= aa (the reference scans linearly; the nodes ascend, so bisect)
+  int lo = 2, hi = npt + 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (A[mid - 1] >= aa) hi = mid; else lo = mid + 1;
+  }
+  if (lo > npt) return nan("");
+  const int I = lo;
   if (I < 3 || I == npt) {
     const int J = (I < 3 ? 3 : npt) - 1;
     const double a0 = A[J - 2], a1 = A[J - 1], a2 = A[J];
@@ -628,6 +633,9 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       s_mfar[NBUF][NBLK][NT / 32];
   __shared__ __align__(8) unsigned long long s_bar, s_full[2], s_empty[2];
 
+  // automatic tile size without a host round trip: the K = 8 and the K = 4 grid are both launched and the one the
+  // window statistic (window_stats_kernel) does not pick retires at once
+  if (P.sel != nullptr && ((P.sel[0] < RTX_K4_WINDOW) != (K == 4))) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x % P.n_tiles;
   const int s = blockIdx.x / P.n_tiles;
@@ -1272,6 +1280,7 @@ int fill_params(rtx_handle* h, VoigtParams& P, int n_states, const double* T, co
   P.use_tma = ((reinterpret_cast<uintptr_t>(grid) & 15u) == 0) ? 1 : 0;
   P.lorentz = 0;
   P.doppler = 0;
+  P.sel = nullptr;
   return RTX_OK;
 }
 
@@ -1337,31 +1346,41 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
     if (tiles * n_states >= 4LL * h->sm_count) { K = k; break; }
   }
   const int forced = (flags >> RTX_VOIGT_TILE_SHIFT) & 0xF;   // test hook: force the tile size
+  bool both = false;                                          // K = 8 and K = 4 grids, chosen on the device
   if (forced == 1 || forced == 2 || forced == 4 || forced == 8) {
     K = forced;
   } else if (K == 8) {
     // narrow windows (coarse grids, low pressures): smaller slices turn partial visits into test-free ones and
-    // four CTAs per SM hide the per-visit latency.  One 8-byte read-back decides; it waits only for state_prep.
-    if (!h->h_pin) RTX_CUDA(cudaMallocHost(&h->h_pin, 2 * sizeof(double)));
+    // four CTAs per SM hide the per-visit latency.  The eval-weighted mean window decides -- on the device: both grids
+    // are launched and the kernels of the size not chosen return at once, so the call never waits for the GPU.
     double* stat = st_wb + n_states;
     window_stats_kernel<<<1, 256, 0, st>>>(n_states, st_wb, grid_dev, nx, stat);
     RTX_CUDA(cudaGetLastError());
     h->launches++;
-    RTX_CUDA(cudaMemcpyAsync(h->h_pin, stat, sizeof(double), cudaMemcpyDeviceToHost, st));
-    RTX_CUDA(cudaStreamSynchronize(st));
-    if (h->h_pin[0] < RTX_K4_WINDOW) K = 4;
+    P.sel = stat;
+    both = true;
   }
-  h->last_K = K;
+  h->last_K = both ? -1 : K;
+  h->d_last_stat = both ? P.sel : nullptr;
+  h->last_stream = stream;
   const int tile_pts = K * NT;
   P.n_tiles = (int)((nx + tile_pts - 1) / tile_pts);
   const size_t nb = (size_t)P.n_tiles * n_states;
-  rc = ensure_scratch(h, h->state_cap, 2 * nb);
+  const int n_tiles4 = both ? (int)((nx + 4 * NT - 1) / (4 * NT)) : 0;
+  const size_t nb4 = (size_t)n_tiles4 * n_states;
+  rc = ensure_scratch(h, h->state_cap, 2 * (nb + nb4));
   if (rc) return rc;
   P.bins = h->d_bins;
   bin_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(n_states, P.n_tiles, tile_pts, grid_dev, nx, P.nu, P.n_lines,
                                                           st_wb, h->d_bins);
   RTX_CUDA(cudaGetLastError());
   h->launches++;
+  if (both) {
+    bin_kernel<<<(unsigned)((nb4 + 255) / 256), 256, 0, st>>>(n_states, n_tiles4, 4 * NT, grid_dev, nx, P.nu, P.n_lines,
+                                                             st_wb, h->d_bins + 2 * nb);
+    RTX_CUDA(cudaGetLastError());
+    h->launches++;
+  }
   // Chebyshev tables of the far-field blocks (once per handle): cos(theta_k) and the node-values -> coefficients matrix
   if (!h->d_cheb) {
     std::vector<double> tab(32 + 32 * 32);
@@ -1393,9 +1412,17 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
     case 2: rc = RTX_LAUNCH(2); break;
     default: rc = RTX_LAUNCH(1); break;
   }
-#undef RTX_LAUNCH
   if (rc) return rc;
   h->launches++;
+  if (both) {                                   // the K = 4 grid of the same call
+    P.n_tiles = n_tiles4;
+    P.bins = h->d_bins + 2 * nb;
+    K = 4;
+    rc = RTX_LAUNCH(4);
+    if (rc) return rc;
+    h->launches++;
+  }
+#undef RTX_LAUNCH
   return RTX_OK;
 }
 

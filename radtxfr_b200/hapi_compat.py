@@ -161,7 +161,9 @@ def absorptionCoefficient_Voigt(Components=None, SourceTables=None, partitionFun
         if as_tensor:
             Omegas = torch.sort(OmegaGrid.to(device=db.device, dtype=torch.float64).reshape(-1))[0]
         else:
-            Omegas = np.sort(np.asarray(OmegaGrid, dtype=np.float64))             # misc/hapi.py:10980
+            Omegas = np.array(OmegaGrid, dtype=np.float64).ravel()                # a copy, like the reference's sort
+            if Omegas.size > 1 and not np.all(Omegas[1:] >= Omegas[:-1]):
+                Omegas.sort()                                                     # misc/hapi.py:10980
     else:
         if OmegaRange is None:
             OmegaRange = (db.nu_min, db.nu_max)                                   # misc/hapi.py:10252-10263
