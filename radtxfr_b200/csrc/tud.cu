@@ -84,9 +84,12 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
       sec[a] = (a0 + a < P.n_angle) ? P.inv_cos[a0 + a] : 1.0;   // padding angles get weight 0 below
       secmax = fmax(secmax, sec[a]);
     }
+    const double ao_max = 708.0 / secmax;
     for (int j = P.n_down - 1; j >= 0; --j) {
-      const double ao = -od[(int64_t)j * P.nx];           // signed, like the reference's exp(-OD/cos th) (a continuum
-                                                          // hook may hand in negative optical depths)
+      // signed, like the reference's exp(-OD/cos th) (a continuum hook may hand in negative optical depths); bounded
+      // above once per layer so that the per-angle exponent stays below the overflow threshold of the scaling trick
+      // (matters only for optical depths below -708 cos(th_max), where the reference overflows as well)
+      const double ao = fmin(-od[(int64_t)j * P.nx], ao_max);
       const double B = planck_fast(c1X3, c2X, s_invT[j], s_exp2);
       // optically thin layer for every lane of the warp and every angle of the block (|x| <= 2^-9): the degree-5
       // Taylor polynomial is exact to < 1e-19 and needs no range reduction
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) 
       double xa[ANGLE_BLOCK], tt[ANGLE_BLOCK], r[ANGLE_BLOCK], pz[ANGLE_BLOCK];
 #pragma unroll
       for (int a = 0; a < ANGLE_BLOCK; ++a) {
-        xa[a] = fmin(fmax(ao * sec[a], -708.0), 708.0);                  // exp(-708) = 3e-308: nothing below matters
+        xa[a] = fmax(ao * sec[a], -708.0);                               // exp(-708) = 3e-308: nothing below matters
         tt[a] = fma(xa[a], c_exp[0], c_exp[1]);                          // 256/ln2; 1.5*2^52 puts k in the low word
       }
 #pragma unroll
