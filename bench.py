@@ -443,10 +443,11 @@ def gpu_arm(args):
         peak = db.handle.fp64_peak()
         achieved = flops / (ms_voigt * 1e-3)
         prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        traffic = None
+        traffic, ncu = None, {}
         if os.path.isfile(prof):
             try:
-                traffic = json.load(open(prof)).get("voigt_tile_kernel_dram_bytes_per_launch")
+                ncu = json.load(open(prof))
+                traffic = ncu.get("voigt_tile_kernel_dram_bytes_per_launch")
             except Exception:
                 traffic = None
         hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
@@ -476,6 +477,14 @@ def gpu_arm(args):
                          "peak_source": "measured in this run: dependent-free DFMA loop (rtx_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "flops_model": "16 flop per asymptote-branch eval, 200 per Weideman eval (SURVEY.md 8d)",
+                         "note": "achieved counts the reference's ALGORITHMIC flops (every (line, grid point) pair of its "
+                                 "windows); the kernel evaluates wing contributions at 32 Chebyshev nodes per 256-point slice "
+                                 "(far-field blocks, deviation < 1e-13) and so issues fewer operations than it is credited "
+                                 "with -- frac above 1 means faster than a perfect FP64 pipe could run the reference's "
+                                 "arithmetic.  The pipe-level view of the same kernel is in `issued`.",
+                         "issued": {"fp64_pipe_pct_of_peak": ncu.get("voigt_tile_kernel_fp64_pipe_pct"),
+                                    "issue_slots_active_pct": ncu.get("voigt_tile_kernel_issue_active_pct"),
+                                    "source": "profiles/roofline_traffic.json (ncu --set full of this command, one launch)"},
                          "hbm_view": {"voigt_tile_kernel": {"algorithmic_bytes": voigt_bytes,
                                                             "achieved_GBps": voigt_bytes / (ms_voigt / args.steps) / 1e6,
                                                             "frac_of_hbm_peak": voigt_bytes / (ms_voigt / args.steps) / 1e6 / hbm_peak},
@@ -494,7 +503,10 @@ def gpu_arm(args):
         line["roofline_tud"] = {"bound": "fp64", "kernel": "tud_kernel", "achieved": tud_flops / (ms_tud / args.steps * 1e-3) / 1e12,
                                 "peak": peak / 1e12, "unit": "TFLOP/s", "frac": tud_flops / (ms_tud / args.steps * 1e-3) / peak,
                                 "flops_model": "5.9e4 algorithmic flop per grid point: 2113 FP64 exp x 25 + 3 x 2046 "
-                                               "recurrence + 200 (SURVEY.md 8d)"}
+                                               "recurrence + 200 (SURVEY.md 8d)",
+                                "issued": {"fp64_pipe_pct_of_peak": ncu.get("tud_kernel_fp64_pipe_pct"),
+                                           "note": "the kernel's exp costs 10 FP64-pipe operations, not the 25 of the model, "
+                                                   "so the pipe is the honest denominator: see profiles/"}}
         if banded:
             line["multi_gpu_bit_identical"] = banded.pop("bit_identical")
             line["banded"] = banded

@@ -1,5 +1,5 @@
 """Run rtx_voigt_sum on one layer group of config 2 (for ncu captures of a single regime).
-    python tools/layer_group_run.py LO HI [reps]"""
+    python tools/layer_group_run.py LO HI [reps] [K]      (K pins the tile size: one grid launch instead of two)"""
 import os
 import sys
 
@@ -12,6 +12,7 @@ from radtxfr_b200 import engine, radiative_transfer as rt, synthetic as syn  # n
 
 lo, hi = int(sys.argv[1]), int(sys.argv[2])
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+K = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 atm = syn.standard_atmosphere()
 tabs = syn.config2_tables()
 db = engine.LineDB([tabs[m] for m in sorted(tabs)])
@@ -23,6 +24,6 @@ T = torch.from_numpy(atm["Ts"].copy()).cuda()[sl]
 pd = torch.from_numpy(np.ascontiguousarray(p)).cuda()[sl]
 wd = torch.from_numpy(w).cuda()[sl].contiguous()
 for _ in range(reps):
-    out = db.voigt_sum(T, pd, wd, grid)
+    out = db.voigt_sum(T, pd, wd, grid, flags=K << 8)
 torch.cuda.synchronize()
 print("ok", float(out.sum()))

@@ -57,11 +57,19 @@ if "app" in which:
         Ts = 280 + 30 * torch.rand(nA, dtype=torch.float64, device="cuda", generator=g)
         tau, La, Ld = (torch.rand((nx, nA), dtype=torch.float64, device="cuda", generator=g) for _ in range(3))
         dT = torch.linspace(-10, 10, nT, dtype=torch.float64, device="cuda")
-        for dt in (None, torch.float32):
-            L, ms = timeit(lambda: engine.apparent_radiance(X, emis, Ts, tau, La, Ld, dT=dT, out_dtype=dt))
+        from radtxfr_b200 import _lib
+        h = engine.default_handle(X.device)
+        for dt, fn in ((torch.float64, "rtx_apparent_radiance"), (torch.float32, "rtx_apparent_radiance_f32")):
+            # preallocated output, C-ABI entry called directly (a 4 GB allocation per call would be timed otherwise)
+            L = torch.empty((nx, nE, nA, nT), dtype=dt, device="cuda")
+            args = (h.h, engine._ptr(X), nx, engine._ptr(emis), nE, engine._ptr(Ts), nA, engine._ptr(tau), engine._ptr(La),
+                    engine._ptr(Ld), engine._ptr(dT), nT, engine._ptr(L), None, engine._stream(X.device))
+            f = getattr(_lib.lib(), fn)
+            _, ms = timeit(lambda: f(*args), reps=20)
             b = L.numel() * L.element_size()
             print("apparent radiance nE=%d nA=%d nT=%d %s: %.3f ms, %.0f GB/s written = %.2f of HBM (%.2f GB)"
                   % (nE, nA, nT, L.dtype, ms, b / ms / 1e6, b / ms / 1e6 / HBM, b / 1e9), flush=True)
+            del L
 if "hsi" in which:
     # config 4: 512 x 512 pixels x 128 bands, 16 atmospheres, 64 emissivities, two-material mixes
     rng = np.random.default_rng(3)

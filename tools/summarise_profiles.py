@@ -74,14 +74,15 @@ def kernel_summary(rep, tag, round_tag):
 
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    pre = sys.argv[2] if len(sys.argv) > 2 else ""            # file-name prefix inside gpurun_out/ (round 2: "r2_")
     os.makedirs(OUT, exist_ok=True)
     # launch list
-    rows = [r for r in csv.reader(open(os.path.join(GP, "launches.csv"))) if len(r) > 10]
+    rows = [r for r in csv.reader(open(os.path.join(GP, pre + "launches.csv"))) if len(r) > 10]
     hdr = rows[0]
     ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
     tot = {}
     out = ["# ncu --metrics gpu__time_duration.sum --clock-control none  (cold-cache, serialised: compare SHARES)",
-           "# command: python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e", "# id, kernel, ns"]
+           "# command: python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-banded", "# id, kernel, ns"]
     for r in rows[1:]:
         name = r[ik].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
         ns = float(r[iv].replace(",", ""))
@@ -92,15 +93,21 @@ def main():
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
         out.append("#   %-70s %10.3f ms %6.2f%%" % (k, v / 1e6, 100 * v / s))
     open(os.path.join(OUT, "%s_launches.csv" % tag), "w").write("\n".join(out) + "\n")
-    dv = kernel_summary(os.path.join(GP, "prof_voigt.ncu-rep"), "voigt_tile_kernel", tag)
-    dt = kernel_summary(os.path.join(GP, "prof_tud.ncu-rep"), "tud_kernel", tag)
+    dv = kernel_summary(os.path.join(GP, pre + "prof_voigt.ncu-rep"), "voigt_tile_kernel", tag)
+    dt = kernel_summary(os.path.join(GP, pre + "prof_tud.ncu-rep"), "tud_kernel", tag)
 
     def mb(d, k):
         return float(d[k].replace(",", ""))
     traffic = {"source": "%s ncu --set full, per launch" % tag,
                "voigt_tile_kernel_dram_bytes_per_launch": 1e6 * (mb(dv, "dram__bytes_read.sum") + mb(dv, "dram__bytes_write.sum")),
                "tud_kernel_dram_bytes_per_launch": 1e6 * (mb(dt, "dram__bytes_read.sum") + mb(dt, "dram__bytes_write.sum")),
-               "units_note": "ncu reports Mbyte for these launches"}
+               "units_note": "ncu reports Mbyte for these launches",
+               "voigt_tile_kernel_fp64_pipe_pct": mb(dv, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+               "voigt_tile_kernel_issue_active_pct": mb(dv, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "voigt_tile_kernel_ms_under_ncu": mb(dv, "gpu__time_duration.sum"),
+               "tud_kernel_fp64_pipe_pct": mb(dt, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+               "tud_kernel_issue_active_pct": mb(dt, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "tud_kernel_ms_under_ncu": mb(dt, "gpu__time_duration.sum")}
     json.dump(traffic, open(os.path.join(OUT, "roofline_traffic.json"), "w"), indent=1)
     print(open(os.path.join(OUT, "%s_launches.csv" % tag)).read()[-900:])
 
