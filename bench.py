@@ -202,7 +202,8 @@ def banded_leg(args, rank, world, dev):
     reps = 3
 
     def timed(fn):
-        fn()                                             # warm-up (workspaces, pinned staging)
+        for _ in range(4):                               # warm-up (workspaces, pinned staging, band-balance feedback)
+            fn()
         best_dev, best_wall = 1e30, 1e30
         for _ in range(reps):
             dist.barrier(); torch.cuda.synchronize()
@@ -217,6 +218,18 @@ def banded_leg(args, rank, world, dev):
         return out, best_dev, best_wall
 
     (X, tau_d, lu_d, ld_d), ms_dev, _ = timed(lambda: D.compute_TUD_banded(500.0, 6000.0, dict(opts), to_host=False, **kw))
+    # how well the bands are balanced: per-rank compute times (before the gather) of the last call, from the feedback
+    # records of compute_TUD_banded
+    fbs = [v for k, v in D._band_feedback.items() if k[2] == X.size]
+    bands = fbs[-1]["events"][2] if fbs else D.plan_bands(X.size, world)
+    own_ms = 0.0
+    if fbs:
+        e0, e1, _ = fbs[-1]["events"]
+        e1.synchronize()
+        own_ms = e0.elapsed_time(e1)
+    allms = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(allms, torch.tensor([own_ms], dtype=torch.float64, device=dev))
+    rank_ms = [float(t.item()) for t in allms]
     (_, tau_h, lu_h, ld_h), _, ms_e2e = timed(lambda: D.compute_TUD_banded(500.0, 6000.0, dict(opts), **kw))
     # exact evals of the whole problem (outside any timed region)
     p, w = rt.layer_weights(db, kw["Ts"], kw["Ps"], kw["PLs"], kw["MFs_VAL"], kw["MFs_ID"])
@@ -252,6 +265,7 @@ def banded_leg(args, rank, world, dev):
            "workload": "config5: 500-6000 cm^-1, %d points x %d layers, %d synthetic lines of 8 gases, band-sharded over %d "
                        "GPU(s), one all_gather of (tau, Lu, Ld)" % (nx, n_layers, args.banded_lines, world),
            "scaling": "strong", "evals": ev, "weideman_fraction": evw / max(1, ev), "ms": ms_dev, "evals_per_s": ev / (ms_dev * 1e-3),
+           "band_points": [b - a for a, b in bands], "band_compute_ms": rank_ms,
            "e2e_ms": ms_e2e, "e2e_evals_per_s": ev / (ms_e2e * 1e-3),
            "e2e_note": "every rank copies the full (tau, Lu, Ld) = %d MB to fresh numpy arrays" % (3 * 8 * nx // 1000000),
            "timing": "best of %d, CUDA events on the launching stream / wall clock, max over ranks" % reps,

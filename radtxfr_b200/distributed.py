@@ -48,6 +48,9 @@ def _dist():
     return dist
 
 
+_band_feedback = {}      # (axis, table, world) -> per-tile cost scale learnt from measured per-rank times
+
+
 def _all_gather_flat(out, inp, group=None):
     """all_gather_into_tensor of flat tensors.  NCCL takes device tensors directly; under the gloo backend (CPU tests,
     or several ranks sharing one GPU while debugging) device tensors are staged through the host."""
@@ -106,37 +109,45 @@ def all_gather_atmospheres(local, owners, n_atm, group=None):
 
 
 def estimate_tile_costs(db, T, p_atm, X, tile=TILE, wing_hw=50.0, wing_abs=0.0):
-    """Relative cost of every `tile`-point tile of the axis X for the Voigt kernel: the number of (line, state) pairs
-    whose wing can reach the tile, plus the pairs whose centre lies in it (the near zone is evaluated point by point,
-    everything further out at 32 nodes per 256 points, so the work per reaching pair is roughly constant).  Host-side,
-    from the sorted line centres and the column extrema the LineDB keeps -- an estimate for balancing bands
-    ("balance bands by estimated evals, not by width"), not a count."""
+    """Relative cost of every `tile`-point tile of the axis X for the Voigt kernel ("balance bands by
+    estimated evals, not by width" -- and since the far-field blocks made wing evaluations cheap, by estimated
+    INSTRUCTIONS): see _tile_costs_from_edges.  Host-side, from the sorted line centres and the column statistics the
+    LineDB keeps; an estimate for cutting bands, not a count."""
     X = np.asarray(X, dtype=float)
     ntiles = (X.size + tile - 1) // tile
     lo = X[np.arange(ntiles) * tile]
     hi = X[np.minimum((np.arange(ntiles) + 1) * tile, X.size) - 1]
-    return _tile_costs_from_edges(db, T, p_atm, lo, hi, wing_hw, wing_abs)
+    return _tile_costs_from_edges(db, T, p_atm, lo, hi, wing_hw, wing_abs, tile)
 
 
-def _tile_costs_from_edges(db, T, p_atm, lo, hi, wing_hw, wing_abs):
-    """estimate_tile_costs from the first (lo) and last (hi) wavenumber of every tile."""
+def _tile_costs_from_edges(db, T, p_atm, lo, hi, wing_hw, wing_abs, tile=TILE):
+    """Cost model per tile = (lines centred in the tile) x sum over states of the cost of one (line, state) pair with
+    the mean broadening of the table and the Doppler width AT THE TILE'S WAVENUMBER, in units of one exact wing
+    evaluation: prologue ~60 per tile the window reaches; wing points 1 each up to the 2 x 350-point near zone and 1/5
+    beyond it (32 nodes per 256 points plus visit overhead); windows of at most 128 points (pass 2) 3 per point;
+    Weideman-core points (|x| + y < 15, half-width (15 - y) GammaD / sqrt(ln 2)) 35 each.  The constants come from the
+    per-layer-group timings of config 2 (profiles/r02_voigt_microbench.txt); what matters for cutting bands is the trend
+    they capture: Doppler widths grow with wavenumber, so the expensive core points pile up at the top of a wide axis
+    (config 5: the upper half of 500-6000 cm^-1 holds half of the evaluations but ~3/4 of the work)."""
     T = np.asarray(T, dtype=float).ravel()
     p_atm = np.asarray(p_atm, dtype=float).ravel()
     nu = db.nu_sorted
-    cost = np.zeros(lo.size)
-    if nu.size == 0:
-        return cost + 1.0
-    # wing bound per state, as the kernel's state_prep does it: max(OmegaWing, HW*Gamma0_max, HW*GammaD_max)
-    r = 296.0 / T
-    g0 = np.abs(p_atm) * db.gamma_air_max * np.maximum(r ** db.n_air_range[0], r ** db.n_air_range[1])
-    gd = db.nu_max * np.sqrt(2.0 * 1.380648813e-16 * T * np.log(2.0) / (db.mass_min * 1.66053873e-24)) / 2.99792458e10
-    wb = np.round(np.maximum(np.maximum(wing_abs, wing_hw * g0), wing_hw * gd), 6)
+    if nu.size == 0 or lo.size == 0:
+        return np.ones(lo.size)
     inside = (np.searchsorted(nu, hi, side="right") - np.searchsorted(nu, lo, side="left")).astype(float)
-    for w in np.unique(wb):
-        n = float(np.sum(wb == w))
-        reach = np.searchsorted(nu, hi + w, side="right") - np.searchsorted(nu, lo - w, side="left")
-        cost += n * (reach + 2.0 * inside)
-    return cost + 1.0
+    dv = np.maximum((hi - lo) / max(tile - 1, 1), 1e-300)                     # grid spacing of each tile
+    mid = 0.5 * (lo + hi)
+    per_line = np.zeros(lo.size)
+    for Ts, ps in zip(T, p_atm):
+        g0 = abs(ps) * db.gamma_air_mean * (296.0 / Ts) ** db.n_air_mean
+        gd = mid * np.sqrt(2.0 * 1.380648813e-16 * Ts * np.log(2.0) / (db.mass_mean * 1.66053873e-24)) / 2.99792458e10
+        w = np.maximum(np.maximum(wing_abs, wing_hw * g0), wing_hw * gd) / dv       # half-window, grid points
+        y = g0 / gd * 0.8325546111576977
+        core = np.minimum(np.where(y < 15.0, 2.0 * (15.0 - y) * gd / 0.8325546111576977 / dv, 0.0), 2.0 * w)
+        cheap = 2.0 * w - core
+        wide = 60.0 * (1.0 + 2.0 * w / tile) + np.minimum(cheap, 700.0) + np.maximum(cheap - 700.0, 0.0) / 5.0
+        per_line += np.where(2.0 * w <= 128.0, 60.0 + 3.0 * cheap, wide) + 35.0 * core
+    return inside * per_line + 1.0
 
 
 def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True, **kwargs):
@@ -146,7 +157,8 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
     Bands start on multiples of the kernel's 2048-point tile and the tile size is pinned (K = 8), so the gathered
     result is bit-identical to a single-GPU compute_TUD with opts["voigt"] = {"tile_k": 8} (the automatic tile size of
     the single-GPU call may pick 1024-point tiles, whose summation order differs).  balance=True cuts the bands by
-    estimated cost (estimate_tile_costs) instead of by size.  The three spectra of every rank travel in ONE
+    estimated cost (estimate_tile_costs) instead of by size, corrected from call to call by the measured per-rank
+    compute times (the band plan does not affect the result: any tile-aligned plan gives the same bits).  The three spectra of every rank travel in ONE
     all_gather of equal-size shards; the host copy goes through the pinned, threaded path of compute_TUD."""
     import torch
     from . import engine, radiative_transfer as rt
@@ -166,17 +178,38 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
     vs = rt._voigt_settings(opts)
     vs["flags"] = (vs["flags"] & ~(0xF << 8)) | FORCE_K8
     costs = None
+    fb_key = None
     if balance:
         ntiles = (nX + TILE - 1) // TILE
         edges = torch.cat([grid_full[::TILE], grid_full[-1:]]).cpu().numpy()       # first point of every tile + the last point
-        costs = _tile_costs_from_edges(db, T, p, edges[:-1], np.append(edges[1:-1], edges[-1]), vs["wing_hw"], vs["wing_abs"])
+        costs = _tile_costs_from_edges(db, T, p, edges[:-1], np.append(edges[1:-1], edges[-1]), vs["wing_hw"], vs["wing_abs"])   # noqa: E501
         assert costs.size == ntiles
+        # feedback: the model above is a first guess; the per-rank compute times of the previous call on the same axis
+        # and table (CUDA events, all-gathered here: one 8-byte-per-rank exchange) rescale the cost of every rank's
+        # tiles, so repeated calls -- the production pattern: one axis, many atmospheres -- converge to equal times
+        fb_key = (float(Xmin), float(Xmax), nX, id(db), world)
+        fb = _band_feedback.get(fb_key)
+        if fb is not None and world > 1:
+            e0, e1, prev_bands = fb["events"]
+            e1.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=db.device)
+            allms = torch.empty(world, dtype=torch.float64, device=db.device)
+            _all_gather_flat(allms, ms, group)
+            allms = allms.cpu().numpy()
+            if np.all(allms > 0):
+                for r, (a, b) in enumerate(prev_bands):
+                    fb["scale"][a // TILE:(b + TILE - 1) // TILE] *= (allms[r] / allms.mean()) ** 0.8
+            fb["last_ms"] = allms
+        if fb is not None:
+            costs = costs * fb["scale"]
     bands = plan_bands(nX, world, weights=costs)
     i0, i1 = bands[rank]
     k = Z_s.size * mu_s.size
     nf = 2 * k + 1
     width = max(1, max(b - a for a, b in bands))
     shard = torch.zeros((nf, width), dtype=torch.float64, device=db.device)       # equal-size shard, padded
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
     if i1 > i0:
         n = i1 - i0
         grid = grid_full[i0:i1]
@@ -187,6 +220,12 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
         else:
             shard[:k, :n] = tau[0].reshape(n, k).T; shard[k:2 * k, :n] = lu[0].reshape(n, k).T
         shard[2 * k, :n] = ld[0]
+    ev1.record()
+    if fb_key is not None:
+        fb = _band_feedback.setdefault(fb_key, {"scale": np.ones((nX + TILE - 1) // TILE)})
+        fb["events"] = (ev0, ev1, bands)
+        while len(_band_feedback) > 8:
+            _band_feedback.pop(next(iter(_band_feedback)))
     flat = torch.empty((world, nf, width), dtype=torch.float64, device=db.device)
     _all_gather_flat(flat.view(-1), shard.view(-1), group)                      # the path's single collective
     full = torch.cat([flat[r, :, : b - a] for r, (a, b) in enumerate(bands) if b > a], dim=1)     # [nf, nX]

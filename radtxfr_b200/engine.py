@@ -267,6 +267,9 @@ class LineDB:
         self.gamma_air_max = float(cat["gamma_air"].max()) if self.n_lines else 0.0
         self.n_air_range = (float(cat["n_air"].min()), float(cat["n_air"].max())) if self.n_lines else (0.0, 0.0)
         self.mass_min = float(np.min(mass))
+        self.gamma_air_mean = float(cat["gamma_air"].mean()) if self.n_lines else 0.0
+        self.n_air_mean = float(cat["n_air"].mean()) if self.n_lines else 0.0
+        self.mass_mean = float(np.mean(np.asarray(mass)[inverse])) if self.n_lines else float(np.mean(mass))
 
     # -- abundance factors ------------------------------------------------------------------------
     def iso_factors(self, Components=None, factor=1.0):
