@@ -266,6 +266,7 @@ def banded_leg(args, rank, world, dev):
                        "GPU(s), one all_gather of (tau, Lu, Ld)" % (nx, n_layers, args.banded_lines, world),
            "scaling": "strong", "evals": ev, "weideman_fraction": evw / max(1, ev), "ms": ms_dev, "evals_per_s": ev / (ms_dev * 1e-3),
            "band_points": [b - a for a, b in bands], "band_compute_ms": rank_ms,
+           "host_prep_ms_rank0": fbs[-1].get("host_prep_ms") if fbs else None,
            "e2e_ms": ms_e2e, "e2e_evals_per_s": ev / (ms_e2e * 1e-3),
            "e2e_note": "every rank copies the full (tau, Lu, Ld) = %d MB to fresh numpy arrays" % (3 * 8 * nx // 1000000),
            "timing": "best of %d, CUDA events on the launching stream / wall clock, max over ranks" % reps,

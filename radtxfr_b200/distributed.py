@@ -49,6 +49,7 @@ def _dist():
 
 
 _band_feedback = {}      # (axis, table, world) -> per-tile cost scale learnt from measured per-rank times
+_edge_cache = {}         # axis -> first wavenumber of every tile (host copy)
 
 
 def _all_gather_flat(out, inp, group=None):
@@ -117,10 +118,10 @@ def estimate_tile_costs(db, T, p_atm, X, tile=TILE, wing_hw=50.0, wing_abs=0.0):
     ntiles = (X.size + tile - 1) // tile
     lo = X[np.arange(ntiles) * tile]
     hi = X[np.minimum((np.arange(ntiles) + 1) * tile, X.size) - 1]
-    return _tile_costs_from_edges(db, T, p_atm, lo, hi, wing_hw, wing_abs, tile)
+    return _tile_costs_from_edges(db, T, p_atm, lo, hi, wing_hw, wing_abs, tile, X.size)
 
 
-def _tile_costs_from_edges(db, T, p_atm, lo, hi, wing_hw, wing_abs, tile=TILE):
+def _tile_costs_from_edges(db, T, p_atm, lo, hi, wing_hw, wing_abs, tile=TILE, nx=None, inside=None):
     """Cost model per tile = (lines centred in the tile) x sum over states of the cost of one (line, state) pair with
     the mean broadening of the table and the Doppler width AT THE TILE'S WAVENUMBER, in units of one exact wing
     evaluation: prologue ~60 per tile the window reaches; wing points 1 each up to the 2 x 350-point near zone and 1/5
@@ -134,20 +135,26 @@ def _tile_costs_from_edges(db, T, p_atm, lo, hi, wing_hw, wing_abs, tile=TILE):
     nu = db.nu_sorted
     if nu.size == 0 or lo.size == 0:
         return np.ones(lo.size)
-    inside = (np.searchsorted(nu, hi, side="right") - np.searchsorted(nu, lo, side="left")).astype(float)
-    dv = np.maximum((hi - lo) / max(tile - 1, 1), 1e-300)                     # grid spacing of each tile
-    mid = 0.5 * (lo + hi)
-    per_line = np.zeros(lo.size)
-    for Ts, ps in zip(T, p_atm):
-        g0 = abs(ps) * db.gamma_air_mean * (296.0 / Ts) ** db.n_air_mean
-        gd = mid * np.sqrt(2.0 * 1.380648813e-16 * Ts * np.log(2.0) / (db.mass_mean * 1.66053873e-24)) / 2.99792458e10
-        w = np.maximum(np.maximum(wing_abs, wing_hw * g0), wing_hw * gd) / dv       # half-window, grid points
-        y = g0 / gd * 0.8325546111576977
-        core = np.minimum(np.where(y < 15.0, 2.0 * (15.0 - y) * gd / 0.8325546111576977 / dv, 0.0), 2.0 * w)
-        cheap = 2.0 * w - core
-        wide = 60.0 * (1.0 + 2.0 * w / tile) + np.minimum(cheap, 700.0) + np.maximum(cheap - 700.0, 0.0) / 5.0
-        per_line += np.where(2.0 * w <= 128.0, 60.0 + 3.0 * cheap, wide) + 35.0 * core
-    return inside * per_line + 1.0
+    if inside is None:
+        inside = (np.searchsorted(nu, hi, side="right") - np.searchsorted(nu, lo, side="left")).astype(float)
+    npts = np.full(lo.size, float(tile))
+    if nx is not None:
+        npts[-1] = nx - (lo.size - 1) * tile                                  # the last tile may be partial
+    # the per-line cost varies smoothly along the axis: evaluate the model on at most 64 sample tiles, interpolate
+    n_all = lo.size
+    samp = np.unique(np.linspace(0, n_all - 1, min(n_all, 64)).round().astype(int))
+    dv = np.maximum((hi[samp] - lo[samp]) / np.maximum(npts[samp] - 1.0, 1.0), 1e-300)   # grid spacing of the sample tiles
+    mid = 0.5 * (lo[samp] + hi[samp])
+    Ts, ps = T[:, None], np.abs(p_atm)[:, None]                                # [n_states, 1] against [1, n_tiles]
+    g0 = ps * db.gamma_air_mean * (296.0 / Ts) ** db.n_air_mean
+    gd = mid[None, :] * np.sqrt(2.0 * 1.380648813e-16 * Ts * np.log(2.0) / (db.mass_mean * 1.66053873e-24)) / 2.99792458e10
+    w = np.maximum(np.maximum(wing_abs, wing_hw * g0), wing_hw * gd) / dv[None, :]    # half-window, grid points
+    y = g0 / gd * 0.8325546111576977
+    core = np.minimum(np.where(y < 15.0, 2.0 * (15.0 - y) * gd / 0.8325546111576977 / dv[None, :], 0.0), 2.0 * w)
+    cheap = 2.0 * w - core
+    wide = 60.0 * (1.0 + 2.0 * w / tile) + np.minimum(cheap, 700.0) + np.maximum(cheap - 700.0, 0.0) / 5.0
+    per_line = (np.where(2.0 * w <= 128.0, 60.0 + 3.0 * cheap, wide) + 35.0 * core).sum(axis=0)
+    return inside * np.interp(np.arange(n_all), samp, per_line) + 1.0
 
 
 def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True, **kwargs):
@@ -162,6 +169,8 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
     all_gather of equal-size shards; the host copy goes through the pinned, threaded path of compute_TUD."""
     import torch
     from . import engine, radiative_transfer as rt
+    import time as _t0
+    t_enter = _t0.perf_counter()
     dist = _dist()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     opts.update(kwargs)
@@ -181,8 +190,18 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
     fb_key = None
     if balance:
         ntiles = (nX + TILE - 1) // TILE
-        edges = torch.cat([grid_full[::TILE], grid_full[-1:]]).cpu().numpy()       # first point of every tile + the last point
-        costs = _tile_costs_from_edges(db, T, p, edges[:-1], np.append(edges[1:-1], edges[-1]), vs["wing_hw"], vs["wing_abs"])   # noqa: E501
+        ekey = (float(Xmin), float(Xmax), nX, str(db.device))
+        edges = _edge_cache.get(ekey)
+        if edges is None:
+            if len(_edge_cache) >= 4:
+                _edge_cache.pop(next(iter(_edge_cache)))
+            edges = torch.cat([grid_full[::TILE], grid_full[-1:]]).cpu().numpy()   # tile starts + last point
+            lo_e, hi_e = edges[:-1], np.append(edges[1:-1], edges[-1])
+            inside = (np.searchsorted(db.nu_sorted, hi_e, side="right") - np.searchsorted(db.nu_sorted, lo_e, side="left")).astype(float)
+            edges = _edge_cache[ekey] = (lo_e, hi_e, inside, id(db))
+        if edges[3] != id(db):
+            edges = (edges[0], edges[1], None, id(db))
+        costs = _tile_costs_from_edges(db, T, p, edges[0], edges[1], vs["wing_hw"], vs["wing_abs"], TILE, nX, edges[2])
         assert costs.size == ntiles
         # feedback: the model above is a first guess; the per-rank compute times of the previous call on the same axis
         # and table (CUDA events, all-gathered here: one 8-byte-per-rank exchange) rescale the cost of every rank's
@@ -208,6 +227,8 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
     nf = 2 * k + 1
     width = max(1, max(b - a for a, b in bands))
     shard = torch.zeros((nf, width), dtype=torch.float64, device=db.device)       # equal-size shard, padded
+    import time as _time
+    t_launch = _time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     if i1 > i0:
@@ -224,6 +245,7 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
     if fb_key is not None:
         fb = _band_feedback.setdefault(fb_key, {"scale": np.ones((nX + TILE - 1) // TILE)})
         fb["events"] = (ev0, ev1, bands)
+        fb["host_prep_ms"] = 1e3 * (t_launch - t_enter)
         while len(_band_feedback) > 8:
             _band_feedback.pop(next(iter(_band_feedback)))
     flat = torch.empty((world, nf, width), dtype=torch.float64, device=db.device)
