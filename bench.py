@@ -423,13 +423,13 @@ def gpu_arm(args):
 
             def e2e_step(i):
                 Xo, tau_d, lu_d, ld_d = D.compute_TUD_batch_sharded(XMIN, XMAX, T_steps[i], M_steps[i], dict(opts), **kw)
-                if rank == 0:
-                    return rt._to_host(tau_d, lu_d, ld_d)
-                return None
-            h2d = 8 * (3 * nL + nL * db.n_iso)
+                # every rank holds all N spectra on its GPU after the gather and copies the atmosphere it owns to its host
+                return rt._to_host(tau_d[rank], lu_d[rank], ld_d[rank])
+            h2d = 8 * (3 * nL + nL * db.n_iso) * world
             d2h = 8 * 3 * nX * world
-            api = ("radtxfr_b200.distributed.compute_TUD_batch_sharded (N atmospheres as numpy in; NCCL all_gather of "
-                   "(tau, Lu, Ld); rank 0 copies all N spectra to numpy); d2h bytes are rank 0's")
+            api = ("radtxfr_b200.distributed.compute_TUD_batch_sharded (N atmospheres as numpy in on every rank; NCCL "
+                   "all_gather of (tau, Lu, Ld) so that every GPU holds all N spectra; every rank copies the spectra of the "
+                   "atmosphere it owns to numpy); byte counts are summed over the ranks")
         e2e_step(0)   # warm
         if world > 1:
             dist.barrier()
