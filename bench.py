@@ -208,16 +208,22 @@ def banded_leg(args, rank, world, dev):
         for _ in range(reps):
             dist.barrier(); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            tw = time.perf_counter(); e0.record()
+            tw = time.perf_counter(); tw_epoch = time.time(); e0.record()
             out = fn()
             e1.record(); torch.cuda.synchronize()
             wall = time.perf_counter() - tw
             t = torch.tensor([e0.elapsed_time(e1), 1e3 * wall], dtype=torch.float64, device=dev)
+            per_rank = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(per_rank, torch.tensor([e0.elapsed_time(e1), tw_epoch, 1e3 * wall], dtype=torch.float64, device=dev))
             dist.all_reduce(t, op=dist.ReduceOp.MAX)      # max over ranks
+            if t[0].item() < best_dev:
+                timed.detail = {"per_rank_ms": [float(x[0]) for x in per_rank],
+                                "start_skew_ms": [1e3 * float(x[1] - per_rank[0][1]) for x in per_rank]}
             best_dev, best_wall = min(best_dev, t[0].item()), min(best_wall, t[1].item())
         return out, best_dev, best_wall
 
     (X, tau_d, lu_d, ld_d), ms_dev, _ = timed(lambda: D.compute_TUD_banded(500.0, 6000.0, dict(opts), to_host=False, **kw))
+    dev_detail = getattr(timed, "detail", None)
     # how well the bands are balanced: per-rank compute times (before the gather) of the last call, from the feedback
     # records of compute_TUD_banded
     fbs = [v for k, v in D._band_feedback.items() if k[2] == X.size]
@@ -266,7 +272,10 @@ def banded_leg(args, rank, world, dev):
                        "GPU(s), one all_gather of (tau, Lu, Ld)" % (nx, n_layers, args.banded_lines, world),
            "scaling": "strong", "evals": ev, "weideman_fraction": evw / max(1, ev), "ms": ms_dev, "evals_per_s": ev / (ms_dev * 1e-3),
            "band_points": [b - a for a, b in bands], "band_compute_ms": rank_ms,
+           "timed_call_detail": dev_detail,
            "host_prep_ms_rank0": fbs[-1].get("host_prep_ms") if fbs else None,
+           "gather_ms_rank0": (fbs[-1]["tail_events"][0].elapsed_time(fbs[-1]["tail_events"][1]) if fbs and "tail_events" in fbs[-1] else None),
+           "assemble_ms_rank0": (fbs[-1]["tail_events"][1].elapsed_time(fbs[-1]["tail_events"][2]) if fbs and "tail_events" in fbs[-1] else None),
            "e2e_ms": ms_e2e, "e2e_evals_per_s": ev / (ms_e2e * 1e-3),
            "e2e_note": "every rank copies the full (tau, Lu, Ld) = %d MB to fresh numpy arrays" % (3 * 8 * nx // 1000000),
            "timing": "best of %d, CUDA events on the launching stream / wall clock, max over ranks" % reps,

@@ -50,6 +50,7 @@ def _dist():
 
 _band_feedback = {}      # (axis, table, world) -> per-tile cost scale learnt from measured per-rank times
 _edge_cache = {}         # axis -> first wavenumber of every tile (host copy)
+_gather_bufs = {}        # device -> (send shard, receive buffer), grow-only
 
 
 def _all_gather_flat(out, inp, group=None):
@@ -182,6 +183,12 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
     # copy is rebuilt only after the kernels are in flight
     X_, grid_full = rt._device_axis(Xmin, Xmax, opts["DVOUT"], db.device)
     nX = grid_full.numel()
+    axis_job = None
+    if X_ is None:                            # the host axis (88 MB for config 5) is built on a side thread meanwhile
+        import threading
+        box = {}
+        axis_job = threading.Thread(target=lambda: box.setdefault("X", rt.make_spectral_axis(Xmin, Xmax, opts["DVOUT"])))
+        axis_job.start()
     db.check_temperatures(T)
     p, w = rt.layer_weights(db, T, opts["Ps"], opts["PLs"], opts["MFs_VAL"], opts["MFs_ID"])
     vs = rt._voigt_settings(opts)
@@ -225,8 +232,18 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
     i0, i1 = bands[rank]
     k = Z_s.size * mu_s.size
     nf = 2 * k + 1
+    # equal-size shards: the widest band rounded up to 64 tiles, so that the persistent send / receive buffers (grow-only,
+    # per device) keep their size while the feedback nudges the cuts -- a fresh allocation would be a cudaMalloc, which
+    # blocks the host until the queued kernels are done and serialises everything the host still has to do
     width = max(1, max(b - a for a, b in bands))
-    shard = torch.zeros((nf, width), dtype=torch.float64, device=db.device)       # equal-size shard, padded
+    width = (width + 64 * TILE - 1) // (64 * TILE) * (64 * TILE)
+    bufs = _gather_bufs.get(str(db.device))
+    if bufs is None or bufs[0].numel() < nf * width or bufs[1].numel() < world * nf * width or bufs[2][0].numel() < k * width:
+        bufs = _gather_bufs[str(db.device)] = (torch.zeros(nf * width, dtype=torch.float64, device=db.device),
+                                               torch.empty(world * nf * width, dtype=torch.float64, device=db.device),
+                                               [torch.empty(k * width if j < 2 else width, dtype=torch.float64, device=db.device)
+                                                for j in range(3)])
+    shard = bufs[0][: nf * width].view(nf, width)                                  # padding beyond the band is never read
     import time as _time
     t_launch = _time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -235,7 +252,7 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
         n = i1 - i0
         grid = grid_full[i0:i1]
         od = db.voigt_sum(T, p, w, grid, out=rt._od_workspace(db.device, T.size, n), **vs)
-        tau, lu, ld = engine.tud(od, T[None, :], grid, Z, Z_s, mu_s, opts["N_angle"], opts["returnOD"])
+        tau, lu, ld = engine.tud(od, T[None, :], grid, Z, Z_s, mu_s, opts["N_angle"], opts["returnOD"], out=bufs[2])
         if k == 1:
             shard[0, :n] = tau.reshape(n); shard[1, :n] = lu.reshape(n)
         else:
@@ -248,17 +265,22 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
         fb["host_prep_ms"] = 1e3 * (t_launch - t_enter)
         while len(_band_feedback) > 8:
             _band_feedback.pop(next(iter(_band_feedback)))
-    flat = torch.empty((world, nf, width), dtype=torch.float64, device=db.device)
-    _all_gather_flat(flat.view(-1), shard.view(-1), group)                      # the path's single collective
+    flat = bufs[1][: world * nf * width].view(world, nf, width)
+    _all_gather_flat(flat.view(-1), shard.reshape(-1), group)                   # the path's single collective
+    ev2 = torch.cuda.Event(enable_timing=True); ev2.record()
     full = torch.cat([flat[r, :, : b - a] for r, (a, b) in enumerate(bands) if b > a], dim=1)     # [nf, nX]
-    if X_ is None:
-        X_ = rt.make_spectral_axis(Xmin, Xmax, opts["DVOUT"])                    # while the GPU works
+    ev3 = torch.cuda.Event(enable_timing=True); ev3.record()
+    if fb_key is not None:
+        _band_feedback[fb_key]["tail_events"] = (ev1, ev2, ev3)
     if k == 1:
         tau_d, lu_d = full[0].reshape(nX, 1, 1), full[1].reshape(nX, 1, 1)
     else:
         tau_d = full[:k].T.contiguous().reshape(nX, Z_s.size, mu_s.size)
         lu_d = full[k:2 * k].T.contiguous().reshape(nX, Z_s.size, mu_s.size)
     ld_d = full[2 * k]
+    if axis_job is not None:
+        axis_job.join()
+        X_ = box["X"]
     if to_host:
         tau_, Lu_, Ld_ = rt._to_host(tau_d, lu_d, ld_d)
     else:

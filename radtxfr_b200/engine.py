@@ -431,7 +431,7 @@ def mako_bands(mode, xmin, xmax, res_factor=None, fwhm_sf=1.0, shift=0.0, scale=
 
 
 # --------------------------------------------------------------------------------------------- line-less ops
-def tud(od, T_layers, grid, Z, altitudes, mu, n_angle, return_od=False, device=None, split=False):
+def tud(od, T_layers, grid, Z, altitudes, mu, n_angle, return_od=False, device=None, split=False, out=None):
     """rtx_tud.  od [n_atm, nL, nx] (or [nL, nx]), T_layers [n_atm, nL]; returns (tau, lu, ld) CUDA tensors of
     shapes [n_atm, nx, n_alt, n_mu], same, [n_atm, nx].  split=True launches the two halves separately and returns
     (tau, lu, ld, ready): tau and lu are complete once the CUDA event `ready` has fired, while the downwelling half
@@ -450,9 +450,15 @@ def tud(od, T_layers, grid, Z, altitudes, mu, n_angle, return_od=False, device=N
     alt = np.ascontiguousarray(np.asarray(altitudes, dtype=np.float64).ravel())
     mu = np.ascontiguousarray(np.asarray(mu, dtype=np.float64).ravel())
     assert Z.size == nL
-    tau = torch.empty((n_atm, nx, alt.size, mu.size), dtype=torch.float64, device=dev)
-    lu = torch.empty_like(tau)
-    ld = torch.empty((n_atm, nx), dtype=torch.float64, device=dev)
+    if out is not None:                       # caller-owned result buffers (flat tensors of sufficient size)
+        k = n_atm * nx * alt.size * mu.size
+        tau = out[0][:k].view(n_atm, nx, alt.size, mu.size)
+        lu = out[1][:k].view(n_atm, nx, alt.size, mu.size)
+        ld = out[2][: n_atm * nx].view(n_atm, nx)
+    else:
+        tau = torch.empty((n_atm, nx, alt.size, mu.size), dtype=torch.float64, device=dev)
+        lu = torch.empty_like(tau)
+        ld = torch.empty((n_atm, nx), dtype=torch.float64, device=dev)
     args = (h.h, n_atm, nL, _ptr(od), _ptr(T_layers), _ptr(grid), nx, _hptr(Z), _hptr(alt), alt.size, _hptr(mu), mu.size,
             int(n_angle), int(bool(return_od)))
     if not split:
