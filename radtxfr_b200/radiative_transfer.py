@@ -312,10 +312,8 @@ def compute_TUD_batch(Xmin, Xmax, Ts, MFs_VAL, opts=options, atm_chunk=None, ils
     n_atm, nL = Ts.shape
     Z_s = np.array([opts["Altitudes"]]).ravel()
     mu_s = np.array([1.0 / np.cos(opts["theta_r"])]).ravel()
-    X_, grid = _device_axis(Xmin, Xmax, opts["DVOUT"], db.device)
-    if X_ is None:
-        X_ = make_spectral_axis(Xmin, Xmax, opts["DVOUT"])
-    nX = X_.size
+    X_, grid = _device_axis(Xmin, Xmax, opts["DVOUT"], db.device)      # on a cache hit the host axis is built after the launches
+    nX = grid.numel()
     db.check_temperatures(Ts)
     if atm_chunk is None:
         atm_chunk = max(1, min(max(n_atm, 1), int(4e9 // (8 * nL * nX))))   # <= 4 GB of optical depth at a time
@@ -324,10 +322,13 @@ def compute_TUD_batch(Xmin, Xmax, Ts, MFs_VAL, opts=options, atm_chunk=None, ils
     outs = []
     band = None
     if ils is not None:
-        band = _mako_bands(X_, None, 1.0, 0.0, 1.0) if ils == "triangle" else _mako_bands_gauss()
+        # linspace(Xmin, Xmax, n) starts at Xmin and ends at Xmax exactly: the clip interval of the triangle bands
+        band = _mako_bands(np.array([float(Xmin), float(Xmax)]), None, 1.0, 0.0, 1.0) if ils == "triangle" else _mako_bands_gauss()
     if n_atm == 0:                                   # a rank that owns no atmosphere (distributed.compute_TUD_batch_sharded)
         nout = nX if band is None else band[0].size
         z = torch.zeros((0, nout, Z_s.size, mu_s.size), dtype=torch.float64, device=db.device)
+        if X_ is None and band is None:
+            X_ = make_spectral_axis(Xmin, Xmax, opts["DVOUT"])
         return (band[0] if band is not None else X_), z, z.clone(), torch.zeros((0, nout), dtype=torch.float64, device=db.device)
     Pb = np.ascontiguousarray(np.broadcast_to(P, (n_atm, nL)))
     PLb = np.ascontiguousarray(np.broadcast_to(PL, (n_atm, nL)))
@@ -350,9 +351,14 @@ def compute_TUD_batch(Xmin, Xmax, Ts, MFs_VAL, opts=options, atm_chunk=None, ils
             lu = R[:, k:2 * k].reshape(nb, na, nal, nmu).permute(1, 0, 2, 3).contiguous()
             ld = R[:, 2 * k:].reshape(nb, na).permute(1, 0).contiguous()
         outs.append((tau, lu, ld))
-    tau = torch.cat([o[0] for o in outs], dim=0)
-    lu = torch.cat([o[1] for o in outs], dim=0)
-    ld = torch.cat([o[2] for o in outs], dim=0)
+    if len(outs) == 1:
+        tau, lu, ld = outs[0]
+    else:
+        tau = torch.cat([o[0] for o in outs], dim=0)
+        lu = torch.cat([o[1] for o in outs], dim=0)
+        ld = torch.cat([o[2] for o in outs], dim=0)
+    if X_ is None and band is None:
+        X_ = make_spectral_axis(Xmin, Xmax, opts["DVOUT"])        # the kernels are in flight
     return (band[0] if band is not None else X_), tau, lu, ld
 
 
