@@ -133,6 +133,8 @@ int rtx_tape3_read(const char* path, double vmin, double vmax, int64_t capacity,
 #define RTX_VOIGT_NOFAR 4096    /* disable the far-field blocks: evaluate every (line, grid point) pair at the grid point
                                  * itself (default: slices a window covers from >= 0.375 slice widths away are summed
                                  * at 32 Chebyshev nodes and interpolated, relative error < 1e-13) */
+#define RTX_VOIGT_NOTILEFAR 16384 /* keep the slice-level far-field blocks but not the tile-level ones (a line whose window
+                                 * covers a whole tile from >= 0.375 tile widths away is summed at the tile's 32 nodes) */
 #define RTX_VOIGT_SDVOIGT 8192  /* absorptionCoefficient_SDVoigt (misc/hapi.py:10657-10905): lines whose Gamma2 = sum_d x_d
                                  * SD_d p gamma_d is non-zero take the quadratic speed-dependent profile (pcqsdhc PART2-4,
                                  * misc/hapi.py:9923-10020); the rest is the Voigt driver */

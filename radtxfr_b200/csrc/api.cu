@@ -238,6 +238,13 @@ extern "C" int rtx_lines_upload(rtx_handle* h, int64_t n, const double* nu, cons
     lo = hi = 0.0;
     if (n > 0) { auto mm = std::minmax_element(v.begin(), v.begin() + n); lo = *mm.first; hi = *mm.second; }
   };
+  auto typical = [&](const std::vector<double>& g, const std::vector<double>& e, double& gt, double& et) {
+    double s1 = 0.0, s2 = 0.0, se = 0.0;
+    for (int64_t i = 0; i < n; ++i) { s1 += fabs(g[i]); s2 += g[i] * g[i]; se += e[i]; }
+    gt = s1 > 0.0 ? s2 / s1 : 0.0;
+    et = n > 0 ? se / (double)n : 0.0;
+  };
+  typical(v_ga, v_na, L.gair_typ, L.nair_typ);
   double dummy;
   minmax(v_nu, L.nu_min, L.nu_max);
   minmax(v_ga, dummy, L.gair_max);
@@ -256,6 +263,7 @@ extern "C" int rtx_lines_upload(rtx_handle* h, int64_t n, const double* nu, cons
     minmax(v_gs, dummy, L.gself_max);
     L.gself_max = std::max(L.gself_max, fabs(dummy));
     minmax(v_ns, L.nself_min, L.nself_max);
+    typical(v_gs, v_ns, L.gself_typ, L.nself_typ);
   }
   if (deltap_air || deltap_self) {
     L.has_deltap = true;

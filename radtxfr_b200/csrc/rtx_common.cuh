@@ -40,6 +40,9 @@ struct LineTable {
   // extrema used for the conservative per-state wing bound
   double nu_min = 0, nu_max = 0, gair_max = 0, gself_max = 0, nair_min = 0, nair_max = 0, nself_min = 0,
          nself_max = 0;
+  // typical values (eval-weighted mean width sum(g^2)/sum(g), mean exponent) for the window statistic that picks the
+  // kernel variant
+  double gair_typ = 0, gself_typ = 0, nair_typ = 0, nself_typ = 0;
 };
 
 struct rtx_handle {

@@ -77,6 +77,15 @@ template <int K, int MODE, bool WS>
 struct ChunkCfg {
   static constexpr int LCH = (K == 8 && MODE != 2 && !WS) ? RTX_LCH_BIG : NT * RTX_ROUNDS;
 };
+// tile-level far-field blocks compiled in (a whole tile at 32 nodes when a window covers it from far away)
+#ifndef RTX_TILEFAR
+#define RTX_TILEFAR 1
+#endif
+// typical window half-width (grid points) from which the variant with tile-level blocks is faster (measured break-even on
+// uniform wings: ~3700 points; tools/tilefar_sweep.py)
+#ifndef RTX_TF_WINDOW
+#define RTX_TF_WINDOW 4000.0
+#endif
 #ifndef RTX_NARROW_MAX
 #define RTX_NARROW_MAX 128
 #endif
@@ -122,7 +131,12 @@ struct VoigtParams {
   double xx[RTX_MAX_EXTRA_DILUENTS];
   const double* cheb;   // [32] Chebyshev nodes cos(theta_k), then [32][32] node-values -> coefficients matrix [k][m]
   int far_ok;    // far-field blocks enabled
-  const double* sel;   // device-side tile-size choice: run only if (sel[0] < RTX_K4_WINDOW) == (K == 4); null = run
+  int tfar_ok;   // tile-level far-field blocks enabled (whole tiles at 32 nodes)
+  // device-side choice of the kernel variant (null = run): sel[0] = eval-weighted mean wing bound, sel[1] = typical
+  // wing, both in grid points.  Variant 0 (K = 4): sel[0] < RTX_K4_WINDOW unless sel_k8; variant 2 (K = 8 with the
+  // tile-level far-field blocks): sel[1] >= RTX_TF_WINDOW and sel_tf; variant 1 (K = 8 without) otherwise.
+  const double* sel;
+  int sel_k8, sel_tf;
   int lorentz;   // PROFILE_LORENTZ instead of PROFILE_VOIGT: no Doppler width, wing = max(OmegaWing, HW*Gamma0)
   int doppler;   // PROFILE_DOPPLER (absorptionCoefficient_Doppler): 1 = with line shift, 2 = LineShift=False
 };
@@ -478,6 +492,8 @@ struct PrepParams {
   double *st_q, *st_d, *st_wb;
   double x_air, x_self, wing_abs, wing_hw;
   double nu_max, gair_max, gself_max, nair_min, nair_max, nself_min, nself_max;
+  double gair_typ, gself_typ, nair_typ, nself_typ;
+  double* st_wt;          // [n_states] typical wing (eval-weighted mean width instead of the largest)
   int doppler, n_extra;
   double xx[RTX_MAX_EXTRA_DILUENTS], xg_max[RTX_MAX_EXTRA_DILUENTS], xn_min[RTX_MAX_EXTRA_DILUENTS], xn_max[RTX_MAX_EXTRA_DILUENTS];
 };
@@ -506,23 +522,36 @@ __global__ void state_prep_kernel(PrepParams P) {
     g0 += fabs(p) * fabs(P.xx[e]) * P.xg_max[e] * fmax(exp(P.xn_min[e] * lnr), exp(P.xn_max[e] * lnr));
   double wb = fmax(fmax(P.wing_abs, P.wing_hw * g0), P.wing_hw * dmax * P.nu_max);
   P.st_wb[s] = wb * (1.0 + 1e-6) + 1e-9;
+  double gt = fabs(p) * (fabs(P.x_air) * P.gair_typ * exp(P.nair_typ * lnr) + fabs(P.x_self) * P.gself_typ * exp(P.nself_typ * lnr));
+  for (int e = 0; e < P.n_extra; ++e)
+    gt += fabs(p) * fabs(P.xx[e]) * P.xg_max[e] * fmax(exp(P.xn_min[e] * lnr), exp(P.xn_max[e] * lnr));
+  if (P.doppler) gt = 0.0;
+  P.st_wt[s] = fmin(wb, fmax(fmax(P.wing_abs, P.wing_hw * gt), P.wing_hw * dmax * 0.5 * P.nu_max));
 }
 
-// eval-weighted mean of the per-state wing bound in grid points: sum(wb^2)/sum(wb) / mean grid spacing
-__global__ void window_stats_kernel(int n_states, const double* __restrict__ st_wb, const double* __restrict__ grid,
-                                    int64_t nx, double* __restrict__ out) {
-  __shared__ double s1[256], s2[256];
-  double a = 0.0, b = 0.0;
-  for (int s = threadIdx.x; s < n_states; s += 256) { const double w = st_wb[s]; a += w * w; b += w; }
-  s1[threadIdx.x] = a; s2[threadIdx.x] = b;
+// eval-weighted mean of the per-state wing in grid points, sum(w^2)/sum(w) / mean grid spacing: out[0] from the wing
+// bound (largest width of the table), out[1] from the typical wing
+__global__ void window_stats_kernel(int n_states, const double* __restrict__ st_wb, const double* __restrict__ st_wt,
+                                    const double* __restrict__ grid, int64_t nx, double* __restrict__ out) {
+  __shared__ double s1[256], s2[256], s3[256], s4[256];
+  double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+  for (int s = threadIdx.x; s < n_states; s += 256) {
+    const double w = st_wb[s], t = st_wt[s];
+    a += w * w; b += w; c += t * t; d += t;
+  }
+  s1[threadIdx.x] = a; s2[threadIdx.x] = b; s3[threadIdx.x] = c; s4[threadIdx.x] = d;
   __syncthreads();
-  for (int d = 128; d > 0; d >>= 1) {
-    if (threadIdx.x < d) { s1[threadIdx.x] += s1[threadIdx.x + d]; s2[threadIdx.x] += s2[threadIdx.x + d]; }
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) {
+      s1[threadIdx.x] += s1[threadIdx.x + k]; s2[threadIdx.x] += s2[threadIdx.x + k];
+      s3[threadIdx.x] += s3[threadIdx.x + k]; s4[threadIdx.x] += s4[threadIdx.x + k];
+    }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
     const double dv = nx > 1 ? (grid[nx - 1] - grid[0]) / (double)(nx - 1) : 0.0;
     out[0] = (s2[0] > 0.0 && dv > 0.0) ? (s1[0] / s2[0]) / dv : 1e300;
+    out[1] = (s4[0] > 0.0 && dv > 0.0) ? (s3[0] / s4[0]) / dv : 1e300;
   }
 }
 
@@ -611,7 +640,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
 // cores stay in FP64.
 // WS = warp-specialised variant: NPW extra producer warps run the prologue one chunk ahead (double-buffered
 // records, mbarrier full/empty handshake); the eight consumer warps never meet at a block-wide barrier.
-template <int K, int MODE, bool WS, bool EXT = false>
+// TFP = tile-level far-field blocks compiled in (K = 8 only; its own instantiation, so that the variant for windows of
+// a few thousand points carries none of its code)
+template <int K, int MODE, bool WS, bool EXT = false, bool TFP = false>
 __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RTX_MINBLOCKS_K4 : RTX_MINBLOCKS)) voigt_tile_kernel(const VoigtParams P) {
   constexpr bool FAST = (MODE == 1);
   constexpr bool F32 = (MODE == 2);
@@ -635,7 +666,10 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
 
   // automatic tile size without a host round trip: the K = 8 and the K = 4 grid are both launched and the one the
   // window statistic (window_stats_kernel) does not pick retires at once
-  if (P.sel != nullptr && ((P.sel[0] < RTX_K4_WINDOW) != (K == 4))) return;
+  if (P.sel != nullptr) {
+    const int want = (!P.sel_k8 && P.sel[0] < RTX_K4_WINDOW) ? 0 : ((P.sel_tf && P.sel[1] >= RTX_TF_WINDOW) ? 2 : 1);
+    if (want != (K == 4 ? 0 : TFP ? 2 : 1)) return;
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x % P.n_tiles;
   const int s = blockIdx.x / P.n_tiles;
@@ -681,21 +715,48 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
   // far-field reach of every slice: a line centred at or below s_far[q] (left of the slice) or at or above
   // s_far[8 + q] (right of it) is at least RTX_FAR_FRAC slice widths away from every point of slice q
   __shared__ double s_far[2 * (NT / 32)];
+  // tile-level far field: a line centred at or below s_tfar[0] / at or above s_tfar[1] is at least RTX_FAR_FRAC tile
+  // widths away from every point of the tile; s_tfar[2] = tile centre, s_tfar[3] = node half-width
+  __shared__ double s_tfar[4];
+  __shared__ unsigned s_mtile[NBUF][NBLK];
+  constexpr bool TF = TFP && (RTX_TILEFAR != 0) && !F32 && !WS;
+  const bool tfar_on = TF && P.tfar_ok != 0 && npts == TILE && !P.doppler;
   if (tid < NT / 32) {
     const double gf = s_grid[tid * (32 * K)], gl = s_grid[tid * (32 * K) + 32 * K - 1];
     const double D = RTX_FAR_FRAC * (gl - gf);
     s_far[tid] = gf - D;
     s_far[NT / 32 + tid] = gl + D;
   }
+  if (tid == 32) {
+    const double gf = s_grid[0], gl = s_grid[TILE - 1];
+    const double D = RTX_FAR_FRAC * (gl - gf);
+    s_tfar[0] = gf - D;
+    s_tfar[1] = gl + D;
+    s_tfar[2] = 0.5 * (gf + gl);
+    s_tfar[3] = 0.5 * (gl - gf) * ((double)TILE / (double)(TILE - 1));
+  }
   __syncthreads();
 
   double acc[K];
+  // this lane's K grid values: kept in shared memory and re-read per visit (RTX_W_SMEM, default) -- most visits are
+  // far-field node visits that never touch them, and the 2*K registers are worth more to the prologue
+#ifndef RTX_W_SMEM
+#define RTX_W_SMEM 1
+#endif
+  const double* __restrict__ wp = s_grid + (warp & (NT / 32 - 1)) * (32 * K) + lane;
+#if RTX_W_SMEM
+#define RTX_W(j) wp[(j) * 32]
+#else
   double w[K];
+#define RTX_W(j) w[j]
+#endif
   float w32[K], w32l[K], a32[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    w[j] = s_grid[(warp & (NT / 32 - 1)) * (32 * K) + j * 32 + lane];
-    const double off = w[j] - s_grid[0];                          // offset from the tile's first point, as hi + lo
+#if !RTX_W_SMEM
+    w[j] = wp[j * 32];
+#endif
+    const double off = wp[j * 32] - s_grid[0];                          // offset from the tile's first point, as hi + lo
     w32[j] = (float)off;
     w32l[j] = (float)(off - (double)w32[j]);
     a32[j] = 0.f;
@@ -716,6 +777,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
   }
   double accn = 0.0;
   bool far_used = false;
+  double acct = 0.0;          // this warp's share of the tile-level node sums (node = lane)
 
   TileScale ts;
   ts.g0 = s_grid[0];
@@ -741,19 +803,35 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       SegRec sr;
       sr.sub = 0;
       double h_keep = 0.0;
+      bool is_tfar = false;
       if (li < last) {
         LineState L = line_state<EXT>(P, li, s, T, p, lnr);
+        // Tile-level far field: the window covers the whole tile (the same comparisons the two searches below would
+        // make, misc/hapi.py:11133-11134), the line centre is >= RTX_FAR_FRAC tile widths away and no point of the tile
+        // is in the Weideman region (the predicate is monotone in |omega - nu0'|, so the nearest point decides).
+        // Such a line is evaluated once per tile at the tile's 32 Chebyshev nodes instead of once per slice.
+        double cte = 0.0, y = 0.0;
+        bool tf = false;
+        if (TF && tfar_on && (L.sg0 <= s_tfar[0] || L.sg0 >= s_tfar[1]) && (s_grid[0] > L.nu - L.W) &&
+            (s_grid[TILE - 1] <= L.nu + L.W) && !(EXT && P.sdv && L.gam2 != 0.0)) {
+          cte = RTX_SQRT_LN2 / L.gamD;
+          y = P.lorentz ? 1e300 : L.gam0 * cte;
+          tf = !(y < 15.0) || !in_weideman(L.sg0 <= s_tfar[0] ? s_grid[0] : s_grid[TILE - 1], L.sg0, cte, y);
+        }
         {
-          const int lo = count_le(s_grid, ts, L.nu - L.W);                // bisect(Omegas, nu-W), misc/hapi.py:11133
-          const int hi = count_le(s_grid, ts, L.nu + L.W);                // bisect(Omegas, nu+W), misc/hapi.py:11134
+          int lo = 0, hi = TILE;
+          if (!tf) {
+            lo = count_le(s_grid, ts, L.nu - L.W);                // bisect(Omegas, nu-W), misc/hapi.py:11133
+            hi = count_le(s_grid, ts, L.nu + L.W);                // bisect(Omegas, nu+W), misc/hapi.py:11134
+          }
           // the bins are cut with a per-state bound on the wing, so a good part of the candidates does not reach the
           // tile: their strength is never computed (blocks of 32 candidates are neighbours in nu, so whole warps skip)
           if (hi > lo) line_strength(P, li, s, T, L);
           if (hi > lo && L.keep) {
             // Lorentz profile Gam0/(pi*(Gam0^2+d^2)) (misc/hapi.py:10142-10150) = the closed form below with h = 0 and
             // no Weideman region
-            const double cte = RTX_SQRT_LN2 / L.gamD;                      // misc/hapi.py:9900
-            const double y = P.lorentz ? 1e300 : L.gam0 * cte;             // misc/hapi.py:9913
+            cte = RTX_SQRT_LN2 / L.gamD;                                   // misc/hapi.py:9900
+            y = P.lorentz ? 1e300 : L.gam0 * cte;                          // misc/hapi.py:9913
             const double h = P.lorentz ? 0.0 : L.gamD * L.gamD / RTX_LN2;  // 1/cte^2
             const double g2 = L.gam0 * L.gam0;
             const double a = L.amp * L.gam0 / RTX_PI;
@@ -767,7 +845,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
             sr.y = y;
             sr.cw = L.amp * (cte / RTX_SQRT_PI);
             int clo = lo, chi = lo;                                        // empty Weideman core
-            if (y < 15.0 && !P.doppler) {
+            if (y < 15.0 && !P.doppler && !tf) {
               // the mask |x|+y<15 is a contiguous index range around sg0; find it with the exact predicate
               // (exact predicate of hum1_wei; it is monotone on either side of sg0, so each end is found by a
               // short walk from the arithmetic estimate sg0 -+ (15-y)/cte, with bisection as the fallback)
@@ -814,7 +892,9 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
               }
             }
             sr.lo = (short)lo; sr.hi = (short)hi; sr.clo = (short)clo; sr.chi = (short)chi;
-            if (EXT && P.sdv && L.gam2 != 0.0) {
+            if (tf) {
+              is_tfar = true;                           // the whole tile at its 32 nodes; no other visit
+            } else if (EXT && P.sdv && L.gam2 != 0.0) {
               // speed-dependent line (Gamma2 != 0): the whole window goes to pass 2, evaluated with pcqsdhc PART2-4
               sr.a = L.gam0 - 1.5 * L.gam2;             // Re c0t
               sr.ah = L.gam2;
@@ -859,7 +939,11 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
         }
         wm = slice_masks<32 * K>(sr.lo, sr.hi, sr.clo, sr.chi, sr.sub != 0, K >= 4 && P.far_ok != 0, sr.sg0, s_far);   // K < 4: too few points per node to pay
       }
-      if (is_wide || has_seg) seg_b[k] = sr;
+      if (is_wide || has_seg || is_tfar) seg_b[k] = sr;
+      if (TF) {
+        const unsigned bt = __ballot_sync(0xffffffffu, is_tfar);
+        if (lane == 0) s_mtile[buf][blk] = bt;
+      }
       if (has_seg) {
 #pragma unroll
         for (int q = 0; q < NT / 32; ++q) sm |= ((sr.e > q * 32 * K) && (sr.s < (q + 1) * 32 * K) ? 1u : 0u) << q;
@@ -889,7 +973,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r_) : "f"(den_));                                       \
       a32[j] = fmaf(af, (u_ + hf) * r_, a32[j]);                                                      \
     } else {                                                                                          \
-      acc[j] = cheap_term<FAST>(w[j], sg0, a, ah, m, c, acc[j]);                                      \
+      acc[j] = cheap_term<FAST>(RTX_W(j), sg0, a, ah, m, c, acc[j]);                                      \
     }                                                                                                 \
   } while (0)
 #define RTX_VISIT_SETUP()                                                                             \
@@ -906,12 +990,32 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
   }
     // A warp owns 32*K contiguous points (lane-strided).  Windows that span the warp's slice take the test-free
     // path; only the slices holding a window end (or a Weideman core) pay for per-point predicates.
+    if (TF && tfar_on) {
+      // tile-level far-field visits: warp q takes records 4q..4q+3 of every block of 32 at the tile's 32 nodes
+      const double tc = s_tfar[2];
+      const double tx = s_tfar[3] * P.cheb[lane];
+#pragma unroll 1
+      for (int blk = 0; blk < NBLK; ++blk) {
+        unsigned mt = s_mtile[buf][blk] & (0xFu << (4 * warp));
+        const SegRec* __restrict__ trecs = s_seg + buf * LCHUNK + blk * 32;
+        while (mt & (mt - 1)) {
+          const SegRec& ra = trecs[__ffs(mt) - 1];
+          mt &= mt - 1;
+          const SegRec& rb = trecs[__ffs(mt) - 1];
+          mt &= mt - 1;
+          acct = cheap_pair_d<FAST>((tc - ra.sg0) + tx, ra.a, ra.ah, ra.m, ra.c, (tc - rb.sg0) + tx, rb.a, rb.ah, rb.m, rb.c,
+                                    acct);
+        }
+        if (mt) {
+          const SegRec& ra = trecs[__ffs(mt) - 1];
+          acct = cheap_d<FAST>((tc - ra.sg0) + tx, ra.a, ra.ah, ra.m, ra.c, acct);
+        }
+      }
+    }
+    // far-field visits: the line is evaluated at this slice's 32 Chebyshev nodes only (one per lane)
 #pragma unroll 1
     for (int blk = 0; blk < NBLK; ++blk) {
-      const P1Rec* __restrict__ recs = (F32 ? reinterpret_cast<const P1Rec*>(s_wide) : reinterpret_cast<const P1Rec*>(s_seg)) +
-                                       buf * LCHUNK + blk * 32;
       {
-        // far-field visits: the line is evaluated at this slice's 32 Chebyshev nodes only (one per lane)
         const SegRec* __restrict__ frecs = s_seg + buf * LCHUNK + blk * 32;
         unsigned mf = s_mfar[buf][blk][warp];
         if (mf) far_used = true;
@@ -928,6 +1032,11 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
           accn = cheap_d<FAST>((sl_c - ra.sg0) + xoff, ra.a, ra.ah, ra.m, ra.c, accn);
         }
       }
+    }
+#pragma unroll 1
+    for (int blk = 0; blk < NBLK; ++blk) {
+      const P1Rec* __restrict__ recs = (F32 ? reinterpret_cast<const P1Rec*>(s_wide) : reinterpret_cast<const P1Rec*>(s_seg)) +
+                                       buf * LCHUNK + blk * 32;
       unsigned m = s_mfull[buf][blk][warp];
 #ifdef RTX_DBG_SKIP_FULL
       m = 0;
@@ -942,7 +1051,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
           const double sg1 = ra.sg0, a1 = ra.a, ah1 = ra.ah, m1 = ra.m, c1 = ra.c;
           const double sg2 = rb.sg0, a2 = rb.a, ah2 = rb.ah, m2 = rb.m, c2 = rb.c;
 #pragma unroll
-          for (int j = 0; j < K; ++j) acc[j] = cheap_pair<FAST>(w[j], sg1, a1, ah1, m1, c1, sg2, a2, ah2, m2, c2, acc[j]);
+          for (int j = 0; j < K; ++j) acc[j] = cheap_pair<FAST>(RTX_W(j), sg1, a1, ah1, m1, c1, sg2, a2, ah2, m2, c2, acc[j]);
         }
       }
       while (m) {
@@ -1136,20 +1245,35 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
   }
 
   // ---- far-field epilogue: node sums -> Chebyshev coefficients (lane m holds c_m) -> Clenshaw at the slice's points
-  if (far_used) {                                  // warp-uniform
+  // (slice level first, then the tile level: the eight warps' shares are summed in warp order through shared memory)
+  double tsum = 0.0;
+  if (TF && tfar_on) {                             // block-uniform; the chunk loop ended with a barrier
+    double* s_t = reinterpret_cast<double*>(s_seg);
+    s_t[warp * 32 + lane] = acct;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NT / 32; ++q) tsum += s_t[q * 32 + lane];
+  }
+  const bool tile_used = TF && __any_sync(0xffffffffu, tsum != 0.0);
+#pragma unroll 1
+  for (int level = 0; level < (TF ? 2 : 1); ++level) {
+    if (level == 0 ? !far_used : !tile_used) continue;   // warp-uniform
+    const double nodes = level == 0 ? accn : tsum;
     const double* __restrict__ dct = P.cheb + 32;  // [k][m] = (2 - [m==0])/32 * cos(m*theta_k)
     double cm = 0.0;
 #pragma unroll 8
-    for (int k = 0; k < 32; ++k) cm = fma(__shfl_sync(0xffffffffu, accn, k), dct[k * 32 + lane], cm);
+    for (int k = 0; k < 32; ++k) cm = fma(__shfl_sync(0xffffffffu, nodes, k), dct[k * 32 + lane], cm);
     const double sl_first = s_grid[own_w * (32 * K)], sl_last = s_grid[own_w * (32 * K) + 32 * K - 1];
-    const double inv_hw = 1.0 / (0.5 * (sl_last - sl_first) * ((double)(32 * K) / (double)(32 * K - 1)));
+    const double inv_hw = level == 0 ? 1.0 / (0.5 * (sl_last - sl_first) * ((double)(32 * K) / (double)(32 * K - 1)))
+                                     : 1.0 / s_tfar[3];
+    const double ctr = level == 0 ? 0.5 * (sl_first + sl_last) : s_tfar[2];
     const double c0 = __shfl_sync(0xffffffffu, cm, 0);
     constexpr int G = K < 4 ? K : 4;               // rows per Clenshaw sweep (register budget)
 #pragma unroll
     for (int j0 = 0; j0 < K; j0 += G) {
       double x2[G], b1[G], b2[G];
 #pragma unroll
-      for (int j = 0; j < G; ++j) { x2[j] = 2.0 * ((w[j0 + j] - sl_c) * inv_hw); b1[j] = 0.0; b2[j] = 0.0; }
+      for (int j = 0; j < G; ++j) { x2[j] = 2.0 * ((RTX_W(j0 + j) - ctr) * inv_hw); b1[j] = 0.0; b2[j] = 0.0; }
 #pragma unroll 1
       for (int mm = 31; mm >= 1; --mm) {
         const double cc = __shfl_sync(0xffffffffu, cm, mm);
@@ -1226,13 +1350,13 @@ size_t tile_smem_bytes() {
                                       (sizeof(SegRec) + (MODE == 2 ? sizeof(WideRec) : 0));
 }
 
-template <int K, int MODE, bool WS, bool EXT = false>
+template <int K, int MODE, bool WS, bool EXT = false, bool TFP = false>
 int launch_tile(const VoigtParams& P, cudaStream_t st) {
   const size_t smem = tile_smem_bytes<K, MODE, WS>();
-  RTX_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<K, MODE, WS, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RTX_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<K, MODE, WS, EXT, TFP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t blocks = (int64_t)P.n_tiles * P.n_states;
   if (blocks > 2147483647LL) { rtx_set_error("rtx_voigt_sum: too many (tile, state) pairs for one launch"); return RTX_E_INVALID; }
-  voigt_tile_kernel<K, MODE, WS, EXT><<<(unsigned)blocks, WS ? NT + 32 * NPW : NT, smem, st>>>(P);
+  voigt_tile_kernel<K, MODE, WS, EXT, TFP><<<(unsigned)blocks, WS ? NT + 32 * NPW : NT, smem, st>>>(P);
   RTX_CUDA(cudaGetLastError());
   return RTX_OK;
 }
@@ -1286,7 +1410,7 @@ int fill_params(rtx_handle* h, VoigtParams& P, int n_states, const double* T, co
 
 int run_prep(rtx_handle* h, VoigtParams& P, cudaStream_t st, double** st_wb_out) {
   const size_t per = (size_t)P.n_states * P.n_iso;
-  int rc = ensure_scratch(h, 2 * per + P.n_states + 2, h->bins_cap);
+  int rc = ensure_scratch(h, 2 * per + 2 * (size_t)P.n_states + 2, h->bins_cap);
   if (rc) return rc;
   double* st_q = h->d_state;
   double* st_d = st_q + per;
@@ -1298,6 +1422,8 @@ int run_prep(rtx_handle* h, VoigtParams& P, cudaStream_t st, double** st_wb_out)
   Q.x_air = P.x_air; Q.x_self = P.x_self; Q.wing_abs = P.wing_abs; Q.wing_hw = P.wing_hw;
   Q.nu_max = L.nu_max; Q.gair_max = L.gair_max; Q.gself_max = L.gself_max; Q.nair_min = L.nair_min;
   Q.nair_max = L.nair_max; Q.nself_min = L.nself_min; Q.nself_max = L.nself_max;
+  Q.gair_typ = L.gair_typ; Q.gself_typ = L.gself_typ; Q.nair_typ = L.nair_typ; Q.nself_typ = L.nself_typ;
+  Q.st_wt = st_wb + P.n_states;
   Q.doppler = P.doppler;
   Q.n_extra = P.n_extra;
   for (int e = 0; e < RTX_MAX_EXTRA_DILUENTS; ++e) {
@@ -1345,28 +1471,41 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
     const int64_t tiles = (nx + (int64_t)k * NT - 1) / ((int64_t)k * NT);
     if (tiles * n_states >= 4LL * h->sm_count) { K = k; break; }
   }
+  const int mode = (flags & RTX_VOIGT_FP32) ? 2 : ((flags & RTX_VOIGT_EXACT_RCP) ? 0 : 1);
+  const bool ws = (flags & RTX_VOIGT_WARPSPEC) != 0;
+  // speed dependence / extra broadening species: the extended instantiation (FP64, not warp-specialised)
+  const bool ext = P.sdv || P.n_extra > 0;
+  P.far_ok = (flags & RTX_VOIGT_NOFAR) ? 0 : 1;
+  P.tfar_ok = (flags & (RTX_VOIGT_NOFAR | RTX_VOIGT_NOTILEFAR)) ? 0 : 1;
+  // the variant with tile-level far-field blocks exists for K = 8, FP64, not warp-specialised
+  const bool tf_variant = P.tfar_ok && !P.doppler && (ext || (!ws && mode != 2));
   const int forced = (flags >> RTX_VOIGT_TILE_SHIFT) & 0xF;   // test hook: force the tile size
-  bool both = false;                                          // K = 8 and K = 4 grids, chosen on the device
+  bool with4 = false;                                         // K = 8 and K = 4 grids, chosen on the device
   if (forced == 1 || forced == 2 || forced == 4 || forced == 8) {
     K = forced;
   } else if (K == 8) {
     // narrow windows (coarse grids, low pressures): smaller slices turn partial visits into test-free ones and
-    // four CTAs per SM hide the per-visit latency.  The eval-weighted mean window decides -- on the device: both grids
-    // are launched and the kernels of the size not chosen return at once, so the call never waits for the GPU.
-    double* stat = st_wb + n_states;
-    window_stats_kernel<<<1, 256, 0, st>>>(n_states, st_wb, grid_dev, nx, stat);
+    // four CTAs per SM hide the per-visit latency.  The eval-weighted mean window decides -- on the device: every
+    // candidate grid is launched and the kernels of the variants not chosen return at once, so the call never waits
+    // for the GPU.
+    with4 = true;
+  }
+  const bool with_tf = (K == 8) && tf_variant;
+  P.sel = nullptr; P.sel_k8 = with4 ? 0 : 1; P.sel_tf = with_tf ? 1 : 0;
+  if (with4 || with_tf) {
+    double* stat = st_wb + 2 * (size_t)n_states;
+    window_stats_kernel<<<1, 256, 0, st>>>(n_states, st_wb, st_wb + n_states, grid_dev, nx, stat);
     RTX_CUDA(cudaGetLastError());
     h->launches++;
     P.sel = stat;
-    both = true;
   }
-  h->last_K = both ? -1 : K;
-  h->d_last_stat = both ? P.sel : nullptr;
+  h->last_K = with4 ? -1 : K;
+  h->d_last_stat = with4 ? P.sel : nullptr;
   h->last_stream = stream;
   const int tile_pts = K * NT;
   P.n_tiles = (int)((nx + tile_pts - 1) / tile_pts);
   const size_t nb = (size_t)P.n_tiles * n_states;
-  const int n_tiles4 = both ? (int)((nx + 4 * NT - 1) / (4 * NT)) : 0;
+  const int n_tiles4 = with4 ? (int)((nx + 4 * NT - 1) / (4 * NT)) : 0;
   const size_t nb4 = (size_t)n_tiles4 * n_states;
   rc = ensure_scratch(h, h->state_cap, 2 * (nb + nb4));
   if (rc) return rc;
@@ -1375,7 +1514,7 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
                                                           st_wb, h->d_bins);
   RTX_CUDA(cudaGetLastError());
   h->launches++;
-  if (both) {
+  if (with4) {
     bin_kernel<<<(unsigned)((nb4 + 255) / 256), 256, 0, st>>>(n_states, n_tiles4, 4 * NT, grid_dev, nx, P.nu, P.n_lines,
                                                              st_wb, h->d_bins + 2 * nb);
     RTX_CUDA(cudaGetLastError());
@@ -1395,13 +1534,8 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
     RTX_CUDA(cudaStreamSynchronize(st));   // tab is a local
   }
   P.cheb = h->d_cheb;
-  P.far_ok = (flags & RTX_VOIGT_NOFAR) ? 0 : 1;
   // default: paired evaluations through a reciprocal with ONE Newton step (relative error <= 2^-40 ~ 9e-13 per term);
   // RTX_VOIGT_EXACT_RCP adds the second step (full double precision)
-  const int mode = (flags & RTX_VOIGT_FP32) ? 2 : ((flags & RTX_VOIGT_EXACT_RCP) ? 0 : 1);
-  const bool ws = (flags & RTX_VOIGT_WARPSPEC) != 0;
-  // speed dependence / extra broadening species: the extended instantiation (FP64, not warp-specialised)
-  const bool ext = P.sdv || P.n_extra > 0;
 #define RTX_LAUNCH(KK)                                                                                        \
   (ext ? (mode == 0 ? launch_tile<KK, 0, false, true>(P, st) : launch_tile<KK, 1, false, true>(P, st))          \
    : ws ? (mode == 2 ? launch_tile<KK, 2, true>(P, st) : mode == 1 ? launch_tile<KK, 1, true>(P, st) : launch_tile<KK, 0, true>(P, st)) \
@@ -1414,7 +1548,13 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
   }
   if (rc) return rc;
   h->launches++;
-  if (both) {                                   // the K = 4 grid of the same call
+  if (with_tf) {                                // K = 8 with the tile-level blocks
+    rc = ext ? (mode == 0 ? launch_tile<8, 0, false, true, true>(P, st) : launch_tile<8, 1, false, true, true>(P, st))
+             : (mode == 0 ? launch_tile<8, 0, false, false, true>(P, st) : launch_tile<8, 1, false, false, true>(P, st));
+    if (rc) return rc;
+    h->launches++;
+  }
+  if (with4) {                                  // the K = 4 grid of the same call
     P.n_tiles = n_tiles4;
     P.bins = h->d_bins + 2 * nb;
     K = 4;

@@ -752,6 +752,60 @@ def test_continuum_hook(mods):
     assert_parity(ODf, OD0 + nL * ramp, RTOL, FLOOR, "OD with callable continuum")
 
 
+def test_voigt_tile_level_far_field(mods):
+    """Tile-level far-field blocks (a line whose window covers a whole 2048-point tile from >= 0.375 tile widths away is
+    summed once at the tile's 32 Chebyshev nodes): with wings of thousands of grid points -- the regime of the
+    reference's own cross-section script, WavenumberWingHW=350 (misc/RT_gen_AbsXS_files.py:18,90) -- the kernel variant
+    that carries them is chosen on the device.  It agrees with the slice-level-only evaluation (RTX_VOIGT_NOTILEFAR) and
+    with the node-free one to 2e-13, with the oracle to the parity tolerance, on uniform, two-spacing and jittered
+    grids; the speed-dependent / extra-diluent instantiation takes the same path."""
+    import make_golden as mg
+    port, syn, engine, hapi = mods["port"], mods["syn"], mods["engine"], mods["hapi"]
+    cols = syn.synthetic_lines(61, 300, 960.0, 1040.0, 1)
+    cols["sw"][::41] *= 1e6
+    db = engine.LineDB(cols)
+    states = [(296.0, 1.0), (250.0, 0.3)]
+    T = np.array([s[0] for s in states]); p = np.array([s[1] for s in states])
+    w = np.tile(db.iso_factors(None, 1.0), (len(states), 1))
+    rng = np.random.default_rng(9)
+    uniform = np.linspace(975.0, 1025.0, 100001)                       # 0.0005 cm^-1: 48 full tiles and a partial one
+    two_step = np.concatenate([np.linspace(975.0, 1000.0, 75001)[:-1], np.linspace(1000.0, 1025.0, 25001)])
+    jitter = np.sort(uniform + rng.uniform(-1e-4, 1e-4, uniform.size))
+    K8 = 8 << 8
+    for name, grid, wing in (("uniform", uniform, 8.0), ("two_step", two_step, 8.0), ("jitter", jitter, 6.0),
+                             ("hw350", uniform, 0.0)):
+        kw = dict(wing_abs=wing) if wing else dict(wing_hw=350.0)
+        tile = db.voigt_sum(T, p, w, grid, flags=128 | K8, **kw).cpu().numpy()
+        slice_only = db.voigt_sum(T, p, w, grid, flags=128 | 16384 | K8, **kw).cpu().numpy()
+        exact = db.voigt_sum(T, p, w, grid, flags=128 | 4096 | K8, **kw).cpu().numpy()
+        assert not np.array_equal(tile, slice_only), name                                   # path taken
+        assert np.max(np.abs(tile - exact) / np.maximum(exact, 1e-300)) < 2e-13, name
+        assert np.max(np.abs(slice_only - exact) / np.maximum(exact, 1e-300)) < 2e-13, name
+        dflt = db.voigt_sum(T, p, w, grid, flags=K8, **kw).cpu().numpy()
+        assert np.max(np.abs(dflt - exact) / np.maximum(exact, 1e-300)) < 5e-12, name       # plus the one-step reciprocal
+        okw = dict(OmegaWing=wing) if wing else dict(OmegaWingHW=350.0)
+        _, ref = port.absorption_coefficient_voigt(cols, T=states[0][0], p=states[0][1], OmegaGrid=grid, **okw)
+        assert_parity(dflt[0], ref, RTOL, FLOOR, "tile-level far field, %s" % name)
+    # narrow wings on the same grid: the statistic keeps the variant without tile-level blocks (identical bits)
+    a = db.voigt_sum(T, p, w, uniform, flags=K8, wing_abs=1.0).cpu().numpy()
+    b = db.voigt_sum(T, p, w, uniform, flags=K8 | 16384, wing_abs=1.0).cpu().numpy()
+    assert np.array_equal(a, b)
+    # speed-dependent lines and an extra diluent with the reference script's wing (extended instantiation)
+    sd = dict(mg.sdv_table())
+    sd["SD_air"] = np.where(np.arange(300) % 2, sd["SD_air"], 0.0)     # lines without speed dependence take the Voigt path
+    hapi.storeTable("sdv_wide", sd)
+    fine = np.linspace(1235.0, 1265.0, 60001)
+    dil = {"air": 0.7, "h2": 0.3}
+    _, xs = hapi.absorptionCoefficient_SDVoigt(SourceTables="sdv_wide", Environment={"T": 280.0, "p": 0.8},
+                                               OmegaGrid=fine, Diluent=dil, WavenumberWingHW=350, _profile_flags=K8)
+    _, xs0 = hapi.absorptionCoefficient_SDVoigt(SourceTables="sdv_wide", Environment={"T": 280.0, "p": 0.8},
+                                                OmegaGrid=fine, Diluent=dil, WavenumberWingHW=350,
+                                                _profile_flags=K8 | 16384)
+    assert not np.array_equal(xs, xs0)
+    _, ref = port.absorption_coefficient_sdvoigt(sd, T=280.0, p=0.8, OmegaGrid=fine, Diluent=dil, OmegaWingHW=350.0)
+    assert_parity(xs, ref, RTOL, FLOOR, "SDVoigt, WavenumberWingHW=350")
+
+
 def test_voigt_automatic_tile_size(mods):
     """Automatic tile size: 2048-point tiles when the windows are thousands of grid points wide (fine grid, low
     layers), 1024-point tiles at four CTAs per SM when they are a few hundred (coarse grid) -- decided from the

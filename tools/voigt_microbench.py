@@ -35,25 +35,28 @@ def main():
     od = torch.empty((66, X.size), dtype=torch.float64, device="cuda")
     if only is None:
         a0 = db.voigt_sum(T, pd, wd, grid, flags=128 | 4096).clone()          # exact reciprocal, no far-field blocks
-        for name, fl in (("default (one-step rcp + far-field)", 0), ("far-field only", 128), ("one-step rcp only", 4096)):
+        for name, fl in (("default (one-step rcp + far-field)", 0), ("far-field only", 128), ("one-step rcp only", 4096),
+                         ("slice-level far-field only", 128 | 16384)):
             a1 = db.voigt_sum(T, pd, wd, grid, flags=fl)
             rel = ((a1 - a0).abs() / a0.abs().clamp_min(1e-300)).max().item()
             print("max relative deviation of %s vs exact: %.3e" % (name, rel), flush=True)
         del a0, a1
     cases = []
     for K in (8,):
-        for fast in (0, 128, 4096, 128 | 4096, 2, 4):
+        for fast in (0, 16384, 128, 4096, 128 | 4096, 2, 4):
             cases.append(("cfg2 K=%d flags=%d" % (K, fast), dict(flags=fast | (K << 8)), T, pd, wd))
     # all-wide: every line +-25 cm^-1 -> almost every visit takes the test-free path
     cases.append(("wide25 K=8 fast=0", dict(flags=8 << 8, wing_abs=25.0), T[:8], pd[:8], wd[:8]))
+    cases.append(("wide25 K=8 notile", dict(flags=16384 | (8 << 8), wing_abs=25.0), T[:8], pd[:8], wd[:8]))
     cases.append(("wide25 K=8 nofar", dict(flags=4096 | (8 << 8), wing_abs=25.0), T[:8], pd[:8], wd[:8]))
     cases.append(("wide25 K=8 fp32", dict(flags=2 | (8 << 8), wing_abs=25.0), T[:8], pd[:8], wd[:8]))
     cases.append(("wide25 K=4 fast=0", dict(flags=4 << 8, wing_abs=25.0), T[:8], pd[:8], wd[:8]))
     # per-layer groups of config 2
     for name, sl in (("layers 0-9", slice(0, 10)), ("layers 10-29", slice(10, 30)), ("layers 30-49", slice(30, 50)),
                      ("layers 50-65", slice(50, 66))):
-        for K in (8, 4, 2):
+        for K in (8, 4):
             cases.append((name + " K=%d" % K, dict(flags=K << 8), T[sl], pd[sl], wd[sl].contiguous()))
+        cases.append((name + " K=8 notile", dict(flags=16384 | (8 << 8)), T[sl], pd[sl], wd[sl].contiguous()))
     for name, kw, Tt, pp, ww in cases:
         if only is not None and only not in name.replace(" ", "_"):
             continue
