@@ -132,10 +132,13 @@ struct VoigtParams {
   const double* cheb;   // [32] Chebyshev nodes cos(theta_k), then [32][32] node-values -> coefficients matrix [k][m]
   int far_ok;    // far-field blocks enabled
   int tfar_ok;   // tile-level far-field blocks enabled (whole tiles at 32 nodes)
-  // device-side choice of the kernel variant (null = run): sel[0] = eval-weighted mean wing bound, sel[1] = typical
-  // wing, both in grid points.  Variant 0 (K = 4): sel[0] < RTX_K4_WINDOW unless sel_k8; variant 2 (K = 8 with the
-  // tile-level far-field blocks): sel[1] >= RTX_TF_WINDOW and sel_tf; variant 1 (K = 8 without) otherwise.
+  // device-side choice of the kernel variant, per state (null = run): sel[2] = 1 / mean grid spacing; st_wb / st_wt =
+  // the state's wing bound / typical wing.  Variant 0 (K = 4): wing bound < RTX_K4_WINDOW grid points unless sel_k8;
+  // variant 2 (K = 8 with the tile-level far-field blocks): typical wing >= RTX_TF_WINDOW points and sel_tf; variant 1
+  // (K = 8 without) otherwise.  The grids of all candidate variants are launched; a CTA of a variant its state does
+  // not pick returns at once.  sel[0], sel[1]: the launch-wide eval-weighted means (reporting only).
   const double* sel;
+  const double *st_wb, *st_wt;
   int sel_k8, sel_tf;
   int lorentz;   // PROFILE_LORENTZ instead of PROFILE_VOIGT: no Doppler width, wing = max(OmegaWing, HW*Gamma0)
   int doppler;   // PROFILE_DOPPLER (absorptionCoefficient_Doppler): 1 = with line shift, 2 = LineShift=False
@@ -552,6 +555,7 @@ __global__ void window_stats_kernel(int n_states, const double* __restrict__ st_
     const double dv = nx > 1 ? (grid[nx - 1] - grid[0]) / (double)(nx - 1) : 0.0;
     out[0] = (s2[0] > 0.0 && dv > 0.0) ? (s1[0] / s2[0]) / dv : 1e300;
     out[1] = (s4[0] > 0.0 && dv > 0.0) ? (s3[0] / s4[0]) / dv : 1e300;
+    out[2] = dv > 0.0 ? 1.0 / dv : 1e300;
   }
 }
 
@@ -666,13 +670,15 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
 
   // automatic tile size without a host round trip: the K = 8 and the K = 4 grid are both launched and the one the
   // window statistic (window_stats_kernel) does not pick retires at once
-  if (P.sel != nullptr) {
-    const int want = (!P.sel_k8 && P.sel[0] < RTX_K4_WINDOW) ? 0 : ((P.sel_tf && P.sel[1] >= RTX_TF_WINDOW) ? 2 : 1);
-    if (want != (K == 4 ? 0 : TFP ? 2 : 1)) return;
-  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x % P.n_tiles;
   const int s = blockIdx.x / P.n_tiles;
+  if (P.sel != nullptr) {
+    const double inv_dv = P.sel[2];
+    const int want = (!P.sel_k8 && P.st_wb[s] * inv_dv < RTX_K4_WINDOW) ? 0
+                     : ((P.sel_tf && P.st_wt[s] * inv_dv >= RTX_TF_WINDOW) ? 2 : 1);
+    if (want != (K == 4 ? 0 : TFP ? 2 : 1)) return;
+  }
   const int64_t p0 = (int64_t)tile * TILE;
   const int npts = (int)min((int64_t)TILE, P.nx - p0);
 
@@ -1410,7 +1416,7 @@ int fill_params(rtx_handle* h, VoigtParams& P, int n_states, const double* T, co
 
 int run_prep(rtx_handle* h, VoigtParams& P, cudaStream_t st, double** st_wb_out) {
   const size_t per = (size_t)P.n_states * P.n_iso;
-  int rc = ensure_scratch(h, 2 * per + 2 * (size_t)P.n_states + 2, h->bins_cap);
+  int rc = ensure_scratch(h, 2 * per + 2 * (size_t)P.n_states + 4, h->bins_cap);
   if (rc) return rc;
   double* st_q = h->d_state;
   double* st_d = st_q + per;
@@ -1433,6 +1439,7 @@ int run_prep(rtx_handle* h, VoigtParams& P, cudaStream_t st, double** st_wb_out)
   RTX_CUDA(cudaGetLastError());
   h->launches++;
   P.st_q = st_q; P.st_d = st_d;
+  P.st_wb = st_wb; P.st_wt = st_wb + P.n_states;
   *st_wb_out = st_wb;
   return RTX_OK;
 }
