@@ -135,12 +135,17 @@ int rtx_tape3_read(const char* path, double vmin, double vmax, int64_t capacity,
                                  * at 32 Chebyshev nodes and interpolated, relative error < 1e-13) */
 #define RTX_VOIGT_NOTILEFAR 16384 /* keep the slice-level far-field blocks but not the tile-level ones (a line whose window
                                  * covers a whole tile from >= 0.375 tile widths away is summed at the tile's 32 nodes) */
+#define RTX_VOIGT_TILEFAR 32768  /* use the tile-level far-field blocks wherever a line qualifies (default: only for states
+                                 * whose typical wing is >= 4000 grid points and whose tiles see >= 600 such lines -- below
+                                 * that the kernel variant without them is faster) */
 #define RTX_VOIGT_SDVOIGT 8192  /* absorptionCoefficient_SDVoigt (misc/hapi.py:10657-10905): lines whose Gamma2 = sum_d x_d
                                  * SD_d p gamma_d is non-zero take the quadratic speed-dependent profile (pcqsdhc PART2-4,
                                  * misc/hapi.py:9923-10020); the rest is the Voigt driver */
 #define RTX_VOIGT_TILE_SHIFT 8 /* bits 8..11: force 256*K grid points per CTA, K in {1,2,4,8} (0 = automatic).
-                                * The automatic choice between K = 8 and K = 4 is made on the device (both grids are
-                                * launched, the one not chosen retires at once), so the call never synchronises;
+                                * The automatic choice between K = 8 and K = 4, and between the K = 8 kernel with and
+                                * without tile-level far-field blocks, is made on the device, per state, from the state's
+                                * wing in grid points (the grids of all candidates are launched; a CTA of a variant its
+                                * state does not pick retires at once), so the call never synchronises;
                                 * force K to pin the summation order (e.g. for bit-identical sharded results). */
 int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, const double* p_dev,
                   const double* weight_dev, double x_air, double x_self, double wing_abs, double wing_hw,
@@ -292,7 +297,8 @@ int rtx_weideman_coeffs(double* out24);
 /* Number of kernels this library has launched on this handle since creation. */
 int rtx_launch_count(rtx_handle* h, uint64_t* n);
 /* Tile size the last rtx_voigt_sum on this handle used: K = grid points per CTA / 256 (0 before the first call).  When
- * the size was chosen on the device this reads 8 bytes back and synchronises the stream of that call. */
+ * the size was chosen on the device (per state) this reports the choice the launch-wide eval-weighted mean wing bound
+ * would make -- the size most of the work ran at; it reads 8 bytes back and synchronises the stream of that call. */
 int rtx_voigt_last_tile(rtx_handle* h, int* K);
 
 #ifdef __cplusplus

@@ -86,6 +86,12 @@ struct ChunkCfg {
 #ifndef RTX_TF_WINDOW
 #define RTX_TF_WINDOW 4000.0
 #endif
+// ... and the estimated number of lines per tile that qualify (2 * line density * (typical wing - 1.375 tile widths)) from
+// which it pays: with a few hundred lines per tile the CTA is bound by the latency of its prologue, not by its visits
+// (measured: 1150 qualifying lines per tile 11 % faster, 220 lines 5 % slower; tools/xs_breakdown.py)
+#ifndef RTX_TF_MINLINES
+#define RTX_TF_MINLINES 600.0
+#endif
 #ifndef RTX_NARROW_MAX
 #define RTX_NARROW_MAX 128
 #endif
@@ -140,6 +146,7 @@ struct VoigtParams {
   const double* sel;
   const double *st_wb, *st_wt;
   int sel_k8, sel_tf;
+  double dens;   // lines per cm^-1 of the table (the tile-level blocks pay only when many lines reach over whole tiles)
   int lorentz;   // PROFILE_LORENTZ instead of PROFILE_VOIGT: no Doppler width, wing = max(OmegaWing, HW*Gamma0)
   int doppler;   // PROFILE_DOPPLER (absorptionCoefficient_Doppler): 1 = with line shift, 2 = LineShift=False
 };
@@ -401,6 +408,36 @@ __device__ __noinline__ double sdvoigt_re(double d, double c0tr, double gam2, do
     w_hum1_wei(x1, y2, w2r, w2i);
   }
   return (cte * RTX_INV_SQRT_PI) * (w1r - w2r);
+}
+
+// Far wing of the speed-dependent profile.  Where pcqsdhc takes PART4 (neither |X| <= 3e-8 |Y| nor |Y| <= 1e-15 |X|,
+// misc/hapi.py:9923, 9968) and both w(Z) come from the one-term asymptote of hum1_wei (|x|+y >= 15 for Z1 and Z2, which
+// also rules cpf3 out: |Z| >= 15/sqrt(2) > 8), the profile is  cte/sqrt(pi) * Re[w1(Z1) - w1(Z2)],  w1 = t/(0.5+t^2)/sqrt(pi),
+// an analytic function of omega whose singularities sit within a few widths of the line centre -- so it can be summed at
+// the Chebyshev nodes of a far slice or tile like the Voigt closed form.  |X|, |Im sqrt(X+Y)| and Re sqrt(X+Y) grow with
+// |omega - nu0'|, so the branch conditions hold on a whole block when they hold at its nearest point (asymptotes, not
+// PART2) and at its farthest point (not PART3).
+// rec: a = Re c0t = Gam0 - 1.5 Gam2, g2 = Gam2, cte;  precomputed ig2 = 1/Gam2, h = 1/(2 cte Gam2).
+__device__ __forceinline__ bool sdv_far_ok(double d_near, double d_far, double c0tr, double gam2, double cte) {
+  const double xr = c0tr / gam2, h = 1.0 / (2.0 * cte * gam2), Y = h * h;
+  const double xin = -d_near / gam2, xif = -d_far / gam2;
+  const double axn = hypot(xr, xin), axf = hypot(xr, xif);
+  if (axn <= 3.0e-8 * Y || Y <= 1.0e-15 * axf || Y <= 1.0e-15 * axn || !(h > 0.0)) return false;
+  double sr, si;
+  csqrt_dev(xr + Y, xin, sr, si);
+  return fabs(si) + (sr - h) >= 15.0 + 1e-9 && (sr - h) > 0.0;   // Z1 = (-si) + i (sr - h); Z2 has the larger y
+}
+// value at distance d from the (shifted) centre, without the amplitude
+__device__ __forceinline__ double sdv_far_term(double d, double c0tr, double gam2, double cte) {
+  const double xr = c0tr / gam2, xi = -d / gam2, h = 1.0 / (2.0 * cte * gam2);
+  double sr, si;
+  csqrt_dev(xr + h * h, xi, sr, si);
+  const double x = -si, x2 = x * x, y1 = sr - h, y2 = sr + h;
+  // Re w1(x + i y) = y (0.5 + x^2 + y^2) / ((0.5 + y^2 - x^2)^2 + 4 x^2 y^2) / sqrt(pi)
+  const double e1 = 0.5 + y1 * y1 - x2, e2 = 0.5 + y2 * y2 - x2;
+  const double w1 = y1 * (0.5 + x2 + y1 * y1) / fma(e1, e1, 4.0 * x2 * y1 * y1);
+  const double w2 = y2 * (0.5 + x2 + y2 * y2) / fma(e2, e2, 4.0 * x2 * y2 * y2);
+  return (cte * (RTX_INV_SQRT_PI * RTX_INV_SQRT_PI)) * (w1 - w2);
 }
 
 struct __align__(16) WideRec {
@@ -675,8 +712,11 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
   const int s = blockIdx.x / P.n_tiles;
   if (P.sel != nullptr) {
     const double inv_dv = P.sel[2];
-    const int want = (!P.sel_k8 && P.st_wb[s] * inv_dv < RTX_K4_WINDOW) ? 0
-                     : ((P.sel_tf && P.st_wt[s] * inv_dv >= RTX_TF_WINDOW) ? 2 : 1);
+    const double wt = P.st_wt[s];
+    const bool tf = P.sel_tf == 2 ||                      // RTX_VOIGT_TILEFAR: wherever a line qualifies
+                    (P.sel_tf && wt * inv_dv >= RTX_TF_WINDOW &&
+                     2.0 * P.dens * (wt * inv_dv - 1.375 * 2048.0) >= RTX_TF_MINLINES * inv_dv);   // est. lines that qualify per tile
+    const int want = (!P.sel_k8 && P.st_wb[s] * inv_dv < RTX_K4_WINDOW) ? 0 : (tf ? 2 : 1);
     if (want != (K == 4 ? 0 : TFP ? 2 : 1)) return;
   }
   const int64_t p0 = (int64_t)tile * TILE;
@@ -725,6 +765,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
   // widths away from every point of the tile; s_tfar[2] = tile centre, s_tfar[3] = node half-width
   __shared__ double s_tfar[4];
   __shared__ unsigned s_mtile[NBUF][NBLK];
+  __shared__ unsigned s_msdf[NBUF][EXT ? NBLK : 1][NT / 32];   // speed-dependent lines: slices summed at their nodes
   constexpr bool TF = TFP && (RTX_TILEFAR != 0) && !F32 && !WS;
   const bool tfar_on = TF && P.tfar_ok != 0 && npts == TILE && !P.doppler;
   if (tid < NT / 32) {
@@ -810,6 +851,7 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       sr.sub = 0;
       double h_keep = 0.0;
       bool is_tfar = false;
+      unsigned sdf = 0;
       if (li < last) {
         LineState L = line_state<EXT>(P, li, s, T, p, lnr);
         // Tile-level far field: the window covers the whole tile (the same comparisons the two searches below would
@@ -818,11 +860,15 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
         // Such a line is evaluated once per tile at the tile's 32 Chebyshev nodes instead of once per slice.
         double cte = 0.0, y = 0.0;
         bool tf = false;
+        const bool sdline = EXT && P.sdv && L.gam2 != 0.0;   // speed-dependent line: pcqsdhc instead of the Voigt profile
         if (TF && tfar_on && (L.sg0 <= s_tfar[0] || L.sg0 >= s_tfar[1]) && (s_grid[0] > L.nu - L.W) &&
-            (s_grid[TILE - 1] <= L.nu + L.W) && !(EXT && P.sdv && L.gam2 != 0.0)) {
+            (s_grid[TILE - 1] <= L.nu + L.W)) {
           cte = RTX_SQRT_LN2 / L.gamD;
           y = P.lorentz ? 1e300 : L.gam0 * cte;
-          tf = !(y < 15.0) || !in_weideman(L.sg0 <= s_tfar[0] ? s_grid[0] : s_grid[TILE - 1], L.sg0, cte, y);
+          const bool left = L.sg0 <= s_tfar[0];
+          const double gn = left ? s_grid[0] : s_grid[TILE - 1], gf = left ? s_grid[TILE - 1] : s_grid[0];
+          tf = sdline ? sdv_far_ok(gn - L.sg0, gf - L.sg0, L.gam0 - 1.5 * L.gam2, L.gam2, cte)
+                      : (!(y < 15.0) || !in_weideman(gn, L.sg0, cte, y));
         }
         {
           int lo = 0, hi = TILE;
@@ -898,15 +944,28 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
               }
             }
             sr.lo = (short)lo; sr.hi = (short)hi; sr.clo = (short)clo; sr.chi = (short)chi;
-            if (tf) {
-              is_tfar = true;                           // the whole tile at its 32 nodes; no other visit
-            } else if (EXT && P.sdv && L.gam2 != 0.0) {
-              // speed-dependent line (Gamma2 != 0): the whole window goes to pass 2, evaluated with pcqsdhc PART2-4
+            if (sdline) {
               sr.a = L.gam0 - 1.5 * L.gam2;             // Re c0t
               sr.ah = L.gam2;
               sr.cw = L.amp;
               sr.sub = 2;
+            }
+            if (tf) {
+              is_tfar = true;                           // the whole tile at its 32 nodes; no other visit
+            } else if (sdline) {
+              // speed-dependent line (Gamma2 != 0): the window goes to pass 2, evaluated with pcqsdhc PART2-4 -- except
+              // the slices it covers from far away, where the profile is the smooth difference of two asymptotes
               has_seg = true; sr.s = sr.clo = (short)lo; sr.e = sr.chi = (short)hi;
+              if (K >= 4 && P.far_ok != 0) {
+#pragma unroll 1
+                for (int q = 0; q < NT / 32; ++q) {
+                  if (lo > q * 32 * K || hi < (q + 1) * 32 * K) continue;             // not covered completely
+                  const bool left = sr.sg0 <= s_far[q];
+                  if (!left && !(sr.sg0 >= s_far[NT / 32 + q])) continue;             // too close
+                  const double g0 = s_grid[q * 32 * K], g1 = s_grid[q * 32 * K + 32 * K - 1];
+                  if (sdv_far_ok((left ? g0 : g1) - sr.sg0, (left ? g1 : g0) - sr.sg0, sr.a, sr.ah, cte)) sdf |= 1u << q;
+                }
+              }
             } else if (P.doppler) {
               // cSqrtLn2divSqrtPi*exp(-cLn2*((sg-sg0)/GamD)**2)/GamD (misc/hapi.py:10160, hapi's truncated constants):
               // the whole window is a "core" of pass 2, evaluated with exp instead of the rational series
@@ -953,6 +1012,14 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       if (has_seg) {
 #pragma unroll
         for (int q = 0; q < NT / 32; ++q) sm |= ((sr.e > q * 32 * K) && (sr.s < (q + 1) * 32 * K) ? 1u : 0u) << q;
+        sm &= ~sdf;
+      }
+      if (EXT) {
+#pragma unroll
+        for (int q = 0; q < NT / 32; ++q) {
+          const unsigned bq = __ballot_sync(0xffffffffu, (sdf >> q) & 1u);
+          if (lane == q) s_msdf[buf][blk][q] = bq;
+        }
       }
 #pragma unroll
       for (int q = 0; q < NT / 32; ++q) {
@@ -1004,6 +1071,17 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
       for (int blk = 0; blk < NBLK; ++blk) {
         unsigned mt = s_mtile[buf][blk] & (0xFu << (4 * warp));
         const SegRec* __restrict__ trecs = s_seg + buf * LCHUNK + blk * 32;
+        if (EXT) {                                  // speed-dependent records one by one, the others below
+          unsigned ms = 0;
+          if ((mt >> lane) & 1u) ms = trecs[lane].sub == 2 ? 1u : 0u;
+          ms = __ballot_sync(0xffffffffu, ms != 0u);
+          mt &= ~ms;
+          while (ms) {
+            const SegRec& ra = trecs[__ffs(ms) - 1];
+            ms &= ms - 1;
+            acct = fma(ra.cw, sdv_far_term((tc - ra.sg0) + tx, ra.a, ra.ah, ra.cte), acct);
+          }
+        }
         while (mt & (mt - 1)) {
           const SegRec& ra = trecs[__ffs(mt) - 1];
           mt &= mt - 1;
@@ -1021,6 +1099,16 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
     // far-field visits: the line is evaluated at this slice's 32 Chebyshev nodes only (one per lane)
 #pragma unroll 1
     for (int blk = 0; blk < NBLK; ++blk) {
+      if (EXT) {
+        const SegRec* __restrict__ frecs = s_seg + buf * LCHUNK + blk * 32;
+        unsigned ms = s_msdf[buf][blk][warp];
+        if (ms) far_used = true;
+        while (ms) {
+          const SegRec& ra = frecs[__ffs(ms) - 1];
+          ms &= ms - 1;
+          accn = fma(ra.cw, sdv_far_term((sl_c - ra.sg0) + xoff, ra.a, ra.ah, ra.cte), accn);
+        }
+      }
       {
         const SegRec* __restrict__ frecs = s_seg + buf * LCHUNK + blk * 32;
         unsigned mf = s_mfar[buf][blk][warp];
@@ -1498,7 +1586,8 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
     with4 = true;
   }
   const bool with_tf = (K == 8) && tf_variant;
-  P.sel = nullptr; P.sel_k8 = with4 ? 0 : 1; P.sel_tf = with_tf ? 1 : 0;
+  P.sel = nullptr; P.sel_k8 = with4 ? 0 : 1; P.sel_tf = with_tf ? ((flags & RTX_VOIGT_TILEFAR) ? 2 : 1) : 0;
+  P.dens = (h->lines.nu_max > h->lines.nu_min) ? (double)h->lines.n / (h->lines.nu_max - h->lines.nu_min) : 0.0;
   if (with4 || with_tf) {
     double* stat = st_wb + 2 * (size_t)n_states;
     window_stats_kernel<<<1, 256, 0, st>>>(n_states, st_wb, st_wb + n_states, grid_dev, nx, stat);

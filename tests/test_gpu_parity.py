@@ -771,7 +771,7 @@ def test_voigt_tile_level_far_field(mods):
     uniform = np.linspace(975.0, 1025.0, 100001)                       # 0.0005 cm^-1: 48 full tiles and a partial one
     two_step = np.concatenate([np.linspace(975.0, 1000.0, 75001)[:-1], np.linspace(1000.0, 1025.0, 25001)])
     jitter = np.sort(uniform + rng.uniform(-1e-4, 1e-4, uniform.size))
-    K8 = 8 << 8
+    K8 = (8 << 8) | 32768          # RTX_VOIGT_TILEFAR: the table is sparse, the automatic choice would not take the variant
     for name, grid, wing in (("uniform", uniform, 8.0), ("two_step", two_step, 8.0), ("jitter", jitter, 6.0),
                              ("hw350", uniform, 0.0)):
         kw = dict(wing_abs=wing) if wing else dict(wing_hw=350.0)
@@ -787,8 +787,12 @@ def test_voigt_tile_level_far_field(mods):
         _, ref = port.absorption_coefficient_voigt(cols, T=states[0][0], p=states[0][1], OmegaGrid=grid, **okw)
         assert_parity(dflt[0], ref, RTOL, FLOOR, "tile-level far field, %s" % name)
     # narrow wings on the same grid: the statistic keeps the variant without tile-level blocks (identical bits)
-    a = db.voigt_sum(T, p, w, uniform, flags=K8, wing_abs=1.0, wing_hw=10.0).cpu().numpy()
-    b = db.voigt_sum(T, p, w, uniform, flags=K8 | 16384, wing_abs=1.0, wing_hw=10.0).cpu().numpy()
+    a = db.voigt_sum(T, p, w, uniform, flags=8 << 8, wing_abs=1.0, wing_hw=10.0).cpu().numpy()
+    b = db.voigt_sum(T, p, w, uniform, flags=(8 << 8) | 16384, wing_abs=1.0, wing_hw=10.0).cpu().numpy()
+    assert np.array_equal(a, b)
+    # ... and so does a sparse table whatever the wing (few hundred lines per tile: the prologue bounds the CTA)
+    a = db.voigt_sum(T, p, w, uniform, flags=8 << 8, wing_abs=8.0).cpu().numpy()
+    b = db.voigt_sum(T, p, w, uniform, flags=(8 << 8) | 16384, wing_abs=8.0).cpu().numpy()
     assert np.array_equal(a, b)
     # speed-dependent lines and an extra diluent with the reference script's wing (extended instantiation)
     sd = dict(mg.sdv_table())
@@ -804,6 +808,22 @@ def test_voigt_tile_level_far_field(mods):
     assert not np.array_equal(xs, xs0)
     _, ref = port.absorption_coefficient_sdvoigt(sd, T=280.0, p=0.8, OmegaGrid=fine, Diluent=dil, OmegaWingHW=350.0)
     assert_parity(xs, ref, RTOL, FLOOR, "SDVoigt, WavenumberWingHW=350")
+    # the far wing of a speed-dependent line (difference of two asymptotes) is summed at the nodes as well: all lines
+    # speed-dependent, node-free evaluation as the yardstick, then the oracle
+    sd_all = dict(mg.sdv_table())
+    hapi.storeTable("sdv_all", sd_all)
+    res = {}
+    for name, fl in (("tile", K8 | 128), ("slice", K8 | 128 | 16384), ("exact", K8 | 128 | 4096), ("default", K8)):
+        _, res[name] = hapi.absorptionCoefficient_SDVoigt(SourceTables="sdv_all", Environment={"T": 280.0, "p": 0.8},
+                                                          OmegaGrid=fine, Diluent=dil, WavenumberWingHW=350,
+                                                          _profile_flags=fl)
+    assert not np.array_equal(res["tile"], res["slice"]) and not np.array_equal(res["slice"], res["exact"])
+    for name in ("tile", "slice"):
+        # the difference w(Z1) - w(Z2) of the reference's formulation cancels ~2 digits more than the Voigt closed form,
+        # at the nodes as at the grid points: rounding noise ~1e-12, not interpolation error
+        assert np.max(np.abs(res[name] - res["exact"]) / np.maximum(res["exact"], 1e-300)) < 2e-11, name
+    _, ref = port.absorption_coefficient_sdvoigt(sd_all, T=280.0, p=0.8, OmegaGrid=fine, Diluent=dil, OmegaWingHW=350.0)
+    assert_parity(res["default"], ref, RTOL, FLOOR, "SDVoigt far wing at the nodes")
 
 
 def test_voigt_automatic_tile_size(mods):

@@ -12,6 +12,7 @@ MARKERS = [("line state (S, widths, wing)", "struct LineState"),
            ("kernel set-up (TMA tile, registers)", "__global__ void __launch_bounds__"),
            ("prologue: records and masks", "auto produce = "),
            ("pass 1: visit set-up", "auto consume = "),
+           ("pass 1: tile-level far-field visits (32 nodes per tile)", "// tile-level far-field visits:"),
            ("pass 1: far-field visits (32 nodes per slice)", "// far-field visits:"),
            ("pass 1: test-free visits", "unsigned m = s_mfull[buf][blk][warp];"),
            ("pass 1: partial visits", "m = s_mtouch["),

@@ -185,8 +185,61 @@ def config5(n_lines=5_000_000, nx=11_000_000, n_layers=60):
     return out
 
 
+def config_xs():
+    """The reference's own cross-section script (misc/RT_gen_AbsXS_files.py:15-30, 87-93): for every (T, p) of a 10 x 5
+    grid, absorptionCoefficient_SDVoigt over 400-7100 cm^-1 at 0.0025 cm^-1 with WavenumberWingHW=350 -- windows of
+    ~10 000 grid points, the regime of the tile-level far-field blocks.  One molecule (synthetic H2O-like table over
+    300-7200 cm^-1, 5 % of the lines with SD_air), all 50 states in one launch; a slice is checked against the oracle."""
+    from radtxfr_b200 import formats
+    n_lines = 60000
+    cols = syn.synthetic_lines(77, n_lines, 300.0, 7200.0, 1)
+    rng = np.random.default_rng(78)
+    cols["SD_air"] = np.where(rng.random(n_lines) < 0.05, rng.uniform(0.05, 0.15, n_lines), 0.0)
+    hapi_compat.storeTable("xs_h2o", cols)
+    nX = round((7100 - 400) / 0.0025) + 1
+    X = np.linspace(400, 7100, nX)
+    T = np.linspace(275, 320, 10); P = np.linspace(0.85, 1.05, 5)
+    db = hapi_compat.line_database(["xs_h2o"])
+    w = np.tile(db.iso_factors(None, 1.0), (50, 1))
+    TT, PP = np.meshgrid(T, P, indexing="ij")
+    gd = torch.from_numpy(X).cuda()
+    Td = torch.from_numpy(TT.ravel().copy()).cuda(); Pd = torch.from_numpy(PP.ravel().copy()).cuda(); wd = torch.from_numpy(w).cuda()
+    out = torch.empty((50, nX), dtype=torch.float64, device="cuda")
+    ev, evw = db.count_evals(Td, Pd, wd, gd, wing_hw=350.0)
+    res = {}
+    for name, fl in (("automatic", engine.VOIGT_SDVOIGT), ("tile_level_forced", engine.VOIGT_SDVOIGT | engine.VOIGT_TILEFAR),
+                     ("slice_level_only", engine.VOIGT_SDVOIGT | engine.VOIGT_NOTILEFAR),
+                     ("no_far_field", engine.VOIGT_SDVOIGT | engine.VOIGT_NOFAR)):
+        f = lambda: db.voigt_sum(Td, Pd, wd, gd, wing_hw=350.0, out=out, flags=fl)
+        f(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); f(); f(); e1.record(); torch.cuda.synchronize()
+        res[name + "_ms"] = e0.elapsed_time(e1) / 2
+    db.voigt_sum(Td, Pd, wd, gd, wing_hw=350.0, out=out, flags=engine.VOIGT_SDVOIGT)
+    # the call a user of the reference makes, one state at a time (numpy in, numpy out)
+    t0 = time.perf_counter()
+    _, xs1 = hapi_compat.absorptionCoefficient_SDVoigt(SourceTables="xs_h2o", Environment={"T": float(T[3]), "p": float(P[2])},
+                                                      WavenumberStep=0.0025, WavenumberRange=[400, 7100], IntensityThreshold=0,
+                                                      WavenumberWingHW=350, OmegaGrid=X)
+    api_s = time.perf_counter() - t0
+    # parity: 4000 points around 1600 cm^-1 of state (T[3], P[2]) against the oracle (lines within reach only)
+    i0 = int((1600.0 - 400.0) / 0.0025)
+    sl = slice(i0, i0 + 4000)
+    near = (cols["nu"] > X[sl][0] - 60.0) & (cols["nu"] < X[sl][-1] + 60.0)
+    sub = {k: v[near] for k, v in cols.items()}
+    t0 = time.perf_counter()
+    _, ref = port.absorption_coefficient_sdvoigt(sub, T=float(T[3]), p=float(P[2]), OmegaGrid=X[sl], OmegaWingHW=350.0)
+    oracle_s = time.perf_counter() - t0
+    ok1, e1_ = parity(out[3 * 5 + 2, sl].cpu().numpy(), ref)
+    ok2, e2_ = parity(xs1[sl], ref)
+    return {"config": "xs", "what": "misc/RT_gen_AbsXS_files.py workload: SDVoigt, 400-7100 @0.0025 (%d pts), WavenumberWingHW=350, "
+            "10 T x 5 p in one launch, %d synthetic lines (5 %% with SD_air)" % (nX, n_lines), "evals": ev, "weideman_evals": evw,
+            **res, "evals_per_s": ev / (res["automatic_ms"] * 1e-3), "single_state_api_s": api_s,
+            "oracle_slice_s": oracle_s, "parity_ok": bool(ok1 and ok2), "max_rel_err": max(e1_, e2_)}
+
+
 if __name__ == "__main__":
     for c in sys.argv[1:]:
-        r = {"1": config1, "3": config3, "4": config4, "5": config5}[c]()
+        r = {"1": config1, "3": config3, "4": config4, "5": config5, "xs": config_xs}[c]()
         if r is not None:
             print(json.dumps(r), flush=True)
