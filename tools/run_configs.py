@@ -217,11 +217,12 @@ def config_xs():
         res[name + "_ms"] = e0.elapsed_time(e1) / 2
     db.voigt_sum(Td, Pd, wd, gd, wing_hw=350.0, out=out, flags=engine.VOIGT_SDVOIGT)
     # the call a user of the reference makes, one state at a time (numpy in, numpy out)
-    t0 = time.perf_counter()
-    _, xs1 = hapi_compat.absorptionCoefficient_SDVoigt(SourceTables="xs_h2o", Environment={"T": float(T[3]), "p": float(P[2])},
-                                                      WavenumberStep=0.0025, WavenumberRange=[400, 7100], IntensityThreshold=0,
-                                                      WavenumberWingHW=350, OmegaGrid=X)
-    api_s = time.perf_counter() - t0
+    for _ in range(2):                                   # the second call is timed (the first uploads / allocates)
+        t0 = time.perf_counter()
+        _, xs1 = hapi_compat.absorptionCoefficient_SDVoigt(SourceTables="xs_h2o", Environment={"T": float(T[3]), "p": float(P[2])},
+                                                          WavenumberStep=0.0025, WavenumberRange=[400, 7100], IntensityThreshold=0,
+                                                          WavenumberWingHW=350, OmegaGrid=X)
+        api_s = time.perf_counter() - t0
     # parity: 4000 points around 1600 cm^-1 of state (T[3], P[2]) against the oracle (lines within reach only)
     i0 = int((1600.0 - 400.0) / 0.0025)
     sl = slice(i0, i0 + 4000)
