@@ -394,7 +394,9 @@ def gpu_arm(args):
     ms_voigt, ms_tud = sum(v_steps), sum(t_steps)
 
     def stats(v):
-        return {"min": float(np.min(v)), "median": float(np.median(v)), "max": float(np.max(v))}
+        # every step's device time as well: an outlier (one slow launch, a hiccup of the box) is then visible as such
+        return {"min": float(np.min(v)), "median": float(np.median(v)), "max": float(np.max(v)),
+                "slowest_step": int(np.argmax(v)), "all": [round(float(x), 3) for x in v]}
     launches = db.handle.launches() + h0.launches() - launches0
     tot = torch.tensor([ms_total, float(E), float(Ew), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -496,14 +498,14 @@ def gpu_arm(args):
             "ms_voigt_per_step": ms_voigt / args.steps, "ms_tud_per_step": ms_tud / args.steps,
             "per_step_ms": {"voigt": stats(v_steps), "tud": stats(t_steps)},
             "ingest_s": ingest_s,
-            "roofline": {"bound": "fp64", "kernel": "voigt_tile_kernel", "achieved": achieved / 1e12,
+            "roofline": {"bound": "fp64", "kernel": "voigt_tile_kernel (K = 8 and K = 4 instantiations, picked per state on the device)", "achieved": achieved / 1e12,
                          "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "measured in this run: dependent-free DFMA loop (rtx_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "flops_model": "16 flop per asymptote-branch eval, 200 per Weideman eval (SURVEY.md 8d)",
                          "note": "achieved counts the reference's ALGORITHMIC flops (every (line, grid point) pair of its "
                                  "windows); the kernel evaluates wing contributions at 32 Chebyshev nodes per 256-point slice "
-                                 "(far-field blocks, deviation < 1e-13) and so issues fewer operations than it is credited "
+                                 "(far-field blocks, at tile level for wings >= 4000 points; deviation < 1e-13) and so issues fewer operations than it is credited "
                                  "with -- frac above 1 means faster than a perfect FP64 pipe could run the reference's "
                                  "arithmetic.  The pipe-level view of the same kernel is in `issued`.",
                          "issued": {"fp64_pipe_pct_of_peak": ncu.get("voigt_tile_kernel_fp64_pipe_pct"),
