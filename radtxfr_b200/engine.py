@@ -319,6 +319,13 @@ class LineDB:
         species other than air / self that the table has columns for (others contribute nothing, as in hapi)."""
         torch = _torch()
         dev = self.device
+        if not any(isinstance(a, torch.Tensor) for a in (T, p, weight)):
+            # host arrays (the shims' single-state calls): one staging array and one copy instead of three
+            Th, ph = np.asarray(T, dtype=np.float64).reshape(-1), np.asarray(p, dtype=np.float64).reshape(-1)
+            n_states = Th.size
+            wh = np.asarray(weight, dtype=np.float64).reshape(n_states, self.n_iso)
+            st = torch.from_numpy(np.concatenate([Th, ph, wh.reshape(-1)])).to(dev)
+            T, p, weight = st[:n_states], st[n_states:2 * n_states], st[2 * n_states:].view(n_states, self.n_iso)
         T = to_device(T, dev).reshape(-1)
         p = to_device(p, dev).reshape(-1)
         n_states = T.numel()

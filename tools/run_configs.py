@@ -28,8 +28,10 @@ def parity(a, b):
     return ok, float(np.max(np.abs(a - b)[big] / np.abs(b[big]))) if big.any() else 0.0
 
 
-def timed(fn, reps=5):
-    fn(); torch.cuda.synchronize()
+def timed(fn, reps=5, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(reps):
         r = fn()
@@ -42,7 +44,8 @@ def config1():
     hapi_compat.storeTable("cfg1", cols)
     grid = np.linspace(800.0, 1300.0, 50001)
     env = {"T": 296.0, "p": 1.0}
-    (om, xs), dt = timed(lambda: hapi_compat.absorptionCoefficient_Voigt(SourceTables="cfg1", Environment=env, OmegaGrid=grid))
+    (om, xs), dt = timed(lambda: hapi_compat.absorptionCoefficient_Voigt(SourceTables="cfg1", Environment=env, OmegaGrid=grid),
+                         reps=300, warm=20)
     db = hapi_compat.line_database(["cfg1"])
     ev, evw = db.count_evals([296.0], [1.0], db.iso_factors(None, 1.0)[None, :], grid)
     gd = torch.from_numpy(grid).cuda(); w = torch.from_numpy(db.iso_factors(None, 1.0)[None, :]).cuda()
