@@ -333,22 +333,33 @@ def gpu_arm(args):
     # stream so that step k's gather overlaps step k+1's Voigt kernel; the timed region ends after the last gather.
     side = torch.cuda.Stream(device=dev) if world > 1 else None
 
-    def gather(tau, lu, ld):
+    # Results go to two persistent (3, nX) buffers used in turn -- (tau, Lu, Ld) of a step are one contiguous block, the
+    # gather reads it in place (no stack, no allocation inside the timed loop), and the buffer of step k is free again
+    # for step k+2 once the gather of step k has fired its event.
+    res = [torch.empty((3, nX), dtype=torch.float64, device=dev) for _ in range(2)]
+    res_free = [None, None]
+
+    def tud_into(k, T):
+        b = res[k % 2]
+        if res_free[k % 2] is not None:
+            torch.cuda.current_stream(dev).wait_event(res_free[k % 2])
+        return engine.tud(od, T[None, :], grid, atm["Zs"], [500.0], [1.0], N_ANGLE, out=(b[0], b[1], b[2]))
+
+    def gather(k):
         done = torch.cuda.Event()
         done.record()
         with torch.cuda.stream(side):
             side.wait_event(done)
-            mine = torch.stack([tau.reshape(-1), lu.reshape(-1), ld.reshape(-1)])
-            for t in (tau, lu, ld):
-                t.record_stream(side)
-            dist.all_gather_into_tensor(gathered, mine)
+            dist.all_gather_into_tensor(gathered, res[k % 2])
+            res_free[k % 2] = torch.cuda.Event()
+            res_free[k % 2].record(side)
 
     def step(i):
         T, p, w = states[i]
         db.voigt_sum(T, p, w, grid, out=od, flags=args.flags)
-        tau, lu, ld = engine.tud(od, T[None, :], grid, atm["Zs"], [500.0], [1.0], N_ANGLE)
+        tau, lu, ld = tud_into(i, T)
         if world > 1:
-            gather(tau, lu, ld)
+            gather(i)
         return tau, lu, ld
 
     for i in range(args.warmup):
@@ -376,10 +387,10 @@ def gpu_arm(args):
         T, p, w = states[i]
         db.voigt_sum(T, p, w, grid, out=od, flags=args.flags)
         ev[2 * k + 1].record()
-        tau, lu, ld = engine.tud(od, T[None, :], grid, atm["Zs"], [500.0], [1.0], N_ANGLE)
+        tau, lu, ld = tud_into(i, T)
         ev[2 * k + 2].record()
         if world > 1:
-            gather(tau, lu, ld)
+            gather(i)
     if world > 1:
         torch.cuda.current_stream(dev).wait_stream(side)      # the last gather is inside the timed region
     ev_end = torch.cuda.Event(enable_timing=True)
