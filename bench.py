@@ -273,6 +273,7 @@ def banded_leg(args, rank, world, dev):
            "scaling": "strong", "evals": ev, "weideman_fraction": evw / max(1, ev), "ms": ms_dev, "evals_per_s": ev / (ms_dev * 1e-3),
            "band_points": [b - a for a, b in bands], "band_compute_ms": rank_ms,
            "timed_call_detail": dev_detail,
+           "balance_history": [{"band_points": h[0], "compute_ms": [round(x, 2) for x in h[1]]} for h in fbs[-1].get("history", [])] if fbs else None,
            "host_prep_ms_rank0": fbs[-1].get("host_prep_ms") if fbs else None,
            "gather_ms_rank0": (fbs[-1]["tail_events"][0].elapsed_time(fbs[-1]["tail_events"][1]) if fbs and "tail_events" in fbs[-1] else None),
            "assemble_ms_rank0": (fbs[-1]["tail_events"][1].elapsed_time(fbs[-1]["tail_events"][2]) if fbs and "tail_events" in fbs[-1] else None),

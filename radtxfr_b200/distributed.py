@@ -223,9 +223,14 @@ def compute_TUD_banded(Xmin, Xmax, opts, group=None, balance=True, to_host=True,
             _all_gather_flat(allms, ms, group)
             allms = allms.cpu().numpy()
             if np.all(allms > 0):
+                # bounded step: one call disturbed from outside (a rank stalled by its host, another job on the box)
+                # must not throw a balanced plan away -- a 2x outlier moves the cuts like a 15 % imbalance would
+                ratio = np.clip(allms / allms.mean(), 0.87, 1.15)
                 for r, (a, b) in enumerate(prev_bands):
-                    fb["scale"][a // TILE:(b + TILE - 1) // TILE] *= (allms[r] / allms.mean()) ** 0.8
+                    fb["scale"][a // TILE:(b + TILE - 1) // TILE] *= ratio[r] ** 0.8
             fb["last_ms"] = allms
+            fb.setdefault("history", []).append(([int(b - a) for a, b in prev_bands], [float(x) for x in allms]))
+            del fb["history"][:-12]
         if fb is not None:
             costs = costs * fb["scale"]
     bands = plan_bands(nX, world, weights=costs)
