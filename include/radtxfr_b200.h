@@ -138,6 +138,8 @@ int rtx_tape3_read(const char* path, double vmin, double vmax, int64_t capacity,
 #define RTX_VOIGT_TILEFAR 32768  /* use the tile-level far-field blocks wherever a line qualifies (default: only for states
                                  * whose typical wing is >= 4000 grid points and whose tiles see >= 600 such lines -- below
                                  * that the kernel variant without them is faster) */
+#define RTX_VOIGT_NOSPLIT 65536  /* small problems (fewer (tile, state) pairs than three per SM): do not split the lines of a
+                                 * tile over several CTAs (default: up to 8 CTAs per tile, partial spectra added in order) */
 #define RTX_VOIGT_SDVOIGT 8192  /* absorptionCoefficient_SDVoigt (misc/hapi.py:10657-10905): lines whose Gamma2 = sum_d x_d
                                  * SD_d p gamma_d is non-zero take the quadratic speed-dependent profile (pcqsdhc PART2-4,
                                  * misc/hapi.py:9923-10020); the rest is the Voigt driver */

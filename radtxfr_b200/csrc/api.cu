@@ -58,7 +58,7 @@ extern "C" int rtx_destroy(rtx_handle* h) {
   if (!h) return RTX_OK;
   DeviceGuard guard(h->device);
   free_lines(h->lines);
-  for (double* p : {h->d_mass, h->d_tipsT, h->d_q, h->d_qref, h->d_state}) if (p) cudaFree(p);
+  for (double* p : {h->d_mass, h->d_tipsT, h->d_q, h->d_qref, h->d_state, h->d_part}) if (p) cudaFree(p);
   if (h->d_bins) cudaFree(h->d_bins);
   if (h->d_cheb) cudaFree(h->d_cheb);
   if (h->d_iso_mol) cudaFree(h->d_iso_mol);

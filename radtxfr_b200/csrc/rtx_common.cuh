@@ -55,6 +55,7 @@ struct rtx_handle {
   LineTable lines;
   // grow-only scratch
   double* d_state = nullptr;  size_t state_cap = 0;   // per-state tables
+  double* d_part = nullptr;   size_t part_cap = 0;    // partial spectra of line-split launches (small problems)
   int32_t* d_bins = nullptr;  size_t bins_cap = 0;    // [n_states][n_tiles][2]
   double* h_pin = nullptr;                             // 2 pinned doubles for small read-backs
   double* d_cheb = nullptr;                            // Chebyshev tables of the Voigt far-field blocks

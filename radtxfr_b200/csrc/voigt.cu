@@ -62,6 +62,10 @@ constexpr int NT = 256;         // threads per CTA
 #ifndef RTX_MINBLOCKS
 #define RTX_MINBLOCKS 3
 #endif
+// K <= 2 (small problems): the CTAs are latency-bound, more of them per SM
+#ifndef RTX_MINBLOCKS_SMALL
+#define RTX_MINBLOCKS_SMALL 4
+#endif
 
 // Lines per chunk (one line per thread per prologue round).  The FP64 kernels keep ONE 80-byte record per line, so
 // the 2048-point tile affords 512-line chunks at three CTAs per SM: half as many block-wide barriers and prologue
@@ -91,6 +95,13 @@ struct ChunkCfg {
 // (measured: 1150 qualifying lines per tile 11 % faster, 220 lines 5 % slower; tools/xs_breakdown.py)
 #ifndef RTX_TF_MINLINES
 #define RTX_TF_MINLINES 600.0
+#endif
+// line split of small problems: at most this many CTAs per (tile, state), aiming at this many CTAs per SM in total
+#ifndef RTX_SPLIT_MAX
+#define RTX_SPLIT_MAX 8
+#endif
+#ifndef RTX_SPLIT_CTAS_PER_SM
+#define RTX_SPLIT_CTAS_PER_SM 4
 #endif
 #ifndef RTX_NARROW_MAX
 #define RTX_NARROW_MAX 128
@@ -146,6 +157,10 @@ struct VoigtParams {
   const double* sel;
   const double *st_wb, *st_wt;
   int sel_k8, sel_tf;
+  // small problems: the candidate lines of a (tile, state) are split over `split` CTAs that write partial sums to
+  // part_out[part][state][nx]; sum_parts_kernel adds them in part order (fixed summation order)
+  int split;
+  double* part_out;
   double dens;   // lines per cm^-1 of the table (the tile-level blocks pay only when many lines reach over whole tiles)
   int lorentz;   // PROFILE_LORENTZ instead of PROFILE_VOIGT: no Doppler width, wing = max(OmegaWing, HW*Gamma0)
   int doppler;   // PROFILE_DOPPLER (absorptionCoefficient_Doppler): 1 = with line shift, 2 = LineShift=False
@@ -538,13 +553,15 @@ struct PrepParams {
   double xx[RTX_MAX_EXTRA_DILUENTS], xg_max[RTX_MAX_EXTRA_DILUENTS], xn_min[RTX_MAX_EXTRA_DILUENTS], xn_max[RTX_MAX_EXTRA_DILUENTS];
 };
 
+// one warp per state: the lanes share the isotopologues (a single-state call is bound by this kernel's latency)
 __global__ void state_prep_kernel(PrepParams P) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= P.n_states) return;
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= P.n_states) return;                    // whole warps leave together
   const double T = P.T[s], p = P.p[s];
   const bool ok = (T >= 70.0) && (T <= 3000.0);   // misc/hapi.py:9571
   double dmax = 0.0;
-  for (int j = 0; j < P.n_iso; ++j) {
+  for (int j = lane; j < P.n_iso; j += 32) {
     const double Q = ok ? tips_lagrange(T, P.tipsT, P.q + (int64_t)j * RTX_TIPS_NPT, RTX_TIPS_NPT) : nan("");
     P.st_q[(int64_t)s * P.n_iso + j] = P.qref[j] / Q;
     const double m = P.mass[j] * RTX_CMASS * 1000.0;
@@ -554,6 +571,9 @@ __global__ void state_prep_kernel(PrepParams P) {
     P.st_d[(int64_t)s * P.n_iso + j] = d;
     dmax = fmax(dmax, d);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  if (lane != 0) return;
   const double lnr = log(RTX_TREF / T);
   const double ra = fmax(exp(P.nair_min * lnr), exp(P.nair_max * lnr));
   const double rs = fmax(exp(P.nself_min * lnr), exp(P.nself_max * lnr));
@@ -606,20 +626,44 @@ __global__ void tips_kernel(int n, int n_iso, const double* __restrict__ T, cons
                                       : nan("");
 }
 
-// candidate line range of every (state, tile): lines with nu in [tile_lo - Wb, tile_hi + Wb]
+// Warp-cooperative bisection on the sorted line centres: every round the 32 lanes probe 32 positions of the current
+// interval (3 rounds for 30 000 lines, 5 for 30 million) -- a thread-per-search bisection is a chain of ~20 dependent
+// global loads, which a single-state call waits for.  RIGHT: number of elements <= v, else number of elements < v.
+template <bool RIGHT>
+__device__ __forceinline__ int64_t warp_bisect(const double* __restrict__ a, int64_t n, double v, int lane) {
+  int64_t lo = 0, hi = n;                                    // the answer lies in [lo, hi]
+  while (hi - lo > 32) {
+    const int64_t len = hi - lo;
+    const int64_t pk = lo + ((int64_t)(lane + 1) * len) / 33;                // lo < pk < hi, ascending with the lane
+    const double x = a[pk];
+    const unsigned m = __ballot_sync(0xffffffffu, RIGHT ? (x <= v) : (x < v));   // 1...10...0: the array is sorted
+    const int cnt = __popc(m);
+    const int64_t p_last = lo + ((int64_t)cnt * len) / 33, p_next = lo + ((int64_t)(cnt + 1) * len) / 33;
+    if (cnt > 0) lo = p_last + 1;
+    if (cnt < 32) hi = p_next;
+  }
+  const int64_t i = lo + lane;
+  const bool in = i < hi && (RIGHT ? (a[i] <= v) : (a[i] < v));
+  return lo + __popc(__ballot_sync(0xffffffffu, in));
+}
+
+// candidate line range of every (state, tile): lines with nu in [tile_lo - Wb, tile_hi + Wb]; one warp per pair
 __global__ void bin_kernel(int n_states, int n_tiles, int tile_pts, const double* __restrict__ grid, int64_t nx,
                            const double* __restrict__ nu, int64_t n_lines, const double* __restrict__ st_wb,
                            int32_t* __restrict__ bins) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= (int64_t)n_states * n_tiles) return;
   const int s = (int)(i / n_tiles), t = (int)(i % n_tiles);
   const int64_t p0 = (int64_t)t * tile_pts;
   const int64_t p1 = min(nx, p0 + tile_pts) - 1;
   const double wb = st_wb[s];
-  const int64_t first = bisect_left_dev64(nu, n_lines, grid[p0] - wb);
-  const int64_t last = bisect_right_dev64(nu, n_lines, grid[p1] + wb);
-  bins[2 * i] = (int32_t)first;
-  bins[2 * i + 1] = (int32_t)last;
+  const int64_t first = warp_bisect<false>(nu, n_lines, grid[p0] - wb, lane);
+  const int64_t last = warp_bisect<true>(nu, n_lines, grid[p1] + wb, lane);
+  if (lane == 0) {
+    bins[2 * i] = (int32_t)first;
+    bins[2 * i + 1] = (int32_t)last;
+  }
 }
 
 // Searches on the shared-memory tile with an arithmetic first guess.  The answers are defined by exact comparisons
@@ -684,7 +728,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
 // TFP = tile-level far-field blocks compiled in (K = 8 only; its own instantiation, so that the variant for windows of
 // a few thousand points carries none of its code)
 template <int K, int MODE, bool WS, bool EXT = false, bool TFP = false>
-__global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RTX_MINBLOCKS_K4 : RTX_MINBLOCKS)) voigt_tile_kernel(const VoigtParams P) {
+__global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RTX_MINBLOCKS_K4 : K <= 2 ? RTX_MINBLOCKS_SMALL : RTX_MINBLOCKS)) voigt_tile_kernel(const VoigtParams P) {
   constexpr bool FAST = (MODE == 1);
   constexpr bool F32 = (MODE == 2);
   constexpr int TILE = K * NT;
@@ -709,7 +753,8 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
   // window statistic (window_stats_kernel) does not pick retires at once
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x % P.n_tiles;
-  const int s = blockIdx.x / P.n_tiles;
+  const int s = (blockIdx.x / P.n_tiles) % P.n_states;
+  const int part = (blockIdx.x / P.n_tiles) / P.n_states;      // 0 unless the lines are split
   if (P.sel != nullptr) {
     const double inv_dv = P.sel[2];
     const double wt = P.st_wt[s];
@@ -833,7 +878,12 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
   const double T = P.T[s], p = P.p[s];
   const double lnr = log(RTX_TREF / T);
   const int64_t bi = 2 * ((int64_t)s * P.n_tiles + tile);
-  const int first = P.bins[bi], last = P.bins[bi + 1];
+  int first = P.bins[bi], last = P.bins[bi + 1];
+  if (P.split > 1) {
+    const int64_t len = last - first;
+    last = first + (int)(len * (part + 1) / P.split);
+    first = first + (int)(len * part / P.split);
+  }
   const int own_lo = warp * (TILE / (NT / 32)), own_hi = own_lo + TILE / (NT / 32);
 
   // Lines are dealt to chunks round-robin (chunk c takes candidates c, c+nchunks, ...), so every chunk spans
@@ -1383,12 +1433,21 @@ __global__ void __launch_bounds__(WS ? NT + 32 * NPW : NT, WS ? 2 : (K == 4 ? RT
     }
   }
 
-  double* out = P.out + (int64_t)s * P.nx + p0;   // only consumer warps get here in the WS variant
+  double* out = (P.split > 1 ? P.part_out + (int64_t)part * P.n_states * P.nx : P.out) + (int64_t)s * P.nx + p0;   // only consumer warps get here in the WS variant
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     const int i = warp * (32 * K) + j * 32 + lane;
     if (i < npts) out[i] = acc[j] + s_acc2[i];
   }
+}
+
+// partial sums of a line-split launch, added in part order
+__global__ void sum_parts_kernel(const double* __restrict__ part, int split, int64_t n, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = part[i];
+  for (int k = 1; k < split; ++k) a += part[(int64_t)k * n + i];
+  out[i] = a;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1448,7 +1507,7 @@ template <int K, int MODE, bool WS, bool EXT = false, bool TFP = false>
 int launch_tile(const VoigtParams& P, cudaStream_t st) {
   const size_t smem = tile_smem_bytes<K, MODE, WS>();
   RTX_CUDA(cudaFuncSetAttribute(voigt_tile_kernel<K, MODE, WS, EXT, TFP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t blocks = (int64_t)P.n_tiles * P.n_states;
+  const int64_t blocks = (int64_t)P.n_tiles * P.n_states * (P.split > 1 ? P.split : 1);
   if (blocks > 2147483647LL) { rtx_set_error("rtx_voigt_sum: too many (tile, state) pairs for one launch"); return RTX_E_INVALID; }
   voigt_tile_kernel<K, MODE, WS, EXT, TFP><<<(unsigned)blocks, WS ? NT + 32 * NPW : NT, smem, st>>>(P);
   RTX_CUDA(cudaGetLastError());
@@ -1499,6 +1558,7 @@ int fill_params(rtx_handle* h, VoigtParams& P, int n_states, const double* T, co
   P.lorentz = 0;
   P.doppler = 0;
   P.sel = nullptr;
+  P.split = 1; P.part_out = nullptr;
   return RTX_OK;
 }
 
@@ -1523,7 +1583,7 @@ int run_prep(rtx_handle* h, VoigtParams& P, cudaStream_t st, double** st_wb_out)
   for (int e = 0; e < RTX_MAX_EXTRA_DILUENTS; ++e) {
     Q.xx[e] = P.xx[e]; Q.xg_max[e] = L.xg_max[e]; Q.xn_min[e] = L.xn_min[e]; Q.xn_max[e] = L.xn_max[e];
   }
-  state_prep_kernel<<<(P.n_states + 127) / 128, 128, 0, st>>>(Q);
+  state_prep_kernel<<<(unsigned)(((int64_t)P.n_states * 32 + 127) / 128), 128, 0, st>>>(Q);
   RTX_CUDA(cudaGetLastError());
   h->launches++;
   P.st_q = st_q; P.st_d = st_d;
@@ -1585,6 +1645,26 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
     // for the GPU.
     with4 = true;
   }
+  // Small problems (fewer tiles than the GPU holds CTAs at once): every CTA is bound by the latency of its own chunk
+  // loop, so the candidate lines of each (tile, state) are split over several CTAs and the partial spectra added
+  // afterwards.  The split depends on the tile size and the number of tiles only, not on the number of states, so that a
+  // batch and its single members keep identical bits.
+  if (!forced && K == 1 && !(flags & RTX_VOIGT_NOSPLIT)) K = 2;   // with the lines split, 512-point tiles repeat less per-line work
+  if (!with4 && K <= 2 && !(flags & RTX_VOIGT_NOSPLIT)) {
+    const int64_t nt0 = (nx + (int64_t)K * NT - 1) / ((int64_t)K * NT);
+    if (nt0 < 3LL * h->sm_count) {
+      P.split = (int)std::min<int64_t>(RTX_SPLIT_MAX, ((int64_t)RTX_SPLIT_CTAS_PER_SM * h->sm_count + nt0 - 1) / nt0);
+      size_t need = (size_t)P.split * n_states * (size_t)nx;
+      if (need > ((size_t)32 << 20)) { P.split = 1; need = 0; }      // 256 MB of partial spectra: not a small problem
+      if (need > h->part_cap) {
+        if (h->d_part) cudaFree(h->d_part);
+        h->d_part = nullptr; h->part_cap = 0;
+        RTX_CUDA(cudaMalloc(&h->d_part, need * sizeof(double)));
+        h->part_cap = need;
+      }
+      P.part_out = P.split > 1 ? h->d_part : nullptr;
+    }
+  }
   const bool with_tf = (K == 8) && tf_variant;
   P.sel = nullptr; P.sel_k8 = with4 ? 0 : 1; P.sel_tf = with_tf ? ((flags & RTX_VOIGT_TILEFAR) ? 2 : 1) : 0;
   P.dens = (h->lines.nu_max > h->lines.nu_min) ? (double)h->lines.n / (h->lines.nu_max - h->lines.nu_min) : 0.0;
@@ -1606,12 +1686,12 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
   rc = ensure_scratch(h, h->state_cap, 2 * (nb + nb4));
   if (rc) return rc;
   P.bins = h->d_bins;
-  bin_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(n_states, P.n_tiles, tile_pts, grid_dev, nx, P.nu, P.n_lines,
+  bin_kernel<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, st>>>(n_states, P.n_tiles, tile_pts, grid_dev, nx, P.nu, P.n_lines,
                                                           st_wb, h->d_bins);
   RTX_CUDA(cudaGetLastError());
   h->launches++;
   if (with4) {
-    bin_kernel<<<(unsigned)((nb4 + 255) / 256), 256, 0, st>>>(n_states, n_tiles4, 4 * NT, grid_dev, nx, P.nu, P.n_lines,
+    bin_kernel<<<(unsigned)((nb4 * 32 + 255) / 256), 256, 0, st>>>(n_states, n_tiles4, 4 * NT, grid_dev, nx, P.nu, P.n_lines,
                                                              st_wb, h->d_bins + 2 * nb);
     RTX_CUDA(cudaGetLastError());
     h->launches++;
@@ -1659,6 +1739,12 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
     h->launches++;
   }
 #undef RTX_LAUNCH
+  if (P.split > 1) {
+    const int64_t n = (int64_t)n_states * nx;
+    sum_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.part_out, P.split, n, out_dev);
+    RTX_CUDA(cudaGetLastError());
+    h->launches++;
+  }
   return RTX_OK;
 }
 

@@ -39,6 +39,7 @@ VOIGT_EXACT_RCP, VOIGT_NOFAR, VOIGT_TILE_SHIFT = 128, 4096, 8
 VOIGT_SDVOIGT = 8192
 VOIGT_NOTILEFAR = 16384
 VOIGT_TILEFAR = 32768
+VOIGT_NOSPLIT = 65536
 MAX_EXTRA_DILUENTS = 4
 # precision names of the shims -> flags.  "fp64" (default): FP64 with the one-Newton-step reciprocal (<= 9e-13 per
 # term) and far-field blocks (< 1e-13); "fp64_fast" is the same thing (kept for round-1 callers); "fp64_exact":

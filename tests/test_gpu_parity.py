@@ -826,6 +826,28 @@ def test_voigt_tile_level_far_field(mods):
     assert_parity(res["default"], ref, RTOL, FLOOR, "SDVoigt far wing at the nodes")
 
 
+def test_voigt_small_problem_line_split(mods):
+    """Small problems (fewer (tile, state) pairs than three per SM -- a single cross-section): the candidate lines of a
+    tile are split over up to eight CTAs whose partial spectra are added in part order.  Same result as the unsplit
+    launch (RTX_VOIGT_NOSPLIT) to rounding, bit-reproducible, parity with the oracle; one-point and empty cases."""
+    port, syn, engine = mods["port"], mods["syn"], mods["engine"]
+    cols = syn.synthetic_lines(71, 3000, 990.0, 1010.0, 1)
+    db = engine.LineDB(cols)
+    for nS, grid in ((1, np.linspace(995.0, 1005.0, 10001)), (3, np.linspace(999.0, 1001.0, 777)), (1, np.array([1000.0]))):
+        T = np.linspace(296.0, 240.0, nS); p = np.geomspace(1.0, 0.1, nS)
+        w = np.tile(db.iso_factors(None, 1.0), (nS, 1))
+        a = db.voigt_sum(T, p, w, grid).cpu().numpy()
+        b = db.voigt_sum(T, p, w, grid).cpu().numpy()
+        c = db.voigt_sum(T, p, w, grid, flags=65536).cpu().numpy()
+        assert np.array_equal(a, b)
+        assert np.max(np.abs(a - c) / np.maximum(c, 1e-300)) < 5e-12
+        if grid.size > 1:
+            assert not np.array_equal(a, c)                                   # the split path was taken
+        for k in range(nS):
+            _, ref = port.absorption_coefficient_voigt(cols, T=T[k], p=p[k], OmegaGrid=grid)
+            assert_parity(a[k], ref, RTOL, FLOOR, "line split, %d states, %d points, state %d" % (nS, grid.size, k))
+
+
 def test_voigt_automatic_tile_size(mods):
     """Automatic tile size: 2048-point tiles when the windows are thousands of grid points wide (fine grid, low
     layers), 1024-point tiles at four CTAs per SM when they are a few hundred (coarse grid) -- decided from the

@@ -253,7 +253,7 @@ def test_flag_literals_match_header():
     for names, vals in consts.items():
         for n, v in zip(names.split(", "), vals.split(", ")):
             setattr(ns, n, int(v))
-    for n in ("FP32", "WARPSPEC", "LORENTZ", "DOPPLER", "NOSHIFT", "EXACT_RCP", "NOFAR", "TILE_SHIFT", "SDVOIGT", "NOTILEFAR", "TILEFAR"):
+    for n in ("FP32", "WARPSPEC", "LORENTZ", "DOPPLER", "NOSHIFT", "EXACT_RCP", "NOFAR", "TILE_SHIFT", "SDVOIGT", "NOTILEFAR", "TILEFAR", "NOSPLIT"):
         assert getattr(ns, "VOIGT_" + n) == val["RTX_VOIGT_" + n], n
     assert "engine.PRECISION_FLAGS[" in shim
     rtm = open(os.path.join(root, "radtxfr_b200", "radiative_transfer.py")).read()
