@@ -826,6 +826,30 @@ def test_voigt_tile_level_far_field(mods):
     assert_parity(res["default"], ref, RTOL, FLOOR, "SDVoigt far wing at the nodes")
 
 
+def test_voigt_tile_level_automatic_on_dense_table(mods):
+    """The variant with tile-level blocks is picked on the device where it pays: config 2's dense table (262 lines per
+    cm^-1) with 6 cm^-1 wings takes it by itself (different bits from RTX_VOIGT_NOTILEFAR), the default 50-half-width
+    wings do not (identical bits); either way the result agrees with the node-free evaluation."""
+    syn, engine, rt = mods["syn"], mods["engine"], mods["rt"]
+    tabs = syn.config2_tables()
+    db = engine.LineDB([tabs[m] for m in sorted(tabs)])
+    atm = syn.standard_atmosphere()
+    p, w = rt.layer_weights(db, atm["Ts"], atm["Ps"], atm["PLs"], atm["MFs_VAL"], atm["MFs_ID"])
+    sl = slice(0, 3)
+    T, pp, ww = atm["Ts"][sl], np.ascontiguousarray(p)[sl], w[sl]
+    grid = rt.make_spectral_axis(700.0, 1500.0, 0.001)
+    K8 = 8 << 8
+    auto = db.voigt_sum(T, pp, ww, grid, flags=128 | K8, wing_abs=6.0).cpu().numpy()
+    no_tile = db.voigt_sum(T, pp, ww, grid, flags=128 | 16384 | K8, wing_abs=6.0).cpu().numpy()
+    exact = db.voigt_sum(T, pp, ww, grid, flags=128 | 4096 | K8, wing_abs=6.0).cpu().numpy()
+    assert not np.array_equal(auto, no_tile)
+    assert np.max(np.abs(auto - exact) / np.maximum(exact, 1e-300)) < 2e-13
+    assert np.max(np.abs(no_tile - exact) / np.maximum(exact, 1e-300)) < 2e-13
+    a = db.voigt_sum(T, pp, ww, grid, flags=K8).cpu().numpy()
+    b = db.voigt_sum(T, pp, ww, grid, flags=K8 | 16384).cpu().numpy()
+    assert np.array_equal(a, b)
+
+
 def test_voigt_small_problem_line_split(mods):
     """Small problems (fewer (tile, state) pairs than three per SM -- a single cross-section): the candidate lines of a
     tile are split over up to eight CTAs whose partial spectra are added in part order.  Same result as the unsplit
