@@ -786,6 +786,14 @@ def test_voigt_tile_level_far_field(mods):
         okw = dict(OmegaWing=wing) if wing else dict(OmegaWingHW=350.0)
         _, ref = port.absorption_coefficient_voigt(cols, T=states[0][0], p=states[0][1], OmegaGrid=grid, **okw)
         assert_parity(dflt[0], ref, RTOL, FLOOR, "tile-level far field, %s" % name)
+    # Lorentz driver (closed form with h = 0, no Weideman region) through the same blocks
+    lt = db.voigt_sum(T, p, w, uniform, flags=128 | K8 | 16, wing_abs=8.0).cpu().numpy()
+    ls = db.voigt_sum(T, p, w, uniform, flags=128 | K8 | 16 | 16384, wing_abs=8.0).cpu().numpy()
+    lx = db.voigt_sum(T, p, w, uniform, flags=128 | K8 | 16 | 4096, wing_abs=8.0).cpu().numpy()
+    assert not np.array_equal(lt, ls)
+    assert np.max(np.abs(lt - lx) / np.maximum(lx, 1e-300)) < 2e-13
+    _, ref = port.absorption_coefficient_lorentz(cols, T=states[0][0], p=states[0][1], OmegaGrid=uniform, OmegaWing=8.0)
+    assert_parity(lt[0], ref, RTOL, FLOOR, "tile-level far field, Lorentz")
     # narrow wings on the same grid: the statistic keeps the variant without tile-level blocks (identical bits)
     a = db.voigt_sum(T, p, w, uniform, flags=8 << 8, wing_abs=1.0, wing_hw=10.0).cpu().numpy()
     b = db.voigt_sum(T, p, w, uniform, flags=(8 << 8) | 16384, wing_abs=1.0, wing_hw=10.0).cpu().numpy()
