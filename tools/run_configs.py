@@ -82,7 +82,7 @@ def config3(n_atm=256):
     opts = dict(rt.options); rt.set_line_database(tabs, opts=opts)
     Ts, MF = syn.perturbed_atmospheres(2, n_atm)
     kw = dict(Zs=atm["Zs"], Ps=atm["Ps"], PLs=atm["PLs"], MFs_ID=atm["MFs_ID"], DVOUT=0.01, N_angle=30)
-    rt.compute_TUD_batch(700.0, 1500.0, Ts[:8], MF[:8], opts=dict(opts), ils="triangle", **kw)
+    rt.compute_TUD_batch(700.0, 1500.0, Ts, MF, opts=dict(opts), ils="triangle", **kw)     # warm-up at full size (workspaces)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     X, tau, lu, ld = rt.compute_TUD_batch(700.0, 1500.0, Ts, MF, opts=dict(opts), ils="triangle", **kw)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
