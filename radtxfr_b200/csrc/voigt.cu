@@ -101,7 +101,7 @@ struct ChunkCfg {
 #define RTX_SPLIT_MAX 8
 #endif
 #ifndef RTX_SPLIT_CTAS_PER_SM
-#define RTX_SPLIT_CTAS_PER_SM 4
+#define RTX_SPLIT_CTAS_PER_SM 3
 #endif
 #ifndef RTX_NARROW_MAX
 #define RTX_NARROW_MAX 128
@@ -1620,12 +1620,7 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
   double* st_wb = nullptr;
   rc = run_prep(h, P, st, &st_wb);
   if (rc) return rc;
-  // tile size: the largest K that still gives every SM a few CTAs
-  int K = 1;
-  for (int k : {8, 4, 2}) {
-    const int64_t tiles = (nx + (int64_t)k * NT - 1) / ((int64_t)k * NT);
-    if (tiles * n_states >= 4LL * h->sm_count) { K = k; break; }
-  }
+  int K = 8;                                                  // automatic: K = 8 / K = 4 per state, see below
   const int mode = (flags & RTX_VOIGT_FP32) ? 2 : ((flags & RTX_VOIGT_EXACT_RCP) ? 0 : 1);
   const bool ws = (flags & RTX_VOIGT_WARPSPEC) != 0;
   // speed dependence / extra broadening species: the extended instantiation (FP64, not warp-specialised)
@@ -1638,23 +1633,29 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
   bool with4 = false;                                         // K = 8 and K = 4 grids, chosen on the device
   if (forced == 1 || forced == 2 || forced == 4 || forced == 8) {
     K = forced;
-  } else if (K == 8) {
-    // narrow windows (coarse grids, low pressures): smaller slices turn partial visits into test-free ones and
-    // four CTAs per SM hide the per-visit latency.  The eval-weighted mean window decides -- on the device: every
-    // candidate grid is launched and the kernels of the variants not chosen return at once, so the call never waits
-    // for the GPU.
+  } else if ((int64_t)nx * n_states <= 65536 && !(flags & RTX_VOIGT_NOSPLIT)) {
+    // tiny problems (one cross-section on some ten thousand points): launch overhead counts, so one grid of 512-point
+    // tiles with the lines split (below) instead of the K = 8 / K = 4 pair
+    K = 2;
+  } else {
+    // 2048-point tiles where the windows are thousands of grid points wide; 1024-point tiles at four CTAs per SM where
+    // they are narrow (coarse grids, low pressures): smaller slices turn partial visits into test-free ones and hide the
+    // per-visit latency.  Each state's own wing decides -- on the device: every candidate grid is launched and the
+    // CTAs of the variants a state does not pick return at once, so the call never waits for the GPU.
     with4 = true;
   }
-  // Small problems (fewer tiles than the GPU holds CTAs at once): every CTA is bound by the latency of its own chunk
-  // loop, so the candidate lines of each (tile, state) are split over several CTAs and the partial spectra added
-  // afterwards.  The split depends on the tile size and the number of tiles only, not on the number of states, so that a
-  // batch and its single members keep identical bits.
-  if (!forced && K == 1 && !(flags & RTX_VOIGT_NOSPLIT)) K = 2;   // with the lines split, 512-point tiles repeat less per-line work
-  if (!with4 && K <= 2 && !(flags & RTX_VOIGT_NOSPLIT)) {
+  // Small launches (fewer (tile, state) pairs than the GPU holds CTAs -- a single cross-section): every CTA is bound by
+  // the latency of its own chunk loop, so the candidate lines of each (tile, state) are split over up to eight CTAs and
+  // the partial spectra added afterwards in part order (bit-reproducible; with a forced tile size there is no split, so
+  // that differently sharded grids keep identical bits).
+  if (!(flags & RTX_VOIGT_NOSPLIT) && !forced) {              // a forced tile size pins the summation order: no split
     const int64_t nt0 = (nx + (int64_t)K * NT - 1) / ((int64_t)K * NT);
-    if (nt0 < 3LL * h->sm_count) {
-      P.split = (int)std::min<int64_t>(RTX_SPLIT_MAX, ((int64_t)RTX_SPLIT_CTAS_PER_SM * h->sm_count + nt0 - 1) / nt0);
-      size_t need = (size_t)P.split * n_states * (size_t)nx;
+    if (nt0 * n_states < 4LL * h->sm_count) {
+      // K <= 2 (4 CTAs per SM, CTAs of a few microseconds): aim at 4 CTAs per SM; K >= 4: fill the slots of one wave
+      // but do not start a second one (391 tiles of 2048 points stay unsplit, 157 are split in two)
+      P.split = K <= 2 ? (int)std::min<int64_t>(RTX_SPLIT_MAX, (4LL * h->sm_count + nt0 - 1) / nt0)
+                       : (int)std::max<int64_t>(1, std::min<int64_t>(RTX_SPLIT_MAX, ((int64_t)RTX_SPLIT_CTAS_PER_SM * h->sm_count) / nt0));
+      size_t need = P.split > 1 ? (size_t)P.split * n_states * (size_t)nx : 0;
       if (need > ((size_t)32 << 20)) { P.split = 1; need = 0; }      // 256 MB of partial spectra: not a small problem
       if (need > h->part_cap) {
         if (h->d_part) cudaFree(h->d_part);
@@ -1665,7 +1666,7 @@ extern "C" int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, c
       P.part_out = P.split > 1 ? h->d_part : nullptr;
     }
   }
-  const bool with_tf = (K == 8) && tf_variant;
+  const bool with_tf = (K == 8) && tf_variant && P.split == 1;   // small launches: the tile-level variant would be one more idle grid
   P.sel = nullptr; P.sel_k8 = with4 ? 0 : 1; P.sel_tf = with_tf ? ((flags & RTX_VOIGT_TILEFAR) ? 2 : 1) : 0;
   P.dens = (h->lines.nu_max > h->lines.nu_min) ? (double)h->lines.n / (h->lines.nu_max - h->lines.nu_min) : 0.0;
   if (with4 || with_tf) {

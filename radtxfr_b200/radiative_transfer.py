@@ -319,6 +319,9 @@ def compute_TUD_batch(Xmin, Xmax, Ts, MFs_VAL, opts=options, atm_chunk=None, ils
         atm_chunk = max(1, min(max(n_atm, 1), int(4e9 // (8 * nL * nX))))   # <= 4 GB of optical depth at a time
     atm_chunk = min(int(atm_chunk), 32768)                                  # rtx_tud: n_atm <= 65535 per launch
     vs = _voigt_settings(opts)
+    # batches never split the lines of a tile over CTAs (engine.VOIGT_NOSPLIT): the kernel variant of a state then depends on
+    # the grid, the table and the state alone, so the result does not depend on how the batch is chunked or sharded
+    vs["flags"] |= engine.VOIGT_NOSPLIT
     outs = []
     band = None
     if ils is not None:

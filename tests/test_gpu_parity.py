@@ -314,6 +314,8 @@ def test_tud_sticky_options_and_compute_od(mods):
 
 
 def test_tud_batch_matches_single(mods):
+    import torch
+    torch_equal = torch.equal
     rt, syn = mods["rt"], mods["syn"]
     atm, tabs, opts, kw = _tud_setup(mods)
     Ts, MF = syn.perturbed_atmospheres(2, 5)
@@ -321,14 +323,28 @@ def test_tud_batch_matches_single(mods):
     X, tau, lu, ld = rt.compute_TUD_batch(700.0, 730.0, Ts, MF[:, :, :], opts=o, atm_chunk=2,
                                           **{k: v for k, v in kw.items() if k not in ("Ts", "MFs_VAL")})
     assert tau.shape == (5, X.size, 1, 1)
+    # automatic kernel variants follow the problem size (a single atmosphere on 600 points is a "tiny" launch whose
+    # lines are split over several CTAs, a chunk of two atmospheres is not): agreement to rounding ...
     for j in (0, 3, 4):
         Xs, t1, u1, d1 = rt.compute_TUD(700.0, 730.0, opts=dict(opts), **dict(kw, Ts=Ts[j], MFs_VAL=MF[j]))
+        for a, b in ((tau[j, :, 0, 0], t1), (lu[j, :, 0, 0], u1), (ld[j], d1)):
+            assert_parity(a.cpu().numpy(), b, 1e-10, 1e-13, "batch member %d vs single call" % j)
+    # a batch does not depend on how it is chunked
+    X2, tau2, lu2, ld2 = rt.compute_TUD_batch(700.0, 730.0, Ts, MF[:, :, :], opts=dict(opts), atm_chunk=5,
+                                              **{k: v for k, v in kw.items() if k not in ("Ts", "MFs_VAL")})
+    assert torch_equal(tau, tau2) and torch_equal(lu, lu2) and torch_equal(ld, ld2)
+    # ... and with the tile size pinned (which also switches the split off) bit for bit
+    o8 = dict(opts); o8["voigt"] = {"tile_k": 8}
+    X, tau, lu, ld = rt.compute_TUD_batch(700.0, 730.0, Ts, MF[:, :, :], opts=dict(o8), atm_chunk=2,
+                                          **{k: v for k, v in kw.items() if k not in ("Ts", "MFs_VAL")})
+    for j in (0, 3, 4):
+        Xs, t1, u1, d1 = rt.compute_TUD(700.0, 730.0, opts=dict(o8), **dict(kw, Ts=Ts[j], MFs_VAL=MF[j]))
         assert np.array_equal(tau[j, :, 0, 0].cpu().numpy(), t1)
         assert np.array_equal(lu[j, :, 0, 0].cpu().numpy(), u1)
         assert np.array_equal(ld[j].cpu().numpy(), d1)
-    Xb, tb, ub, db_ = rt.compute_TUD_batch(700.0, 1400.0, Ts[:2], MF[:2], opts=dict(opts), ils="triangle",
+    Xb, tb, ub, db_ = rt.compute_TUD_batch(700.0, 1400.0, Ts[:2], MF[:2], opts=dict(o8), ils="triangle",
                                            **dict({k: v for k, v in kw.items() if k not in ("Ts", "MFs_VAL")}, DVOUT=0.25))
-    Xs, t1, u1, d1 = rt.compute_TUD(700.0, 1400.0, opts=dict(opts), **dict(kw, Ts=Ts[1], MFs_VAL=MF[1], DVOUT=0.25))
+    Xs, t1, u1, d1 = rt.compute_TUD(700.0, 1400.0, opts=dict(o8), **dict(kw, Ts=Ts[1], MFs_VAL=MF[1], DVOUT=0.25))
     xo, tt = rt.ILS_MAKO(Xs, t1)
     assert np.array_equal(xo, Xb) and np.array_equal(tb[1, :, 0, 0].cpu().numpy(), tt)
 
