@@ -138,8 +138,10 @@ int rtx_tape3_read(const char* path, double vmin, double vmax, int64_t capacity,
 #define RTX_VOIGT_TILEFAR 32768  /* use the tile-level far-field blocks wherever a line qualifies (default: only for states
                                  * whose typical wing is >= 4000 grid points and whose tiles see >= 600 such lines -- below
                                  * that the kernel variant without them is faster) */
-#define RTX_VOIGT_NOSPLIT 65536  /* small problems (fewer (tile, state) pairs than three per SM): do not split the lines of a
-                                 * tile over several CTAs (default: up to 8 CTAs per tile, partial spectra added in order) */
+#define RTX_VOIGT_NOSPLIT 65536  /* small launches (fewer (tile, state) pairs than four per SM -- a single cross-section): do
+                                 * not split the candidate lines of a tile over several CTAs (default: up to 8 CTAs per
+                                 * tile, partial spectra added in part order; never with a forced tile size).  Batch
+                                 * callers set it so that results do not depend on how the batch is chunked. */
 #define RTX_VOIGT_SDVOIGT 8192  /* absorptionCoefficient_SDVoigt (misc/hapi.py:10657-10905): lines whose Gamma2 = sum_d x_d
                                  * SD_d p gamma_d is non-zero take the quadratic speed-dependent profile (pcqsdhc PART2-4,
                                  * misc/hapi.py:9923-10020); the rest is the Voigt driver */
@@ -147,8 +149,9 @@ int rtx_tape3_read(const char* path, double vmin, double vmax, int64_t capacity,
                                 * The automatic choice between K = 8 and K = 4, and between the K = 8 kernel with and
                                 * without tile-level far-field blocks, is made on the device, per state, from the state's
                                 * wing in grid points (the grids of all candidates are launched; a CTA of a variant its
-                                * state does not pick retires at once), so the call never synchronises;
-                                * force K to pin the summation order (e.g. for bit-identical sharded results). */
+                                * state does not pick retires at once), so the call never synchronises; problems of at
+                                * most 65 536 points x states take one grid of 512-point tiles instead.
+                                * Force K to pin the summation order (e.g. for bit-identical sharded results). */
 int rtx_voigt_sum(rtx_handle* h, int n_states, const double* T_dev, const double* p_dev,
                   const double* weight_dev, double x_air, double x_self, double wing_abs, double wing_hw,
                   double s_threshold, const double* grid_dev, int64_t nx, double* out_dev, int flags,
