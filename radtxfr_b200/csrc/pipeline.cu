@@ -124,8 +124,9 @@ extern "C" int rtx_tud_from_lines(rtx_handle* h, int n_atm, int n_layers, const 
     if ((rc = rtx_layer_weights(h, ns, T_dev + o, P_pa_dev + o, PL_km_dev + o, mf_ppmv_dev + o * n_mol, n_mol, mf_id_host,
                                 p_atm, wgt, stream)))
       return rc;
+    // a batch never splits the lines of a tile over CTAs: the result must not depend on the chunking below
     if ((rc = rtx_voigt_sum(h, ns, T_dev + o, p_atm, wgt, x_air, x_self, wing_abs, wing_hw, s_threshold, grid_dev, nx, od,
-                            voigt_flags, stream)))
+                            voigt_flags | RTX_VOIGT_NOSPLIT, stream)))
       return rc;
     if ((rc = rtx_tud(h, na, n_layers, od, T_dev + o, grid_dev, nx, Z_host, alt_host, n_alt, mu_host, n_mu, n_angle,
                       return_od, tau_dev + (int64_t)a0 * out_stride, lu_dev + (int64_t)a0 * out_stride,
