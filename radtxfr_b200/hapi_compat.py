@@ -83,6 +83,9 @@ def storeTable(name, cols):
     invalidate(name)
 
 
+_grid_cache = {}         # device -> (host copy of the last large axis, its device copy)
+
+
 def invalidate(name=None):
     """Drop the device copies of table `name` (all tables when None): the next call uploads again.  Needed only after
     an in-place edit of column values that engine.table_fingerprint cannot see."""
@@ -157,6 +160,7 @@ def absorptionCoefficient_Voigt(Components=None, SourceTables=None, partitionFun
     if OmegaStep_ > 0.1: warn('Big wavenumber step: possible accuracy decline')   # misc/hapi.py:10974
 
     as_tensor = isinstance(OmegaGrid, torch.Tensor)
+    grid_dev = None
     if OmegaGrid is not None:
         if as_tensor:
             Omegas = torch.sort(OmegaGrid.to(device=db.device, dtype=torch.float64).reshape(-1))[0]
@@ -168,6 +172,15 @@ def absorptionCoefficient_Voigt(Components=None, SourceTables=None, partitionFun
         if OmegaRange is None:
             OmegaRange = (db.nu_min, db.nu_max)                                   # misc/hapi.py:10252-10263
         Omegas = _hapi_grid(OmegaRange, OmegaStep_)
+    if not as_tensor and Omegas.size >= (1 << 16):
+        # loops over (T, p) on one large axis (misc/RT_gen_AbsXS_files.py:87-93): the device copy of the axis is kept
+        # and reused while the host values are unchanged (compared in full: 20 MB/ms, a tenth of the upload)
+        hit = _grid_cache.get(str(db.device))
+        if hit is not None and hit[0].size == Omegas.size and np.array_equal(hit[0], Omegas):
+            grid_dev = hit[1]
+        else:
+            grid_dev = engine.to_device(Omegas, db.device)
+            _grid_cache[str(db.device)] = (Omegas.copy(), grid_dev)
 
     T = float(Environment['T'])
     p = float(Environment['p'])
@@ -197,12 +210,15 @@ def absorptionCoefficient_Voigt(Components=None, SourceTables=None, partitionFun
     if db.n_lines:
         db.check_temperatures([T])
         db.check_tips(w_iso != 0.0)
-    xs = db.voigt_sum(np.array([T]), np.array([p]), w_iso[None, :], Omegas, x_air=x_air, x_self=x_self,
+    xs = db.voigt_sum(np.array([T]), np.array([p]), w_iso[None, :], Omegas if grid_dev is None else grid_dev, x_air=x_air, x_self=x_self,
                       wing_abs=float(OmegaWing), wing_hw=float(OmegaWingHW),
                       s_threshold=float(IntensityThreshold), x_extra=x_extra,
                       flags=engine.PRECISION_FLAGS[VARIABLES["precision"]] | int(_profile_flags))[0]
     if as_tensor:
         return Omegas, xs
+    if xs.numel() >= (1 << 18):
+        from . import radiative_transfer as _rt          # pinned staging buffer + threaded copy-out (lazy: it imports this module)
+        return Omegas, _rt._to_host(xs)[0]
     return Omegas, xs.cpu().numpy()
 
 
