@@ -27,6 +27,13 @@
 //     lane-per-point by the warp that owns that part of the tile (shared-memory accumulator, no atomics): wings
 //     record by record, two rows at a time; cores flattened across record boundaries, two steps at a time, so the
 //     24-term rational series never diverges against the cheap branch inside a warp.
+//   * far field: on a slice (32*K points) or a whole tile that a window covers from >= 0.375 block widths away the
+//     closed form is summed at the block's 32 Chebyshev nodes only and interpolated once per (tile, state) -- K times
+//     (slice) or 8 K times (tile) fewer evaluations; the tile level lives in its own instantiation (TFP).  The far wing of a
+//     speed-dependent line (difference of two asymptotes) goes the same way.
+//   * which instantiation a state runs in (K = 8, K = 8 with tile-level blocks, K = 4) is decided on the device from
+//     the state's own wing: the grids of all candidates are launched and the CTAs of the others return at once.  Small
+//     launches split the candidate lines of a tile over several CTAs (partial spectra added in part order).
 //   * flags select the Lorentz and Doppler drivers of hapi (same skeleton, different wing rule and profile).
 //   * FP64 throughout (an optional FP32 mode exists for the asymptote branch); summation order is fixed, so
 //     results are bit-reproducible run to run and, with the tile size pinned, independent of how the grid is
