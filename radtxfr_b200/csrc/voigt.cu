@@ -7,7 +7,7 @@
 // Design (B200-first, not a translation):
 //   * one CTA (256 threads) per (wavenumber tile, state): 2048-point tiles at 80 registers and 72 KB of shared memory
 //     (three CTAs per SM) when the windows are thousands of grid points wide, 1024-point tiles at 64 registers
-//     (four CTAs per SM) when they are a few hundred (window_stats_kernel decides).  The tile of the spectral grid is
+//     (four CTAs per SM) when they are a few hundred (each state by its own wing, on the device).  The tile of the spectral grid is
 //     staged in shared memory by one TMA bulk copy (cp.async.bulk + mbarrier) and kept there: the prologue searches
 //     it with exact comparisons, so window membership is decided on the same doubles the reference bisects, and the
 //     evaluation passes read it back.
