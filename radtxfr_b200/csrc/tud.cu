@@ -13,8 +13,14 @@
 
 namespace {
 
+#ifndef RTX_TUD_ANGLE_BLOCK
+#define RTX_TUD_ANGLE_BLOCK 10
+#endif
+#ifndef RTX_TUD_MINBLOCKS
+#define RTX_TUD_MINBLOCKS 4
+#endif
 constexpr int TUD_THREADS = 128;
-constexpr int ANGLE_BLOCK = 10;
+constexpr int ANGLE_BLOCK = RTX_TUD_ANGLE_BLOCK;
 struct TudParams {
   int n_atm, n_layers, n_alt, n_mu, n_angle, n_down, return_od, max_cnt;
   int64_t nx;
@@ -28,7 +34,7 @@ struct TudParams {
   double wsum;                      // sum of cos(th)*sin(th) over ALL angles
 };
 
-__global__ void __launch_bounds__(TUD_THREADS, 4) tud_kernel(const TudParams P) {
+__global__ void __launch_bounds__(TUD_THREADS, RTX_TUD_MINBLOCKS) tud_kernel(const TudParams P) {
   __shared__ double s_exp2[256];                      // 2^(j/256), correctly rounded by exp2()
   __shared__ double s_invT[RTX_MAX_LAYERS];           // 1/T of this block's atmosphere
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_exp2[i] = exp2((double)i * 0.00390625);
