@@ -850,6 +850,31 @@ def test_voigt_tile_level_far_field(mods):
     assert_parity(res["default"], ref, RTOL, FLOOR, "SDVoigt far wing at the nodes")
 
 
+def test_wide_wings_against_reference_golden(mods):
+    """Tile- and slice-level far-field blocks against outputs of the unmodified reference (tests/golden/widewing.npz):
+    absorptionCoefficient_Voigt with OmegaWing = 8 cm^-1 and WavenumberWingHW = 350, absorptionCoefficient_SDVoigt with
+    WavenumberWingHW = 350 (speed-dependent far wings at the nodes) -- through the shim, automatic choice, and with the
+    tile-level variant forced (the 300-line table is too sparse for the automatic choice to take it)."""
+    import make_golden as mg
+    hapi = mods["hapi"]
+    g = golden("widewing.npz")
+    hapi.storeTable("wide", mg.widewing_table())
+    hapi.storeTable("wide_sd", mg.sdv_table())
+    grid = np.linspace(*mg.WIDE_GRID)
+    T, p, dil = mg.WIDE_SD_CASE
+    for fl in (0, (8 << 8) | 32768, (8 << 8) | 16384):
+        _, xs = hapi.absorptionCoefficient_Voigt(SourceTables="wide", Environment={"T": 296.0, "p": 1.0}, OmegaGrid=grid,
+                                                 OmegaWing=8.0, _profile_flags=fl)
+        assert_parity(xs, g["voigt_w8"], RTOL, FLOOR, "OmegaWing=8, flags %d" % fl)
+        _, xs = hapi.absorptionCoefficient_Voigt(SourceTables="wide", Environment={"T": 250.0, "p": 0.3}, OmegaGrid=grid,
+                                                 WavenumberWingHW=350.0, _profile_flags=fl)
+        assert_parity(xs, g["voigt_hw350"], RTOL, FLOOR, "WavenumberWingHW=350, flags %d" % fl)
+        _, xs = hapi.absorptionCoefficient_SDVoigt(SourceTables="wide_sd", Environment={"T": T, "p": p},
+                                                   OmegaGrid=np.linspace(*mg.WIDE_SD_GRID), Diluent=dil,
+                                                   WavenumberWingHW=350.0, _profile_flags=fl)
+        assert_parity(xs, g["sd_hw350"], RTOL, FLOOR, "SDVoigt WavenumberWingHW=350, flags %d" % fl)
+
+
 def test_voigt_tile_level_automatic_on_dense_table(mods):
     """The variant with tile-level blocks is picked on the device where it pays: config 2's dense table (262 lines per
     cm^-1) with 6 cm^-1 wings takes it by itself (different bits from RTX_VOIGT_NOTILEFAR), the default 50-half-width

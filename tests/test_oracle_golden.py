@@ -219,3 +219,20 @@ def test_sdvoigt_and_diluents_port():
     ref = s * (1j / z * 0.564189583547756)
     wr, wi = port.cpf3(x, y)
     assert np.allclose(wr, ref.real, rtol=1e-14) and np.allclose(wi, ref.imag, rtol=1e-14)
+
+
+def test_wide_wings_port():
+    """The port on windows of 16 000 grid points and more (OmegaWing = 8 cm^-1, the reference script's
+    WavenumberWingHW = 350) against the reference's outputs (tests/golden/widewing.npz)."""
+    import make_golden as mg
+    g = golden("widewing.npz")
+    cols = mg.widewing_table()
+    grid = np.linspace(*mg.WIDE_GRID)
+    _, xs = port.absorption_coefficient_voigt(cols, T=296.0, p=1.0, OmegaGrid=grid, OmegaWing=8.0)
+    assert_parity(xs, g["voigt_w8"], what="Voigt, OmegaWing=8", **TIGHT)
+    _, xs = port.absorption_coefficient_voigt(cols, T=250.0, p=0.3, OmegaGrid=grid, OmegaWingHW=350.0)
+    assert_parity(xs, g["voigt_hw350"], what="Voigt, WavenumberWingHW=350", **TIGHT)
+    T, p, dil = mg.WIDE_SD_CASE
+    _, xs = port.absorption_coefficient_sdvoigt(mg.sdv_table(), T=T, p=p, OmegaGrid=np.linspace(*mg.WIDE_SD_GRID), Diluent=dil,
+                                                OmegaWingHW=350.0)
+    assert_parity(xs, g["sd_hw350"], rtol=1e-10, floor=1e-15, what="SDVoigt, WavenumberWingHW=350")

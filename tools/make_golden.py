@@ -271,6 +271,32 @@ def g_sdvoigt():
          "PART2-4, :9923-10020); :10906-11141 with gamma_h2 / gamma_he diluents", **out)
 
 
+def widewing_table():
+    cols = syn.synthetic_lines(61, 300, 960.0, 1040.0, 1)
+    cols["sw"][::41] *= 1e6
+    return cols
+
+
+WIDE_GRID = (990.0, 1010.0, 40001)            # 0.0005 cm^-1: 19 full 2048-point tiles and a partial one
+WIDE_SD_GRID = (1240.0, 1260.0, 40001)
+WIDE_SD_CASE = (280.0, 0.8, {"air": 0.7, "h2": 0.3})
+
+
+def g_widewing():
+    """Wings of thousands of grid points -- the regime of the tile-level far-field blocks: absorptionCoefficient_Voigt with
+    OmegaWing = 8 cm^-1 and with the reference script's WavenumberWingHW = 350 (misc/RT_gen_AbsXS_files.py:18,90), and
+    absorptionCoefficient_SDVoigt with that wing on the speed-dependent table."""
+    cols = widewing_table()
+    grid = np.linspace(*WIDE_GRID)
+    out = {}
+    _, out["voigt_w8"] = R.ref_xsect(cols, 296.0, 1.0, grid, OmegaWing=8.0)
+    _, out["voigt_hw350"] = R.ref_xsect(cols, 250.0, 0.3, grid, WavenumberWingHW=350.0)
+    T, p, dil = WIDE_SD_CASE
+    _, out["sd_hw350"] = R.ref_xsect_sd(sdv_table(), T, p, np.linspace(*WIDE_SD_GRID), Diluent=dil, WavenumberWingHW=350.0)
+    save("widewing.npz", source="misc/hapi.py:10906-11141 (OmegaWing=8, WavenumberWingHW=350) and :10657-10905 (SDVoigt, "
+         "WavenumberWingHW=350) on fine grids: windows of 16 000 grid points and more", **out)
+
+
 def g_lut():
     """SDVoigt on a table without SD columns (the reference's own call convention, misc/RT_gen_AbsXS_files.py:90)
     and the AFIT_XS writer, whose source is lifted out of the script with ast (the script itself fetches HITRAN
@@ -387,6 +413,6 @@ def g_mbi():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi", "lorentz", "doppler", "spectra", "sensor_f32", "reduce2", "sdvoigt"]
+    which = sys.argv[1:] or ["wofz", "profile", "tips", "xsect", "tud", "sensor", "bt", "reduce", "lut", "optcols", "mbi", "lorentz", "doppler", "spectra", "sensor_f32", "reduce2", "sdvoigt", "widewing"]
     for w in which:
         globals()["g_" + w]()
