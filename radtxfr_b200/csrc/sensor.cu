@@ -506,7 +506,13 @@ __global__ void apparent_kernel(const double* __restrict__ X, int64_t nx, const 
 // factors c1 X^3 and c2 X in registers; the per-pixel 1/T is formed once per pixel (not per output) into shared
 // memory; exp is the table-driven one of the layer integration (no libm call, no FP64 divide per output), and the
 // 64-bit div/mod of a flat (pixel, band) index is gone.  Stores are 256 contiguous bytes per warp.
-constexpr int HSI_THREADS = 128, HSI_PB = 64, HSI_MAXMIX = 4;
+#ifndef RTX_HSI_UNROLL
+#define RTX_HSI_UNROLL 4
+#endif
+#ifndef RTX_HSI_PB
+#define RTX_HSI_PB 64
+#endif
+constexpr int HSI_THREADS = 128, HSI_PB = RTX_HSI_PB, HSI_MAXMIX = 4, HSI_UNROLL = RTX_HSI_UNROLL;
 // NMIX > 0: materials per pixel known at compile time (per-pixel offsets and fractions staged in shared memory, 32-bit
 // offsets); NMIX = 0: any n_mix, read from global memory.
 template <typename OutT, int NMIX>
@@ -542,7 +548,7 @@ __global__ void __launch_bounds__(HSI_THREADS) hsi_kernel(const double* __restri
       const double* __restrict__ la_x = la + x;
       const double* __restrict__ ld_x = ld + x;
       OutT* __restrict__ out = L + k0 * nx + x;
-#pragma unroll 4
+#pragma unroll(HSI_UNROLL)
       for (int p = 0; p < np; ++p) {
         double em = 0.0;
         if (NMIX > 0) {
